@@ -1,0 +1,128 @@
+/* b200vad.h -- C ABI of the B200-native VAD inference hot path.
+ *
+ * The reference (arnavsshah/universal-voice-activity-detection) is pure Python and has no
+ * FFI of its own: its "operator interface" for this path is the set of library calls listed
+ * below.  Each entry point names the reference call site it replaces (paths relative to the
+ * reference root).  Conventions for every function:
+ *   - plain pointers and sizes only; device pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); nothing synchronises
+ *     and nothing allocates unless documented; the caller owns every buffer;
+ *   - returns 0 on success, <0 on error (B200VAD_E*); b200vad_last_error() gives the message
+ *     of the calling thread's last failure;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef B200VAD_H
+#define B200VAD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VAD_OK 0
+#define B200VAD_EINVAL (-1)
+#define B200VAD_ECUDA (-2)
+#define B200VAD_ENOMEM (-3)
+#define B200VAD_ESTATE (-4)
+
+#if defined(__GNUC__)
+#define B200VAD_API __attribute__((visibility("default")))
+#else
+#define B200VAD_API
+#endif
+
+#define B200VAD_ABI_VERSION 1
+#define B200VAD_HIDDEN 128      /* LSTM hidden size (PyanNet2.py:60-66 LSTM_DEFAULTS) */
+#define B200VAD_NUM_MEL 80      /* FbankConfig.num_filters */
+
+B200VAD_API int b200vad_abi_version(void);
+B200VAD_API const char* b200vad_last_error(void);
+
+/* Build the per-device constant tables (povey window, FFT twiddles, Kaldi mel triangles).
+ * Allocates a few KB of device memory once per device.  Must precede any fbank call. */
+B200VAD_API int b200vad_init(int device);
+
+/* ---- a1: lhotse Fbank(FbankConfig(sampling_rate=16000)).extract / extract_batch
+ * (src/utils/helper.py:120-130, src/datasets/ami/utils.py:152-163 and siblings).
+ * T = (N + 80) / 160 frames per row. */
+B200VAD_API int64_t b200vad_fbank_num_frames(int64_t num_samples);
+/* wav: (B, N) f32 rows `wav_stride` elements apart; lens: optional (B) i32 valid samples per
+ * row (NULL = N); feats: (B, T, 80) f32, rows shorter than T are padded with lhotse's
+ * LOG_EPSILON; row_sum_ws: (B) f64 scratch. */
+B200VAD_API int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride,
+                      float* feats, int64_t T, double* row_sum_ws, void* stream);
+
+/* ---- a2: PyanNet2.forward (src/models/segmentation/PyanNet2.py:154-187): nn.LSTM stack
+ * (4 x BiLSTM(128) by default) + Linear/LeakyReLU x2 + Linear(1) + Sigmoid.
+ * Weights are packed once into an opaque device blob in kernel layout. */
+B200VAD_API size_t b200vad_model_packed_bytes(int D, int num_layers);
+/* one call per (layer, direction); w_ih (512, D_l), w_hh (512, 128), b_ih/b_hh (512): f32 device */
+B200VAD_API int b200vad_model_pack_lstm(void* packed, int D, int num_layers, int layer, int direction, const float* w_ih,
+                            const float* w_hh, const float* b_ih, const float* b_hh, void* stream);
+/* linear.0 (128,256)+(128), linear.1 (128,128)+(128), classifier (1,128)+(1): f32 device */
+B200VAD_API int b200vad_model_pack_head(void* packed, int D, int num_layers, const float* w1, const float* b1, const float* w2,
+                            const float* b2, const float* wc, const float* bc, void* stream);
+B200VAD_API size_t b200vad_model_workspace_bytes(int B, int64_t T);
+/* x: (B, T, D) f32 -> prob: (B, T) f32 in (0,1).  The batch is processed in chunks that fit
+ * `ws_bytes` (>= b200vad_model_workspace_bytes(1, T)). */
+B200VAD_API int b200vad_model_forward_f32(const void* packed, int D, int num_layers, const float* x, int B, int64_t T, float* prob,
+                              void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a3/a4: PyanNet.forward / SincNet.forward (src/models/segmentation/PyanNet.py:164-197,
+ * src/models/blocks/sincnet.py:73-103).  a5: get_num_frames (src/utils/receptive_field.py:165-193). */
+B200VAD_API int64_t b200vad_sincnet_num_frames(int64_t num_samples);
+B200VAD_API size_t b200vad_sincnet_packed_bytes(void);
+/* wav_norm (1)+(1); low_hz_, band_hz_ (40); window_ (125); n_ (125); conv1 (60,80,5)+(60);
+ * conv2 (60,60,5)+(60); norm{0,1,2} weight/bias (80),(60),(60): f32 device */
+B200VAD_API int b200vad_sincnet_pack(void* packed, const float* wav_norm_w, const float* wav_norm_b, const float* low_hz,
+                         const float* band_hz, const float* window, const float* n, const float* conv1_w,
+                         const float* conv1_b, const float* conv2_w, const float* conv2_b, const float* norm0_w,
+                         const float* norm0_b, const float* norm1_w, const float* norm1_b, const float* norm2_w,
+                         const float* norm2_b, void* stream);
+B200VAD_API size_t b200vad_sincnet_workspace_bytes(int B, int64_t N);
+/* wav: (B, N) f32 -> out: (B, Ts, 60) f32 (time-major, i.e. already "b t f" of PyanNet.py:178) */
+B200VAD_API int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int64_t N, int64_t wav_stride, float* out,
+                                void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a6/a7: median_filter (src/utils/helper.py:66-97) as called by VadModel.predict_step
+ * (src/engines/vad_engine.py:204-211): out[b,t] = median over a zero-padded window of `kernel`
+ * frames of (prob < thr ? 0 : 1).  elem_bytes = 1 (uint8) or 8 (int64, the reference's dtype).
+ * near_count (optional, i32, must be zeroed by the caller): number of frames with
+ * |prob - thr| <= near_tol, the "near-threshold" set parity reports separately. */
+B200VAD_API int b200vad_median_window(double speech_window, double window);
+B200VAD_API int b200vad_threshold_median(const float* prob, int B, int64_t T, float thr, int kernel, void* out, int elem_bytes,
+                             int32_t* near_count, float near_tol, void* stream);
+
+/* ---- a8/a9: run-length segment extraction (src/scripts/predict.py:447-458, 472-490).
+ * dec: flat uint8 decisions; stream r = dec[offsets[r], offsets[r+1]) (offsets: (R+1) i64,
+ * NULL = R rows of T frames).  Emits (r, first_frame, last_frame_inclusive) i32 triples for
+ * every run of >= min_run frames (2 = the reference's `end - start > 0`), ordered by (r, first).
+ * counts: (R) i32 out; seg_off: (R+1) i64 out (seg_off[R] = total); seg: (cap, 3) i32. */
+B200VAD_API int b200vad_segments(const uint8_t* dec, const int64_t* offsets, int R, int64_t T, int min_run, int32_t* counts,
+                     int64_t* seg_off, int32_t* seg, int64_t cap, void* stream);
+
+/* ---- whole path on device buffers: fbank -> PyanNet2 -> threshold/median -> segments */
+B200VAD_API size_t b200vad_pipeline_workspace_bytes(int B, int64_t N);
+B200VAD_API int b200vad_pipeline_fbank_f32(const void* packed, int num_layers, const float* wav, const int32_t* lens, int B,
+                               int64_t N, int64_t wav_stride, float thr, int kernel, float* prob /* (B,T) */,
+                               uint8_t* dec /* (B,T) */, int32_t* counts, int64_t* seg_off, int32_t* seg, int64_t cap,
+                               void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- host-buffer session: the same path with HOST waveforms and HOST results.  The session
+ * owns pinned staging buffers, device buffers and two CUDA streams, and overlaps the H2D copy
+ * of chunk i+1 with the compute of chunk i.  This is the call `e2e` times in bench.py. */
+typedef struct b200vad_session b200vad_session;
+B200VAD_API int b200vad_session_create(int device, const void* packed_device, int num_layers, int max_chunk_rows, int64_t N,
+                           b200vad_session** out);
+/* wav_host: (B, N) f32; outputs on host: dec (B,T) u8 (optional), prob (B,T) f32 (optional),
+ * seg (cap,3) i32, *nseg total segments.  Blocks until results are on the host. */
+B200VAD_API int b200vad_session_run_host(b200vad_session* s, const float* wav_host, int B, float thr, int kernel, uint8_t* dec_host,
+                             float* prob_host, int32_t* seg_host, int64_t cap, int64_t* nseg);
+B200VAD_API void b200vad_session_destroy(b200vad_session* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VAD_H */

@@ -1,0 +1,253 @@
+"""torch.library custom ops over the C ABI (CUDA implementations only -- no CPU kernels).
+
+  b200vad::fbank(wav, lens?)                        -> (B, T, 80) f32      [a1]
+  b200vad::lstm_head(x, packed, num_layers)         -> (B, T) f32 prob     [a2]
+  b200vad::sincnet(wav, packed)                     -> (B, Ts, 60) f32     [a3/a4]
+  b200vad::threshold_median(prob, thr, kernel, i64) -> (B, T) u8 | i64     [a6/a7]
+  b200vad::segments(dec, offsets?, min_run)         -> (S, 3) i32, (R) i32 [a8/a9]
+  b200vad::vad_pipeline(wav, lens?, packed, L, thr, kernel) -> prob, dec, seg, counts
+
+Each op enqueues on ``torch.cuda.current_stream()`` and never synchronises, except
+``segments`` / ``vad_pipeline`` which read one int64 (the segment total) to size their output.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_MAX_WS_BYTES = 12 << 30     # cap for per-call workspaces; larger batches are chunked inside the C call
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _prep(t: torch.Tensor, dtype, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.B200VadError(f"{what} must be a CUDA tensor (there is no CPU implementation of this path)")
+    if t.dtype != dtype:
+        raise _lib.B200VadError(f"{what} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ensure(device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    _lib.init(idx)
+    return idx
+
+
+# ------------------------------------------------------------------ fbank
+@torch.library.custom_op("b200vad::fbank", mutates_args=(), device_types="cuda")
+def fbank(wav: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    wav = _prep(wav, torch.float32, "wav")
+    if wav.dim() != 2:
+        raise _lib.B200VadError("wav must be (B, N)")
+    B, N = wav.shape
+    L = _lib.lib()
+    T = L.b200vad_fbank_num_frames(N)
+    feats = torch.empty((B, T, 80), dtype=torch.float32, device=wav.device)
+    if B == 0 or T == 0:
+        return feats
+    with torch.cuda.device(wav.device):
+        _ensure(wav.device)
+        lens_ptr = None
+        if lens is not None:
+            lens = _prep(lens.to(torch.int32), torch.int32, "lens")
+            lens_ptr = lens.data_ptr()
+        sums = torch.empty(B, dtype=torch.float64, device=wav.device)
+        for b0 in range(0, B, 32768):
+            b1 = min(B, b0 + 32768)
+            _lib.check(L.b200vad_fbank_f32(wav[b0:b1].data_ptr(), None if lens_ptr is None else lens[b0:b1].data_ptr(),
+                                           b1 - b0, N, wav.stride(0), feats[b0:b1].data_ptr(), T,
+                                           sums[b0:b1].data_ptr(), _stream_ptr(wav.device)), "b200vad_fbank_f32")
+    return feats
+
+
+@fbank.register_fake
+def _(wav, lens=None):
+    B, N = wav.shape
+    return wav.new_empty((B, (N + 80) // 160, 80))
+
+
+# ------------------------------------------------------------------ LSTM stack + head
+@torch.library.custom_op("b200vad::lstm_head", mutates_args=(), device_types="cuda")
+def lstm_head(x: torch.Tensor, packed: torch.Tensor, num_layers: int) -> torch.Tensor:
+    x = _prep(x, torch.float32, "x")
+    if x.dim() != 3:
+        raise _lib.B200VadError("x must be (B, T, D)")
+    B, T, D = x.shape
+    L = _lib.lib()
+    if packed.numel() != L.b200vad_model_packed_bytes(D, num_layers):
+        raise _lib.B200VadError("packed blob does not match (D, num_layers)")
+    prob = torch.empty((B, T), dtype=torch.float32, device=x.device)
+    if B == 0 or T == 0:
+        return prob
+    with torch.cuda.device(x.device):
+        _ensure(x.device)
+        need = L.b200vad_model_workspace_bytes(B, T)
+        ws = _ws(min(need, max(_MAX_WS_BYTES, L.b200vad_model_workspace_bytes(1, T))), x.device)
+        _lib.check(L.b200vad_model_forward_f32(packed.data_ptr(), D, num_layers, x.data_ptr(), B, T, prob.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream_ptr(x.device)),
+                   "b200vad_model_forward_f32")
+    return prob
+
+
+@lstm_head.register_fake
+def _(x, packed, num_layers):
+    return x.new_empty((x.shape[0], x.shape[1]))
+
+
+# ------------------------------------------------------------------ SincNet
+@torch.library.custom_op("b200vad::sincnet", mutates_args=(), device_types="cuda")
+def sincnet(wav: torch.Tensor, packed: torch.Tensor) -> torch.Tensor:
+    wav = _prep(wav, torch.float32, "wav")
+    if wav.dim() != 2:
+        raise _lib.B200VadError("wav must be (B, N)")
+    B, N = wav.shape
+    L = _lib.lib()
+    Ts = L.b200vad_sincnet_num_frames(N)
+    if Ts < 1:
+        raise _lib.B200VadError("waveform shorter than the SincNet receptive field (991 samples)")
+    out = torch.empty((B, Ts, 60), dtype=torch.float32, device=wav.device)
+    if B == 0:
+        return out
+    with torch.cuda.device(wav.device):
+        _ensure(wav.device)
+        need = L.b200vad_sincnet_workspace_bytes(B, N)
+        ws = _ws(min(need, max(_MAX_WS_BYTES, L.b200vad_sincnet_workspace_bytes(1, N))), wav.device)
+        _lib.check(L.b200vad_sincnet_forward_f32(packed.data_ptr(), wav.data_ptr(), B, N, wav.stride(0), out.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr(wav.device)),
+                   "b200vad_sincnet_forward_f32")
+    return out
+
+
+@sincnet.register_fake
+def _(wav, packed):
+    from .host import get_num_frames
+    return wav.new_empty((wav.shape[0], get_num_frames(wav.shape[1]), 60))
+
+
+# ------------------------------------------------------------------ threshold + median
+@torch.library.custom_op("b200vad::threshold_median", mutates_args=(), device_types="cuda")
+def threshold_median(prob: torch.Tensor, thr: float, kernel: int, as_int64: bool) -> torch.Tensor:
+    prob = _prep(prob, torch.float32, "prob")
+    if prob.dim() != 2:
+        raise _lib.B200VadError("prob must be (B, T)")
+    B, T = prob.shape
+    out = torch.empty((B, T), dtype=torch.int64 if as_int64 else torch.uint8, device=prob.device)
+    if B == 0 or T == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(prob.device):
+        for b0 in range(0, B, 32768):
+            b1 = min(B, b0 + 32768)
+            _lib.check(L.b200vad_threshold_median(prob[b0:b1].data_ptr(), b1 - b0, T, float(thr), int(kernel),
+                                                  out[b0:b1].data_ptr(), 8 if as_int64 else 1, None, 0.0,
+                                                  _stream_ptr(prob.device)), "b200vad_threshold_median")
+    return out
+
+
+@threshold_median.register_fake
+def _(prob, thr, kernel, as_int64):
+    return prob.new_empty(prob.shape, dtype=torch.int64 if as_int64 else torch.uint8)
+
+
+def near_threshold_count(prob: torch.Tensor, thr: float, tol: float) -> int:
+    """Number of frames with |p - thr| <= tol (reported separately by the parity tests)."""
+    return int(((prob - thr).abs() <= tol).sum().item())
+
+
+# ------------------------------------------------------------------ segments
+@torch.library.custom_op("b200vad::segments", mutates_args=(), device_types="cuda")
+def segments(dec: torch.Tensor, offsets: Optional[torch.Tensor] = None, min_run: int = 2) -> Tuple[torch.Tensor, torch.Tensor]:
+    dec = _prep(dec, torch.uint8, "dec")
+    L = _lib.lib()
+    dev = dec.device
+    if offsets is None:
+        if dec.dim() != 2:
+            raise _lib.B200VadError("dec must be (R, T) when offsets is None")
+        R, T = dec.shape
+        total_frames = R * T
+        off_ptr = None
+    else:
+        offsets = _prep(offsets.to(torch.int64), torch.int64, "offsets")
+        R, T = offsets.numel() - 1, 0
+        total_frames = dec.numel()
+        off_ptr = offsets.data_ptr()
+    counts = torch.zeros(max(R, 0), dtype=torch.int32, device=dev)
+    if R <= 0:
+        return torch.empty((0, 3), dtype=torch.int32, device=dev), counts
+    cap = total_frames // max(min_run + 1, 2) + R + 1
+    seg_off = torch.empty(R + 1, dtype=torch.int64, device=dev)
+    seg = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.b200vad_segments(dec.data_ptr(), off_ptr, R, T, int(min_run), counts.data_ptr(), seg_off.data_ptr(),
+                                      seg.data_ptr(), cap, _stream_ptr(dev)), "b200vad_segments")
+    total = int(seg_off[R].item())
+    return seg[:total].clone(), counts
+
+
+@segments.register_fake
+def _(dec, offsets=None, min_run=2):
+    ctx = torch.library.get_ctx()
+    n = ctx.new_dynamic_size()
+    R = dec.shape[0] if offsets is None else offsets.numel() - 1
+    return dec.new_empty((n, 3), dtype=torch.int32), dec.new_empty((R,), dtype=torch.int32)
+
+
+# ------------------------------------------------------------------ whole path
+@torch.library.custom_op("b200vad::vad_pipeline", mutates_args=(), device_types="cuda")
+def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.Tensor, num_layers: int, thr: float,
+                 kernel: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    wav = _prep(wav, torch.float32, "wav")
+    if wav.dim() != 2:
+        raise _lib.B200VadError("wav must be (B, N)")
+    B, N = wav.shape
+    L = _lib.lib()
+    dev = wav.device
+    T = L.b200vad_fbank_num_frames(N)
+    prob = torch.empty((B, T), dtype=torch.float32, device=dev)
+    dec = torch.empty((B, T), dtype=torch.uint8, device=dev)
+    counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    if B == 0 or T == 0:
+        return prob, dec, torch.empty((0, 3), dtype=torch.int32, device=dev), counts
+    if B > 65535:
+        raise _lib.B200VadError("vad_pipeline handles at most 65535 rows per call; shard the batch")
+    per_row = (T + 2) // 3
+    cap = B * per_row
+    seg = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    seg_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _ensure(dev)
+        lens_ptr = None
+        if lens is not None:
+            lens = _prep(lens.to(torch.int32), torch.int32, "lens")
+            lens_ptr = lens.data_ptr()
+        need = L.b200vad_pipeline_workspace_bytes(B, N)
+        minimum = L.b200vad_pipeline_workspace_bytes(B, N) - L.b200vad_model_workspace_bytes(B, T) + \
+            L.b200vad_model_workspace_bytes(1, T)
+        ws = _ws(min(need, max(_MAX_WS_BYTES, minimum)), dev)
+        _lib.check(L.b200vad_pipeline_fbank_f32(packed.data_ptr(), num_layers, wav.data_ptr(), lens_ptr, B, N, wav.stride(0),
+                                                float(thr), int(kernel), prob.data_ptr(), dec.data_ptr(), counts.data_ptr(),
+                                                seg_off.data_ptr(), seg.data_ptr(), cap, ws.data_ptr(), ws.numel(),
+                                                _stream_ptr(dev)), "b200vad_pipeline_fbank_f32")
+    total = int(seg_off[B].item())
+    return prob, dec, seg[:total].clone(), counts
+
+
+@vad_pipeline.register_fake
+def _(wav, lens, packed, num_layers, thr, kernel):
+    ctx = torch.library.get_ctx()
+    n = ctx.new_dynamic_size()
+    B, N = wav.shape
+    T = (N + 80) // 160
+    return (wav.new_empty((B, T)), wav.new_empty((B, T), dtype=torch.uint8), wav.new_empty((n, 3), dtype=torch.int32),
+            wav.new_empty((B,), dtype=torch.int32))

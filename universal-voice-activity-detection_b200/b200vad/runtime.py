@@ -1,0 +1,94 @@
+"""Runtime around the kernels: the host-buffer session (C++ object behind the C ABI) and the
+multi-GPU plumbing (shard by utterance, gather segment lists).  One process per GPU."""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .host import shard_range  # noqa: F401  (re-export)
+
+
+class HostSession:
+    """waveforms on the HOST -> decisions / probabilities / segments on the HOST.
+
+    Wraps ``b200vad_session_*``: the session owns device buffers and two CUDA streams and
+    overlaps the H2D copy of chunk i+1 with the compute of chunk i.  Pass pinned tensors
+    (``tensor.pin_memory()``) for full PCIe bandwidth.
+    """
+
+    def __init__(self, packed: torch.Tensor, num_layers: int, num_samples: int, chunk_rows: int = 1024,
+                 device: Optional[int] = None):
+        if not packed.is_cuda:
+            raise _lib.B200VadError("packed weights must live on the GPU")
+        self.device = packed.device.index if device is None else device
+        self.packed = packed
+        self.N = int(num_samples)
+        self.T = (self.N + 80) // 160
+        self.chunk_rows = int(chunk_rows)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b200vad_session_create(self.device, packed.data_ptr(), num_layers, self.chunk_rows, self.N,
+                                                     C.byref(h)), "b200vad_session_create")
+        self._h = h
+
+    def run(self, wav: torch.Tensor, thr: float = 0.5, kernel: int = 49, want_dec: bool = True, want_prob: bool = False,
+            out: Optional[dict] = None):
+        """wav: (B, N) float32 CPU tensor.  Returns dict(dec, prob, seg) of CPU tensors."""
+        if wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2 or wav.shape[1] != self.N or not wav.is_contiguous():
+            raise _lib.B200VadError("wav must be a contiguous CPU float32 tensor of shape (B, N)")
+        B = wav.shape[0]
+        out = out if out is not None else {}
+        if want_dec and ("dec" not in out or out["dec"].shape[0] < B):
+            out["dec"] = torch.empty((B, self.T), dtype=torch.uint8).pin_memory()
+        if want_prob and ("prob" not in out or out["prob"].shape[0] < B):
+            out["prob"] = torch.empty((B, self.T), dtype=torch.float32).pin_memory()
+        cap = B * ((self.T + 2) // 3)
+        if "seg_buf" not in out or out["seg_buf"].shape[0] < cap:
+            out["seg_buf"] = torch.empty((max(cap, 1), 3), dtype=torch.int32).pin_memory()
+        nseg = C.c_int64(0)
+        _lib.check(_lib.lib().b200vad_session_run_host(
+            self._h, wav.data_ptr(), B, float(thr), int(kernel),
+            out["dec"].data_ptr() if want_dec else None, out["prob"].data_ptr() if want_prob else None,
+            out["seg_buf"].data_ptr(), cap, C.byref(nseg)), "b200vad_session_run_host")
+        out["seg"] = out["seg_buf"][: nseg.value]
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().b200vad_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gather_segments(seg: torch.Tensor, row_base: int = 0, group=None) -> torch.Tensor:
+    """All-gather per-rank segment triples (S_r, 3) int32 -> (sum S_r, 3) on every rank, rows
+    re-based to global utterance ids by adding ``row_base`` to column 0.  Two collectives: one
+    all_gather of the counts, one all_gather of the triples padded to max(count).
+    Works on CUDA tensors with the NCCL backend and on CPU tensors with gloo."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        s = seg.clone()
+        s[:, 0] += row_base
+        return s
+    world = dist.get_world_size(group)
+    local = seg.clone()
+    local[:, 0] += row_base
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=seg.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(max(counts), 1)
+    padded = torch.zeros((m, 3), dtype=torch.int32, device=seg.device)
+    padded[: local.shape[0]] = local
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)

@@ -1,0 +1,584 @@
+// extern "C" entry points of libb200vad.so (declared in include/b200vad.h).
+#include "kernels.cuh"
+#include "../../include/b200vad.h"
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+namespace b200vad {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int round32(int k) { return (k + 31) / 32 * 32; }
+
+// ---------------------------------------------------------------- packed model layout
+struct LayerOff {
+    size_t wih_hi, wih_lo, bias, whh;
+    int D, Kp;
+};
+struct ModelLayout {
+    std::vector<LayerOff> layers;
+    size_t w1_hi, w1_lo, b1, w2_hi, w2_lo, b2, wc, bc, total;
+};
+static ModelLayout model_layout(int D, int L) {
+    ModelLayout m;
+    size_t off = 0;
+    for (int l = 0; l < L; ++l) {
+        LayerOff o;
+        o.D = (l == 0) ? D : 2 * kHidden;
+        o.Kp = round32(o.D);
+        o.wih_hi = off; off = align_up(off + sizeof(__half) * 2 * kGates * o.Kp);
+        o.wih_lo = off; off = align_up(off + sizeof(__half) * 2 * kGates * o.Kp);
+        o.bias = off;   off = align_up(off + sizeof(float) * 2 * kGates);
+        o.whh = off;    off = align_up(off + sizeof(__half) * 2 * kGates * kHidden);
+        m.layers.push_back(o);
+    }
+    m.w1_hi = off; off = align_up(off + sizeof(__half) * kHidden * 2 * kHidden);
+    m.w1_lo = off; off = align_up(off + sizeof(__half) * kHidden * 2 * kHidden);
+    m.b1 = off;    off = align_up(off + sizeof(float) * kHidden);
+    m.w2_hi = off; off = align_up(off + sizeof(__half) * kHidden * kHidden);
+    m.w2_lo = off; off = align_up(off + sizeof(__half) * kHidden * kHidden);
+    m.b2 = off;    off = align_up(off + sizeof(float) * kHidden);
+    m.wc = off;    off = align_up(off + sizeof(float) * kHidden);
+    m.bc = off;    off = align_up(off + sizeof(float));
+    m.total = off;
+    return m;
+}
+
+// bytes of workspace per (sequence, frame): xg fp32 [1024] + two fp16 layer buffers [256]
+constexpr size_t kModelBytesPerFrame = sizeof(float) * 2 * kGates + 2 * sizeof(__half) * 2 * kHidden;
+
+static int model_forward(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+    B200VAD_CHECK_ARG(packed && x && prob && ws, "null pointer");
+    B200VAD_CHECK_ARG(D > 0 && L > 0 && B >= 0 && T >= 0, "bad shape");
+    B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+    if (B == 0 || T == 0) return B200VAD_OK;
+    B200VAD_CHECK_ARG(T < (1 << 24), "T too large");
+    const ModelLayout m = model_layout(D, L);
+    const char* pk = reinterpret_cast<const char*>(packed);
+    const size_t per_row = align_up((size_t)T * kModelBytesPerFrame) + 512;
+    int64_t Bc = (int64_t)(ws_bytes / per_row);
+    // one GEMM launch handles < 65535*128 rows
+    Bc = std::min<int64_t>(Bc, (int64_t)(65000LL * 128 / T));
+    Bc = std::min<int64_t>(Bc, B);
+    if (Bc < 1) {
+        set_error("model_forward: workspace too small (%zu bytes; need >= %zu per sequence)", ws_bytes, per_row);
+        return B200VAD_ENOMEM;
+    }
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = (int)std::min<int64_t>(Bc, B - b0);
+        const int64_t rows = (int64_t)bc * T;
+        char* w = reinterpret_cast<char*>(ws);
+        float* xg = reinterpret_cast<float*>(w);
+        __half* y0 = reinterpret_cast<__half*>(w + align_up(sizeof(float) * 2 * kGates * rows));
+        __half* y1 = reinterpret_cast<__half*>(reinterpret_cast<char*>(y0) + align_up(sizeof(__half) * 2 * kHidden * rows));
+        const void* in = x + b0 * T * D;
+        int in_half = 0;
+        __half* out = y0;
+        for (int l = 0; l < L; ++l) {
+            const LayerOff& lo = m.layers[l];
+            GemmArgs g;
+            g.A = in; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
+            g.N = 2 * kGates; g.K = lo.D; g.Kp = lo.Kp;
+            g.W_hi = reinterpret_cast<const __half*>(pk + lo.wih_hi);
+            g.W_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
+            g.bias = reinterpret_cast<const float*>(pk + lo.bias);
+            g.C = xg; g.ldc = 2 * kGates; g.c_half = 0; g.act = 0;
+            int rc = gemm_launch(g, in_half, in_half ? 2 : 3, st);
+            if (rc) return rc;
+            rc = lstm_recurrent_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), out, bc, (int)T, st);
+            if (rc) return rc;
+            in = out; in_half = 1;
+            out = (out == y0) ? y1 : y0;
+        }
+        // head: Linear(256,128)+lrelu -> Linear(128,128)+lrelu -> Linear(128,1)+sigmoid; z buffers alias xg
+        float* z1 = xg;
+        float* z2 = xg + rows * kHidden;
+        GemmArgs g;
+        g.A = in; g.lda = 2 * kHidden; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
+        g.N = kHidden; g.K = 2 * kHidden; g.Kp = 2 * kHidden;
+        g.W_hi = reinterpret_cast<const __half*>(pk + m.w1_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w1_lo);
+        g.bias = reinterpret_cast<const float*>(pk + m.b1);
+        g.C = z1; g.ldc = kHidden; g.c_half = 0; g.act = 1;
+        int rc = gemm_launch(g, 1, 2, st);
+        if (rc) return rc;
+        g.A = z1; g.lda = kHidden; g.K = kHidden; g.Kp = kHidden;
+        g.W_hi = reinterpret_cast<const __half*>(pk + m.w2_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w2_lo);
+        g.bias = reinterpret_cast<const float*>(pk + m.b2);
+        g.C = z2;
+        rc = gemm_launch(g, 0, 3, st);
+        if (rc) return rc;
+        rc = classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc),
+                               prob + b0 * T, st);
+        if (rc) return rc;
+    }
+    return B200VAD_OK;
+}
+
+// ---------------------------------------------------------------- SincNet packed layout
+struct SincLayout {
+    size_t filt, sinc_hi, sinc_lo, c1_f32, c1_hi, c1_lo, c1_b, c2_f32, c2_hi, c2_lo, c2_b, wn_w, wn_b, n0_w, n0_b, n1_w, n1_b,
+        n2_w, n2_b, total;
+};
+constexpr int kSincK = 251, kSincKp = 256, kC1K = 400, kC1Kp = 416, kC2K = 300, kC2Kp = 320;
+static SincLayout sinc_layout() {
+    SincLayout s;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    s.filt = take(sizeof(float) * 80 * kSincK);
+    s.sinc_hi = take(sizeof(__half) * 80 * kSincKp);
+    s.sinc_lo = take(sizeof(__half) * 80 * kSincKp);
+    s.c1_f32 = take(sizeof(float) * 60 * kC1K);
+    s.c1_hi = take(sizeof(__half) * 60 * kC1Kp);
+    s.c1_lo = take(sizeof(__half) * 60 * kC1Kp);
+    s.c1_b = take(sizeof(float) * 60);
+    s.c2_f32 = take(sizeof(float) * 60 * kC2K);
+    s.c2_hi = take(sizeof(__half) * 60 * kC2Kp);
+    s.c2_lo = take(sizeof(__half) * 60 * kC2Kp);
+    s.c2_b = take(sizeof(float) * 60);
+    s.wn_w = take(4); s.wn_b = take(4);
+    s.n0_w = take(sizeof(float) * 80); s.n0_b = take(sizeof(float) * 80);
+    s.n1_w = take(sizeof(float) * 60); s.n1_b = take(sizeof(float) * 60);
+    s.n2_w = take(sizeof(float) * 60); s.n2_b = take(sizeof(float) * 60);
+    s.total = off;
+    return s;
+}
+struct SincDims {
+    int64_t L1, P1, L2, P2, L3, P3;
+};
+static SincDims sinc_dims(int64_t N) {
+    SincDims d;
+    d.L1 = N >= 251 ? (N - 251) / 10 + 1 : 0;
+    d.P1 = d.L1 / 3;
+    d.L2 = d.P1 >= 5 ? d.P1 - 4 : 0;
+    d.P2 = d.L2 / 3;
+    d.L3 = d.P2 >= 5 ? d.P2 - 4 : 0;
+    d.P3 = d.L3 / 3;
+    return d;
+}
+static size_t sinc_ws_per_row(int64_t N) {
+    SincDims d = sinc_dims(N);
+    // normalised wave + conv1 out + pooled1 + conv2 out + pooled2 + conv3 out, stats
+    return align_up(sizeof(float) * N) + align_up(sizeof(float) * d.L1 * 80) + align_up(sizeof(float) * d.P1 * 80) +
+           align_up(sizeof(float) * d.L2 * 60) + align_up(sizeof(float) * d.P2 * 60) + align_up(sizeof(float) * d.L3 * 60) +
+           align_up(sizeof(double) * 2 * 80) + 2048;
+}
+
+}  // namespace b200vad
+
+using namespace b200vad;
+
+extern "C" {
+
+int b200vad_abi_version(void) { return B200VAD_ABI_VERSION; }
+const char* b200vad_last_error(void) { return g_err; }
+
+int b200vad_init(int device) {
+    int n = 0;
+    B200VAD_CUDA(cudaGetDeviceCount(&n));
+    B200VAD_CHECK_ARG(device >= 0 && device < n, "no such CUDA device");
+    B200VAD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200VAD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("b200vad_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return B200VAD_ESTATE;
+    }
+    return fbank_tables_init(device);
+}
+
+int64_t b200vad_fbank_num_frames(int64_t n) { return n < 0 ? 0 : (n + kFrameShift / 2) / kFrameShift; }
+
+int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride, float* feats, int64_t T,
+                      double* row_sum_ws, void* stream) {
+    B200VAD_CHECK_ARG(B >= 0 && N >= 0 && T >= 0, "negative size");
+    if (B == 0 || T == 0) return B200VAD_OK;
+    B200VAD_CHECK_ARG(wav && feats && row_sum_ws, "null pointer");
+    B200VAD_CHECK_ARG(N >= 1 && wav_stride >= N, "need N >= 1 and wav_stride >= N");
+    B200VAD_CHECK_ARG(B <= 65535, "B must be <= 65535 per call");
+    int dev = 0;
+    B200VAD_CUDA(cudaGetDevice(&dev));
+    return fbank_launch(wav, lens, B, N, wav_stride, feats, T, row_sum_ws, dev, (cudaStream_t)stream);
+}
+
+size_t b200vad_model_packed_bytes(int D, int L) {
+    if (D <= 0 || L <= 0) return 0;
+    return model_layout(D, L).total;
+}
+
+int b200vad_model_pack_lstm(void* packed, int D, int L, int layer, int dir, const float* w_ih, const float* w_hh,
+                            const float* b_ih, const float* b_hh, void* stream) {
+    B200VAD_CHECK_ARG(packed && w_ih && w_hh && b_ih && b_hh, "null pointer");
+    B200VAD_CHECK_ARG(D > 0 && L > 0 && layer >= 0 && layer < L && (dir == 0 || dir == 1), "bad index");
+    ModelLayout m = model_layout(D, L);
+    const LayerOff& lo = m.layers[layer];
+    char* pk = reinterpret_cast<char*>(packed);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = split_weights(w_ih, kGates, lo.D, lo.Kp, reinterpret_cast<__half*>(pk + lo.wih_hi) + (size_t)dir * kGates * lo.Kp,
+                           reinterpret_cast<__half*>(pk + lo.wih_lo) + (size_t)dir * kGates * lo.Kp, st);
+    if (rc) return rc;
+    rc = add_bias(b_ih, b_hh, reinterpret_cast<float*>(pk + lo.bias) + dir * kGates, kGates, st);
+    if (rc) return rc;
+    return pack_whh(w_hh, reinterpret_cast<__half*>(pk + lo.whh) + (size_t)dir * kGates * kHidden, st);
+}
+
+int b200vad_model_pack_head(void* packed, int D, int L, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const float* wc, const float* bc, void* stream) {
+    B200VAD_CHECK_ARG(packed && w1 && b1 && w2 && b2 && wc && bc, "null pointer");
+    B200VAD_CHECK_ARG(D > 0 && L > 0, "bad shape");
+    ModelLayout m = model_layout(D, L);
+    char* pk = reinterpret_cast<char*>(packed);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = split_weights(w1, kHidden, 2 * kHidden, 2 * kHidden, reinterpret_cast<__half*>(pk + m.w1_hi),
+                           reinterpret_cast<__half*>(pk + m.w1_lo), st);
+    if (rc) return rc;
+    rc = split_weights(w2, kHidden, kHidden, kHidden, reinterpret_cast<__half*>(pk + m.w2_hi),
+                       reinterpret_cast<__half*>(pk + m.w2_lo), st);
+    if (rc) return rc;
+    B200VAD_CUDA(cudaMemcpyAsync(pk + m.b1, b1, sizeof(float) * kHidden, cudaMemcpyDeviceToDevice, st));
+    B200VAD_CUDA(cudaMemcpyAsync(pk + m.b2, b2, sizeof(float) * kHidden, cudaMemcpyDeviceToDevice, st));
+    B200VAD_CUDA(cudaMemcpyAsync(pk + m.wc, wc, sizeof(float) * kHidden, cudaMemcpyDeviceToDevice, st));
+    B200VAD_CUDA(cudaMemcpyAsync(pk + m.bc, bc, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return B200VAD_OK;
+}
+
+size_t b200vad_model_workspace_bytes(int B, int64_t T) {
+    if (B <= 0 || T <= 0) return 0;
+    return (size_t)B * (align_up((size_t)T * kModelBytesPerFrame) + 512) + 4096;
+}
+
+int b200vad_model_forward_f32(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
+                              size_t ws_bytes, void* stream) {
+    return model_forward(packed, D, L, x, B, T, prob, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- SincNet
+int64_t b200vad_sincnet_num_frames(int64_t n) { return sinc_dims(n).P3; }
+size_t b200vad_sincnet_packed_bytes(void) { return sinc_layout().total; }
+
+int b200vad_sincnet_pack(void* packed, const float* wav_norm_w, const float* wav_norm_b, const float* low_hz,
+                         const float* band_hz, const float* window, const float* n, const float* conv1_w,
+                         const float* conv1_b, const float* conv2_w, const float* conv2_b, const float* norm0_w,
+                         const float* norm0_b, const float* norm1_w, const float* norm1_b, const float* norm2_w,
+                         const float* norm2_b, void* stream) {
+    B200VAD_CHECK_ARG(packed && wav_norm_w && wav_norm_b && low_hz && band_hz && window && n && conv1_w && conv1_b &&
+                          conv2_w && conv2_b && norm0_w && norm0_b && norm1_w && norm1_b && norm2_w && norm2_b,
+                      "null pointer");
+    SincLayout s = sinc_layout();
+    char* pk = reinterpret_cast<char*>(packed);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = sinc_filters_launch(low_hz, band_hz, window, n, reinterpret_cast<float*>(pk + s.filt), st);
+    if (rc) return rc;
+    rc = split_weights(reinterpret_cast<float*>(pk + s.filt), 80, kSincK, kSincKp, reinterpret_cast<__half*>(pk + s.sinc_hi),
+                       reinterpret_cast<__half*>(pk + s.sinc_lo), st);
+    if (rc) return rc;
+    rc = repack_conv_launch(conv1_w, 60, 80, 5, reinterpret_cast<float*>(pk + s.c1_f32), st);
+    if (rc) return rc;
+    rc = split_weights(reinterpret_cast<float*>(pk + s.c1_f32), 60, kC1K, kC1Kp, reinterpret_cast<__half*>(pk + s.c1_hi),
+                       reinterpret_cast<__half*>(pk + s.c1_lo), st);
+    if (rc) return rc;
+    rc = repack_conv_launch(conv2_w, 60, 60, 5, reinterpret_cast<float*>(pk + s.c2_f32), st);
+    if (rc) return rc;
+    rc = split_weights(reinterpret_cast<float*>(pk + s.c2_f32), 60, kC2K, kC2Kp, reinterpret_cast<__half*>(pk + s.c2_hi),
+                       reinterpret_cast<__half*>(pk + s.c2_lo), st);
+    if (rc) return rc;
+    struct { size_t off; const float* src; size_t n; } cp[] = {
+        {s.c1_b, conv1_b, 60}, {s.c2_b, conv2_b, 60}, {s.wn_w, wav_norm_w, 1}, {s.wn_b, wav_norm_b, 1},
+        {s.n0_w, norm0_w, 80}, {s.n0_b, norm0_b, 80}, {s.n1_w, norm1_w, 60}, {s.n1_b, norm1_b, 60},
+        {s.n2_w, norm2_w, 60}, {s.n2_b, norm2_b, 60}};
+    for (auto& c : cp) B200VAD_CUDA(cudaMemcpyAsync(pk + c.off, c.src, sizeof(float) * c.n, cudaMemcpyDeviceToDevice, st));
+    return B200VAD_OK;
+}
+
+size_t b200vad_sincnet_workspace_bytes(int B, int64_t N) {
+    if (B <= 0 || N <= 0) return 0;
+    return (size_t)B * sinc_ws_per_row(N) + 4096;
+}
+
+int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int64_t N, int64_t wav_stride, float* out,
+                                void* workspace, size_t ws_bytes, void* stream) {
+    B200VAD_CHECK_ARG(packed && wav && out && workspace, "null pointer");
+    B200VAD_CHECK_ARG(B >= 0 && N >= 0 && wav_stride >= N, "bad shape");
+    B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    const SincDims d = sinc_dims(N);
+    B200VAD_CHECK_ARG(d.P3 >= 1, "waveform shorter than the SincNet receptive field (991 samples)");
+    if (B == 0) return B200VAD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const SincLayout s = sinc_layout();
+    const char* pk = reinterpret_cast<const char*>(packed);
+    const size_t per_row = sinc_ws_per_row(N);
+    int64_t Bc = std::min<int64_t>((int64_t)(ws_bytes / per_row), B);
+    Bc = std::min<int64_t>(Bc, 60000);
+    Bc = std::min<int64_t>(Bc, std::max<int64_t>(1, 65000LL * 128 / std::max<int64_t>(d.L1, 1)));
+    if (Bc < 1) {
+        set_error("sincnet_forward: workspace too small (%zu bytes; need >= %zu per row)", ws_bytes, per_row);
+        return B200VAD_ENOMEM;
+    }
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = (int)std::min<int64_t>(Bc, B - b0);
+        char* w = reinterpret_cast<char*>(workspace);
+        auto take = [&](size_t bytes) { char* p = w; w += align_up(bytes); return p; };
+        float* wn = reinterpret_cast<float*>(take(sizeof(float) * N * bc));
+        float* c1 = reinterpret_cast<float*>(take(sizeof(float) * d.L1 * 80 * bc));
+        float* p1 = reinterpret_cast<float*>(take(sizeof(float) * d.P1 * 80 * bc));
+        float* c2 = reinterpret_cast<float*>(take(sizeof(float) * d.L2 * 60 * bc));
+        float* p2 = reinterpret_cast<float*>(take(sizeof(float) * d.P2 * 60 * bc));
+        float* c3 = reinterpret_cast<float*>(take(sizeof(float) * d.L3 * 60 * bc));
+        double* stats = reinterpret_cast<double*>(take(sizeof(double) * 2 * 80 * bc));
+        int rc = wave_instnorm_launch(wav + b0 * wav_stride, bc, N, wav_stride, reinterpret_cast<const float*>(pk + s.wn_w),
+                                      reinterpret_cast<const float*>(pk + s.wn_b), stats, wn, st);
+        if (rc) return rc;
+        GemmArgs g;
+        // sinc conv: rows (b, t) = wn[b, 10 t : 10 t + 251]
+        g.A = wn; g.lda = 10; g.rows_per_batch = d.L1; g.a_batch_stride = N; g.M = d.L1 * bc;
+        g.N = 80; g.K = kSincK; g.Kp = kSincKp;
+        g.W_hi = reinterpret_cast<const __half*>(pk + s.sinc_hi); g.W_lo = reinterpret_cast<const __half*>(pk + s.sinc_lo);
+        g.bias = nullptr; g.C = c1; g.ldc = 80; g.c_half = 0; g.act = 2;
+        rc = gemm_launch(g, 0, 3, st);
+        if (rc) return rc;
+        rc = pool_norm_lrelu_launch(c1, bc, d.L1, 80, p1, stats, reinterpret_cast<const float*>(pk + s.n0_w),
+                                    reinterpret_cast<const float*>(pk + s.n0_b), st);
+        if (rc) return rc;
+        // Conv1d(80, 60, 5): rows (b, t) = p1[b, t : t + 5, :]
+        g.A = p1; g.lda = 80; g.rows_per_batch = d.L2; g.a_batch_stride = d.P1 * 80; g.M = d.L2 * bc;
+        g.N = 60; g.K = kC1K; g.Kp = kC1Kp;
+        g.W_hi = reinterpret_cast<const __half*>(pk + s.c1_hi); g.W_lo = reinterpret_cast<const __half*>(pk + s.c1_lo);
+        g.bias = reinterpret_cast<const float*>(pk + s.c1_b); g.C = c2; g.ldc = 60; g.act = 0;
+        rc = gemm_launch(g, 0, 3, st);
+        if (rc) return rc;
+        rc = pool_norm_lrelu_launch(c2, bc, d.L2, 60, p2, stats, reinterpret_cast<const float*>(pk + s.n1_w),
+                                    reinterpret_cast<const float*>(pk + s.n1_b), st);
+        if (rc) return rc;
+        g.A = p2; g.lda = 60; g.rows_per_batch = d.L3; g.a_batch_stride = d.P2 * 60; g.M = d.L3 * bc;
+        g.N = 60; g.K = kC2K; g.Kp = kC2Kp;
+        g.W_hi = reinterpret_cast<const __half*>(pk + s.c2_hi); g.W_lo = reinterpret_cast<const __half*>(pk + s.c2_lo);
+        g.bias = reinterpret_cast<const float*>(pk + s.c2_b); g.C = c3; g.ldc = 60; g.act = 0;
+        rc = gemm_launch(g, 0, 3, st);
+        if (rc) return rc;
+        rc = pool_norm_lrelu_launch(c3, bc, d.L3, 60, out + b0 * d.P3 * 60, stats, reinterpret_cast<const float*>(pk + s.n2_w),
+                                    reinterpret_cast<const float*>(pk + s.n2_b), st);
+        if (rc) return rc;
+    }
+    return B200VAD_OK;
+}
+
+// ---------------------------------------------------------------- post-processing
+int b200vad_median_window(double speech_window, double window) {
+    int k = (int)(speech_window / window);   // helper.py:85-87
+    if (k % 2 == 0) k -= 1;
+    return k;
+}
+
+int b200vad_threshold_median(const float* prob, int B, int64_t T, float thr, int kernel, void* out, int elem_bytes,
+                             int32_t* near_count, float near_tol, void* stream) {
+    B200VAD_CHECK_ARG(B >= 0 && T >= 0, "negative size");
+    if (B == 0 || T == 0) return B200VAD_OK;
+    B200VAD_CHECK_ARG(prob && out, "null pointer");
+    B200VAD_CHECK_ARG(elem_bytes == 1 || elem_bytes == 8, "elem_bytes must be 1 or 8");
+    B200VAD_CHECK_ARG(B <= 65535, "B must be <= 65535 per call");
+    return threshold_median_launch(prob, B, T, thr, kernel, out, elem_bytes, near_count, near_tol, (cudaStream_t)stream);
+}
+
+int b200vad_segments(const uint8_t* dec, const int64_t* offsets, int R, int64_t T, int min_run, int32_t* counts,
+                     int64_t* seg_off, int32_t* seg, int64_t cap, void* stream) {
+    B200VAD_CHECK_ARG(R >= 0 && cap >= 0 && min_run >= 1, "bad size");
+    if (R == 0) return B200VAD_OK;
+    B200VAD_CHECK_ARG(dec && counts && seg_off && (seg || cap == 0), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    B200VAD_CHECK_ARG(offsets || T >= 0, "bad T");
+    return segments_launch(dec, offsets, T, R, min_run, 0, counts, seg_off, seg, cap, st);
+}
+
+// ---------------------------------------------------------------- fused device pipeline
+static size_t pipeline_ws_bytes(int B, int64_t N) {
+    int64_t T = b200vad_fbank_num_frames(N);
+    return align_up(sizeof(float) * (size_t)B * T * kNumMel) + align_up(sizeof(double) * B) +
+           b200vad_model_workspace_bytes(B, T) + 4096;
+}
+size_t b200vad_pipeline_workspace_bytes(int B, int64_t N) {
+    if (B <= 0 || N <= 0) return 0;
+    return pipeline_ws_bytes(B, N);
+}
+
+static int pipeline_run(const void* packed, int L, const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride,
+                        float thr, int kernel, int row_base, float* prob, uint8_t* dec, int32_t* counts, int64_t* seg_off,
+                        int32_t* seg, int64_t cap, void* ws, size_t ws_bytes, cudaStream_t st) {
+    B200VAD_CHECK_ARG(packed && wav && prob && dec && counts && seg_off && ws, "null pointer");
+    B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+    const int64_t T = b200vad_fbank_num_frames(N);
+    if (B == 0 || T == 0) return B200VAD_OK;
+    char* w = reinterpret_cast<char*>(ws);
+    float* feats = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * (size_t)B * T * kNumMel);
+    double* sums = reinterpret_cast<double*>(w); w += align_up(sizeof(double) * B);
+    size_t used = (size_t)(w - reinterpret_cast<char*>(ws));
+    if (ws_bytes < used + b200vad_model_workspace_bytes(1, T)) {
+        set_error("pipeline: workspace too small (%zu bytes)", ws_bytes);
+        return B200VAD_ENOMEM;
+    }
+    int dev = 0;
+    B200VAD_CUDA(cudaGetDevice(&dev));
+    int rc = fbank_launch(wav, lens, B, N, stride, feats, T, sums, dev, st);
+    if (rc) return rc;
+    rc = model_forward(packed, kNumMel, L, feats, B, T, prob, w, ws_bytes - used, st);
+    if (rc) return rc;
+    rc = threshold_median_launch(prob, B, T, thr, kernel, dec, 1, nullptr, 0.f, st);
+    if (rc) return rc;
+    return segments_launch(dec, nullptr, T, B, 2, row_base, counts, seg_off, seg, cap, st);
+}
+
+int b200vad_pipeline_fbank_f32(const void* packed, int L, const float* wav, const int32_t* lens, int B, int64_t N,
+                               int64_t stride, float thr, int kernel, float* prob, uint8_t* dec, int32_t* counts,
+                               int64_t* seg_off, int32_t* seg, int64_t cap, void* ws, size_t ws_bytes, void* stream) {
+    B200VAD_CHECK_ARG(B >= 0 && B <= 65535 && N >= 1 && stride >= N, "bad shape");
+    return pipeline_run(packed, L, wav, lens, B, N, stride, thr, kernel, 0, prob, dec, counts, seg_off, seg, cap, ws, ws_bytes,
+                        (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- host-buffer session
+struct b200vad_session {
+    int device;
+    const void* packed;
+    int L;
+    int chunk;
+    int64_t N, T, max_seg_per_row;
+    cudaStream_t copy_stream, compute_stream;
+    cudaEvent_t copied[2], consumed[2];
+    float* wav_dev[2];
+    float* prob_dev[2];
+    uint8_t* dec_dev[2];
+    int32_t* counts_dev;
+    int64_t* seg_off_dev;
+    int32_t* seg_dev;       // grows with B
+    int64_t seg_dev_rows;
+    void* ws;
+    size_t ws_bytes;
+    int64_t* totals_host;   // pinned, one per chunk
+    int64_t totals_cap;
+};
+
+int b200vad_session_create(int device, const void* packed_device, int num_layers, int max_chunk_rows, int64_t N,
+                           b200vad_session** out) {
+    B200VAD_CHECK_ARG(out && packed_device, "null pointer");
+    B200VAD_CHECK_ARG(num_layers > 0 && max_chunk_rows > 0 && max_chunk_rows <= 65535 && N >= 1, "bad shape");
+    int rc = b200vad_init(device);
+    if (rc) return rc;
+    b200vad_session* s = new b200vad_session();
+    memset(s, 0, sizeof(*s));
+    s->device = device; s->packed = packed_device; s->L = num_layers; s->chunk = max_chunk_rows; s->N = N;
+    s->T = b200vad_fbank_num_frames(N);
+    s->max_seg_per_row = (s->T + 2) / 3;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&s->compute_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        ok(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+        ok(cudaMalloc(&s->wav_dev[i], sizeof(float) * (size_t)s->chunk * N));
+        ok(cudaMalloc(&s->prob_dev[i], sizeof(float) * (size_t)s->chunk * s->T));
+        ok(cudaMalloc(&s->dec_dev[i], (size_t)s->chunk * s->T));
+    }
+    ok(cudaMalloc(&s->counts_dev, sizeof(int32_t) * s->chunk));
+    ok(cudaMalloc(&s->seg_off_dev, sizeof(int64_t) * (s->chunk + 1)));
+    s->ws_bytes = pipeline_ws_bytes(s->chunk, N);
+    ok(cudaMalloc(&s->ws, s->ws_bytes));
+    s->totals_cap = 1024;
+    ok(cudaMallocHost(&s->totals_host, sizeof(int64_t) * s->totals_cap));
+    if (e != cudaSuccess) {
+        set_error("b200vad_session_create: %s", cudaGetErrorString(e));
+        b200vad_session_destroy(s);
+        return e == cudaErrorMemoryAllocation ? B200VAD_ENOMEM : B200VAD_ECUDA;
+    }
+    *out = s;
+    return B200VAD_OK;
+}
+
+int b200vad_session_run_host(b200vad_session* s, const float* wav_host, int B, float thr, int kernel, uint8_t* dec_host,
+                             float* prob_host, int32_t* seg_host, int64_t cap, int64_t* nseg) {
+    B200VAD_CHECK_ARG(s && wav_host && nseg && (seg_host || cap == 0), "null pointer");
+    B200VAD_CHECK_ARG(B >= 0 && cap >= 0, "bad size");
+    *nseg = 0;
+    if (B == 0) return B200VAD_OK;
+    B200VAD_CUDA(cudaSetDevice(s->device));
+    const int nchunks = (B + s->chunk - 1) / s->chunk;
+    if (nchunks > s->totals_cap) {
+        set_error("session_run_host: too many chunks (%d)", nchunks);
+        return B200VAD_EINVAL;
+    }
+    if (s->seg_dev_rows < B) {
+        if (s->seg_dev) cudaFree(s->seg_dev);
+        s->seg_dev = nullptr;
+        B200VAD_CUDA(cudaMalloc(&s->seg_dev, sizeof(int32_t) * 3 * (size_t)B * s->max_seg_per_row));
+        s->seg_dev_rows = B;
+    }
+    const int64_t N = s->N, T = s->T;
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        const int b0 = c * s->chunk, bc = std::min(s->chunk, B - b0);
+        // wait until the compute of chunk c-2 released this buffer
+        if (c >= 2) B200VAD_CUDA(cudaStreamWaitEvent(s->copy_stream, s->consumed[buf], 0));
+        B200VAD_CUDA(cudaMemcpyAsync(s->wav_dev[buf], wav_host + (size_t)b0 * N, sizeof(float) * (size_t)bc * N,
+                                     cudaMemcpyHostToDevice, s->copy_stream));
+        B200VAD_CUDA(cudaEventRecord(s->copied[buf], s->copy_stream));
+        B200VAD_CUDA(cudaStreamWaitEvent(s->compute_stream, s->copied[buf], 0));
+        int32_t* seg_c = s->seg_dev + 3 * (size_t)b0 * s->max_seg_per_row;
+        int rc = pipeline_run(s->packed, s->L, s->wav_dev[buf], nullptr, bc, N, N, thr, kernel, b0, s->prob_dev[buf],
+                              s->dec_dev[buf], s->counts_dev, s->seg_off_dev, seg_c, (int64_t)bc * s->max_seg_per_row, s->ws,
+                              s->ws_bytes, s->compute_stream);
+        if (rc) return rc;
+        B200VAD_CUDA(cudaMemcpyAsync(&s->totals_host[c], s->seg_off_dev + bc, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                     s->compute_stream));
+        if (dec_host)
+            B200VAD_CUDA(cudaMemcpyAsync(dec_host + (size_t)b0 * T, s->dec_dev[buf], (size_t)bc * T, cudaMemcpyDeviceToHost,
+                                         s->compute_stream));
+        if (prob_host)
+            B200VAD_CUDA(cudaMemcpyAsync(prob_host + (size_t)b0 * T, s->prob_dev[buf], sizeof(float) * (size_t)bc * T,
+                                         cudaMemcpyDeviceToHost, s->compute_stream));
+        B200VAD_CUDA(cudaEventRecord(s->consumed[buf], s->compute_stream));
+    }
+    B200VAD_CUDA(cudaStreamSynchronize(s->compute_stream));
+    int64_t total = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * s->chunk;
+        int64_t n = s->totals_host[c];
+        int64_t take = std::max<int64_t>(0, std::min<int64_t>(n, cap - total));
+        if (take > 0)
+            B200VAD_CUDA(cudaMemcpyAsync(seg_host + 3 * total, s->seg_dev + 3 * (size_t)b0 * s->max_seg_per_row,
+                                         sizeof(int32_t) * 3 * take, cudaMemcpyDeviceToHost, s->compute_stream));
+        total += n;
+    }
+    B200VAD_CUDA(cudaStreamSynchronize(s->compute_stream));
+    *nseg = total;
+    return B200VAD_OK;
+}
+
+void b200vad_session_destroy(b200vad_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (int i = 0; i < 2; ++i) {
+        if (s->wav_dev[i]) cudaFree(s->wav_dev[i]);
+        if (s->prob_dev[i]) cudaFree(s->prob_dev[i]);
+        if (s->dec_dev[i]) cudaFree(s->dec_dev[i]);
+        if (s->copied[i]) cudaEventDestroy(s->copied[i]);
+        if (s->consumed[i]) cudaEventDestroy(s->consumed[i]);
+    }
+    if (s->counts_dev) cudaFree(s->counts_dev);
+    if (s->seg_off_dev) cudaFree(s->seg_off_dev);
+    if (s->seg_dev) cudaFree(s->seg_dev);
+    if (s->ws) cudaFree(s->ws);
+    if (s->totals_host) cudaFreeHost(s->totals_host);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->compute_stream) cudaStreamDestroy(s->compute_stream);
+    delete s;
+}
+
+}  // extern "C"

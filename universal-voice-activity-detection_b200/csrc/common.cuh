@@ -1,0 +1,109 @@
+// Shared device/host helpers for the b200vad kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define B200VAD_OK 0
+#define B200VAD_EINVAL (-1)
+#define B200VAD_ECUDA (-2)
+#define B200VAD_ENOMEM (-3)
+#define B200VAD_ESTATE (-4)
+
+namespace b200vad {
+
+void set_error(const char* fmt, ...);
+
+#define B200VAD_CHECK_ARG(cond, msg)                                   \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            b200vad::set_error("%s: invalid argument: %s", __func__, msg); \
+            return B200VAD_EINVAL;                                     \
+        }                                                              \
+    } while (0)
+
+#define B200VAD_CUDA(call)                                             \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) {                                      \
+            b200vad::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__)); \
+            return B200VAD_ECUDA;                                      \
+        }                                                              \
+    } while (0)
+
+#define B200VAD_LAUNCH_CHECK()                                         \
+    do {                                                               \
+        cudaError_t e__ = cudaGetLastError();                          \
+        if (e__ != cudaSuccess) {                                      \
+            b200vad::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
+            return B200VAD_ECUDA;                                      \
+        }                                                              \
+    } while (0)
+
+// model / feature constants (reference: lhotse FbankConfig defaults; PyanNet2.py:60-67)
+constexpr int kFrameLen = 400;
+constexpr int kFrameShift = 160;
+constexpr int kFftLen = 512;
+constexpr int kNumMel = 80;
+constexpr int kPadLeft = 120;
+constexpr int kHidden = 128;
+constexpr int kGates = 4 * kHidden;
+constexpr float kLogEpsilon = -23.025850929940457f;   // lhotse LOG_EPSILON (feature pad value)
+constexpr float kEpsilon = 1.1920928955078125e-07f;    // torch.finfo(float).eps
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// sigmoid / tanh from one ex2 + one rcp each (~2 ulp); arguments clamped so the
+// exponential never overflows (sigmoid(+-30), tanh(+-15) are already 1 in fp32).
+__device__ __forceinline__ float sigmoid_acc(float x) {
+    x = fminf(fmaxf(x, -30.f), 30.f);
+    return fast_rcp(1.f + fast_ex2(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float tanh_acc(float x) {
+    x = fminf(fmaxf(x, -15.f), 15.f);
+    float e = fast_ex2(2.8853900817779268f * x);   // exp(2x)
+    return 1.f - 2.f * fast_rcp(e + 1.f);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- legacy warp MMA helpers (m16n8k16, fp16 x fp16 -> fp32) ----
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+
+// fp32 -> (hi, lo) fp16 pair with hi + lo ~= x to ~22 bits
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+}  // namespace b200vad

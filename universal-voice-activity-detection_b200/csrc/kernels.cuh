@@ -1,0 +1,42 @@
+// Internal launcher interface shared by the translation units of libb200vad.so.
+#pragma once
+#include "common.cuh"
+
+namespace b200vad {
+
+struct GemmArgs {
+    const void* A;
+    int64_t lda, rows_per_batch, a_batch_stride;   // in elements of A
+    int64_t M;
+    int N, K, Kp;                                   // Kp = K rounded up to 32 (W row stride)
+    const __half* W_hi;
+    const __half* W_lo;
+    const float* bias;
+    void* C;
+    int64_t ldc;
+    int c_half;                                     // 1: write fp16, 0: fp32
+    int act;                                        // 0 none, 1 leaky_relu(0.01), 2 abs
+};
+
+int gemm_launch(const GemmArgs& a, int a_half, int terms, cudaStream_t stream);
+int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, cudaStream_t stream);
+int fbank_tables_init(int device);
+int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, int64_t T_out,
+                 double* row_sums, int device, cudaStream_t stream);
+int lstm_recurrent_launch(const float* xg, const __half* whh, __half* y, int B, int T, cudaStream_t stream);
+int classifier_launch(const float* z, int64_t rows, const float* wc, const float* bc, float* prob, cudaStream_t stream);
+int pack_whh(const float* w, __half* out, cudaStream_t stream);
+int add_bias(const float* a, const float* b, float* out, int n, cudaStream_t stream);
+int threshold_median_launch(const float* prob, int B, int64_t T, float thr, int kernel, void* out, int elem,
+                            int32_t* near_count, float near_tol, cudaStream_t stream);
+// offsets == nullptr: R uniform rows of uniform_T frames
+int segments_launch(const uint8_t* dec, const int64_t* offsets, int64_t uniform_T, int R, int min_run, int row_base,
+                    int32_t* counts, int64_t* seg_off, int32_t* seg, int64_t cap, cudaStream_t stream);
+int sinc_filters_launch(const float* low, const float* band, const float* window, const float* n, float* out, cudaStream_t s);
+int repack_conv_launch(const float* w, int Cout, int Cin, int k, float* out, cudaStream_t s);
+int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, const float* gamma, const float* beta,
+                         double* stats, float* out, cudaStream_t s);
+int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
+                           const float* beta, cudaStream_t s);
+
+}  // namespace b200vad

@@ -1,0 +1,192 @@
+// SincNet front-end pieces (src/models/blocks/sincnet.py:34-103), channel-last layout.
+//
+//   wav (B,N) --InstanceNorm1d(1)--> (B,N) --sinc conv 80x251 /10, abs--> (B,L1,80)
+//   --MaxPool3 + InstanceNorm(80) + leaky_relu--> (B,P1,80) --Conv1d(80,60,5)--> (B,L2,60)
+//   --pool/norm/lrelu--> (B,P2,60) --Conv1d(60,60,5)--> (B,L3,60) --pool/norm/lrelu--> (B,Ts,60)
+//
+// Activations are kept time-major / channel-fastest so that (a) every convolution is the
+// overlapping-row GEMM of gemm.cu, and (b) the final (B,Ts,60) tensor already is the LSTM
+// input of PyanNet.forward (PyanNet.py:178 rearrange "b f t -> b t f") with no transpose.
+// InstanceNorm statistics (biased variance over time per (batch, channel), eps 1e-5) are
+// accumulated in double while the max-pool output is written, then applied in place together
+// with the affine transform and LeakyReLU(0.01).
+#include "kernels.cuh"
+
+namespace b200vad {
+
+// ---------------------------------------------------------------- sinc filter synthesis
+// asteroid-filterbanks 0.4 ParamSincFB.filters(): 40 cos + 40 sin band-pass filters of 251 taps.
+// low_hz_, band_hz_: (40); window_: (125); n_: (125).  out: (80, 251) fp32.
+__global__ void sinc_filters_kernel(const float* __restrict__ low_hz_, const float* __restrict__ band_hz_,
+                                    const float* __restrict__ window_, const float* __restrict__ n_, float* __restrict__ out) {
+    const int f = blockIdx.x;          // 0..39
+    const int j = threadIdx.x;         // 0..125 (125 = centre tap)
+    const float min_low = 50.f, min_band = 50.f, nyq = 8000.f;
+    float low = min_low + fabsf(low_hz_[f]);
+    float high = fminf(fmaxf(low + min_band + fabsf(band_hz_[f]), min_low), nyq);
+    float band = high - low;
+    float inv = 2.f * band;
+    float* cosf_row = out + (size_t)f * 251;
+    float* sinf_row = out + (size_t)(40 + f) * 251;
+    if (j == 125) {
+        cosf_row[125] = (2.f * band) / inv;
+        sinf_row[125] = 0.f / inv;
+        return;
+    }
+    if (j > 125) return;
+    float n = n_[j], w = window_[j];
+    float ft_low = low * n, ft_high = high * n;
+    float cl = ((sinf(ft_high) - sinf(ft_low)) / (n / 2.f)) * w;
+    float sl = ((cosf(ft_low) - cosf(ft_high)) / (n / 2.f)) * w;
+    cosf_row[j] = cl / inv;
+    cosf_row[250 - j] = cl / inv;
+    sinf_row[j] = sl / inv;
+    sinf_row[250 - j] = (-sl) / inv;
+}
+int sinc_filters_launch(const float* low, const float* band, const float* window, const float* n, float* out, cudaStream_t s) {
+    sinc_filters_kernel<<<40, 128, 0, s>>>(low, band, window, n, out);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// Conv1d weight (Cout, Cin, k) -> GEMM weight (Cout, k*Cin) matching channel-last rows
+__global__ void repack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int k, float* __restrict__ out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int tot = Cout * Cin * k;
+    if (idx >= tot) return;
+    int co = idx / (Cin * k), rem = idx % (Cin * k), kk = rem / Cin, ci = rem % Cin;
+    out[idx] = w[((size_t)co * Cin + ci) * k + kk];
+}
+int repack_conv_launch(const float* w, int Cout, int Cin, int k, float* out, cudaStream_t s) {
+    int tot = Cout * Cin * k;
+    repack_conv_kernel<<<(tot + 255) / 256, 256, 0, s>>>(w, Cout, Cin, k, out);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// ---------------------------------------------------------------- waveform instance norm
+// stats[b] = (sum, sumsq) in double
+__global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wav, int64_t N, int64_t stride,
+                                                         double* __restrict__ stats) {
+    const int b = blockIdx.y;
+    const float* row = wav + (int64_t)b * stride;
+    const int64_t chunk = 256 * 32;
+    int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, N);
+    float s = 0.f, q = 0.f;
+    for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+        float v = __ldg(row + i);
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    double ds = s, dq = q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    __shared__ double ps[8], pq[8];
+    if ((threadIdx.x & 31) == 0) { ps[threadIdx.x >> 5] = ds; pq[threadIdx.x >> 5] = dq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int i = 0; i < 8; ++i) { a += ps[i]; c += pq[i]; }
+        atomicAdd(stats + 2 * b, a);
+        atomicAdd(stats + 2 * b + 1, c);
+    }
+}
+__global__ void __launch_bounds__(256) wave_norm_kernel(const float* __restrict__ wav, int64_t N, int64_t stride,
+                                                        const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    double mean = stats[2 * b] / (double)N;
+    double var = stats[2 * b + 1] / (double)N - mean * mean;
+    float rstd = (float)(1.0 / sqrt(fmax(var, 0.0) + 1e-5));
+    float m = (float)mean, g = gamma[0], be = beta[0];
+    const float* row = wav + (int64_t)b * stride;
+    float* o = out + (int64_t)b * N;
+    for (int64_t i = (int64_t)blockIdx.x * 256 * 16 + threadIdx.x; i < min(N, ((int64_t)blockIdx.x + 1) * 256 * 16); i += 256)
+        o[i] = (row[i] - m) * rstd * g + be;
+}
+int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, const float* gamma, const float* beta,
+                         double* stats, float* out, cudaStream_t s) {
+    B200VAD_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B, s));
+    dim3 g1((unsigned)((N + 8191) / 8192), B);
+    wave_stats_kernel<<<g1, 256, 0, s>>>(wav, N, stride, stats);
+    B200VAD_LAUNCH_CHECK();
+    dim3 g2((unsigned)((N + 4095) / 4096), B);
+    wave_norm_kernel<<<g2, 256, 0, s>>>(wav, N, stride, stats, gamma, beta, out);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// ---------------------------------------------------------------- MaxPool1d(3,3) + InstanceNorm stats
+// in: (B, L, C) -> pooled (B, P, C), P = L / 3 (floor).  stats[(b*C + c)*2 + {0,1}] += sum, sumsq.
+constexpr int kPoolRows = 64;   // pooled rows per CTA
+__global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict__ in, int64_t L, int C, int64_t P,
+                                                         float* __restrict__ pooled, double* __restrict__ stats) {
+    const int b = blockIdx.y;
+    const int lanes = 256 / C;                 // row lanes (3 for C=80, 4 for C=60)
+    const int c = threadIdx.x % C, rl = threadIdx.x / C;
+    const int64_t p0 = (int64_t)blockIdx.x * kPoolRows;
+    float s = 0.f, q = 0.f;
+    if (rl < lanes) {
+        for (int64_t p = p0 + rl; p < min(P, p0 + kPoolRows); p += lanes) {
+            const float* src = in + ((int64_t)b * L + 3 * p) * C + c;
+            float v = fmaxf(fmaxf(__ldg(src), __ldg(src + C)), __ldg(src + 2 * C));
+            pooled[((int64_t)b * P + p) * C + c] = v;
+            s += v;
+            q = fmaf(v, v, q);
+        }
+    }
+    __shared__ float ss[256], sq[256];
+    ss[threadIdx.x] = s;
+    sq[threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double a = 0, d = 0;
+        for (int r = 0; r < lanes; ++r) { a += ss[r * C + threadIdx.x]; d += sq[r * C + threadIdx.x]; }
+        atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2, a);
+        atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2 + 1, d);
+    }
+}
+// in place: x = leaky_relu((x - mean) * rstd * gamma + beta)
+__global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, int64_t P, int C, const double* __restrict__ stats,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta) {
+    const int b = blockIdx.y;
+    __shared__ float sc[128], sh[128];
+    if (threadIdx.x < C) {
+        double mean = stats[((int64_t)b * C + threadIdx.x) * 2] / (double)P;
+        double var = stats[((int64_t)b * C + threadIdx.x) * 2 + 1] / (double)P - mean * mean;
+        float rstd = (float)(1.0 / sqrt(fmax(var, 0.0) + 1e-5));
+        float g = gamma[threadIdx.x];
+        sc[threadIdx.x] = rstd * g;
+        sh[threadIdx.x] = beta[threadIdx.x] - (float)mean * rstd * g;
+    }
+    __syncthreads();
+    const int64_t tot = P * C;
+    float* base = x + (int64_t)b * tot;
+    for (int64_t i = (int64_t)blockIdx.x * 256 * 16 + threadIdx.x; i < min(tot, ((int64_t)blockIdx.x + 1) * 256 * 16); i += 256) {
+        int c = (int)(i % C);
+        float v = fmaf(base[i], sc[c], sh[c]);
+        base[i] = v > 0.f ? v : 0.01f * v;
+    }
+}
+int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
+                           const float* beta, cudaStream_t s) {
+    if (C > 128 || C < 1) {
+        set_error("pool_norm: C must be in [1,128]");
+        return B200VAD_EINVAL;
+    }
+    const int64_t P = L / 3;
+    if (P <= 0 || B == 0) return B200VAD_OK;
+    B200VAD_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, s));
+    dim3 g1((unsigned)((P + kPoolRows - 1) / kPoolRows), B);
+    pool_stats_kernel<<<g1, 256, 0, s>>>(in, L, C, P, pooled, stats);
+    B200VAD_LAUNCH_CHECK();
+    dim3 g2((unsigned)((P * C + 4095) / 4096), B);
+    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+}  // namespace b200vad
