@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- audio-hours/sec of the VAD inference hot path (fbank + PyanNet2 forward +
+threshold/median + segments) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): a batch of 4096 x 8 s synthetic 16 kHz utterances per GPU
+(random-init PyanNet2, seed 42).  One "step" = one pass of the whole path over that batch.
+  value : whole-job audio-hours/sec with the waveforms already resident in HBM
+          (torch.ops.b200vad.vad_pipeline on device buffers), CUDA events, max over ranks.
+  e2e   : the same metric through the host-facing C ABI (b200vad_session_run_host): waveforms in
+          PINNED HOST memory, H2D copy of every step's input and D2H of its results inside the
+          timed region.
+  roofline : the dominant kernel (LSTM recurrence), timed live with CUDA events on its own stream
+          inside the timed region (b200vad_profile_*), algorithmic FLOPs / measured duration.
+  cpu_baseline : the oracle (CPU restatement of the reference path) on a bounded sample, rank 0, N=1.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port) instead.
+Multi-GPU: `torchrun --nproc-per-node N bench.py --gpus N ...`; utterances are sharded across ranks
+(no data-path collective), segment lists are gathered with NCCL inside the step; scaling = weak.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "universal-voice-activity-detection_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-hours/sec (fbank+VAD fwd)"
+UNIT = "audio-hours/s"
+ROWS, SECONDS = 4096, 8.0
+N_SAMPLES = int(SECONDS * 16000)
+T_FRAMES = (N_SAMPLES + 80) // 160
+# algorithmic FLOPs of the recurrence per frame: 4 layers x 2 dirs x (128 x 512 MACs) x 2 (SURVEY 8d / DESIGN.md)
+REC_FLOP_PER_FRAME = 4 * 2 * 128 * 512 * 2
+MODEL_FLOP_PER_FRAME = 2.884e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(sample_rows, steps, warmup, threads):
+    """The reference path on the host cores (oracle port): fbank -> PyanNet2 -> where/medfilt -> Python RLE."""
+    import torch
+    import oracle
+    from b200vad import synth
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    model = oracle.VadModel("PyanNet2", {"encoding_dim": 80}).eval()
+    wav = synth.noise_batch(sample_rows, N_SAMPLES, seed=1234)
+
+    def step():
+        with torch.no_grad():
+            feats = oracle.lhotse_fbank(wav)
+            dec = model.predict_step({"inputs": feats}).squeeze(-1)
+        segs = [oracle.rle_segments(dec[i].tolist(), 0.01) for i in range(dec.shape[0])]
+        return segs
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return (sample_rows * SECONDS / 3600.0) / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample_rows = 128
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    value, dt = cpu_reference(sample_rows, steps, warmup, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ROWS} x {SECONDS:.0f} s utterances, 16 kHz, fbank + PyanNet2 forward + median + segments",
+                       "sample": f"{sample_rows} x {SECONDS:.0f} s per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample_rows} x {SECONDS:.0f} s utterances per step, torch CPU threads={threads}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS, help="utterances per GPU per step (default = the named workload)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import b200vad
+    from b200vad import _lib, synth
+    from src.engines import VadModel
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the b200 path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    rows = args.rows
+    L = _lib.lib()
+
+    torch.manual_seed(42)
+    model = VadModel("PyanNet2", {"encoding_dim": 80}).eval()
+    blob = b200vad.pack_model(model.model.state_dict(), dev, 80, 4)
+    # this rank's shard of the global utterance list (weak scaling: `rows` per GPU)
+    lo, hi = b200vad.shard_range(rows * world, rank, world)
+    wav_host = synth.noise_batch(hi - lo, N_SAMPLES, seed=1234 + rank, pin=True)
+    wav_dev = wav_host.to(dev)
+    hours_step_global = rows * world * SECONDS / 3600.0
+
+    def device_step():
+        prob, dec, seg, counts = torch.ops.b200vad.vad_pipeline(wav_dev, None, blob, 4, 0.5, 49)
+        if world > 1:
+            seg = b200vad.gather_segments(seg, row_base=lo)
+        return seg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    for _ in range(warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.b200vad_launch_count()
+    L.b200vad_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        device_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.b200vad_launch_count() - launches0
+    tot_ms, nl = C.c_double(0), C.c_int(0)
+    _lib.check(L.b200vad_profile_collect(C.byref(tot_ms), C.byref(nl)), "profile_collect")
+    L.b200vad_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / steps
+    value = hours_step_global / (ms_per_step / 1e3)
+
+    # ---------------- end-to-end arm (host buffers through the C ABI session)
+    sess = b200vad.HostSession(blob, 4, N_SAMPLES, chunk_rows=1024, device=local)
+    out = {}
+
+    def e2e_step():
+        res = sess.run(wav_host, 0.5, 49, want_dec=True, want_prob=False, out=out)
+        seg = res["seg"]
+        if world > 1:
+            seg = b200vad.gather_segments(seg.to(dev), row_base=lo)
+        return res
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    nseg = 0
+    for _ in range(steps):
+        nseg = e2e_step()["seg"].shape[0]
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    # the session synchronises internally, so host wall time and device events bracket the same region
+    t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / steps
+    e2e_value = hours_step_global / (e2e_ms / 1e3)
+    h2d = wav_host.numel() * 4
+    d2h = (hi - lo) * T_FRAMES + nseg * 12 + 8 * ((hi - lo + 1023) // 1024)
+    sess.close()
+
+    if rank == 0:
+        peaks = load_peaks()
+        n_launch = max(nl.value, 1)
+        # each launch = one layer over one batch chunk; total algorithmic FLOPs of all launches in the timed region:
+        total_rec_flops = REC_FLOP_PER_FRAME * T_FRAMES * (hi - lo) * steps
+        avg_launch_ms = tot_ms.value / n_launch
+        achieved = total_rec_flops / n_launch / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else 0.0
+        peak = peaks["tf_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (fbank, activations, cell state in f32)", "data": "synthetic",
+            "config": {"workload": f"{rows} x {SECONDS:.0f} s synthetic 16 kHz utterances per GPU: fbank + PyanNet2 (4xBiLSTM128, random-init seed 42) "
+                                   "forward + threshold/median(49) + segments", "rows_per_gpu": rows, "samples_per_row": N_SAMPLES,
+                       "frames_per_row": T_FRAMES, "parallelism": f"utterance-sharded x{world}",
+                       "l2": f"inputs ({rows * N_SAMPLES * 4 / 1e9:.2f} GB waveforms + GBs of intermediates per step) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "api": "b200vad_session_run_host (pinned host waveforms -> host decisions + segments)"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "lstm_recurrent_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "launches": int(nl.value), "avg_launch_ms": avg_launch_ms,
+                         "share_of_step": tot_ms.value / (ms_per_step * steps) if ms_per_step > 0 else None,
+                         "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); kernel runs fp16 operands at the same tensor rate",
+                         "algorithmic_flops_per_frame": REC_FLOP_PER_FRAME},
+            "whole_model_tflops": MODEL_FLOP_PER_FRAME * T_FRAMES * (hi - lo) / (ms_per_step / 1e3) / 1e12,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.skip_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_reference(512, 1, 1, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"512 x {SECONDS:.0f} s utterances (oracle: torch CPU fbank + nn.LSTM + scipy medfilt + Python RLE), {dt:.1f} s/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

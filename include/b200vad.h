@@ -40,6 +40,13 @@ extern "C" {
 B200VAD_API int b200vad_abi_version(void);
 B200VAD_API const char* b200vad_last_error(void);
 
+/* Instrumentation used by bench.py: number of kernels this library has launched in this
+ * process, and CUDA-event timing of the dominant kernel (the LSTM recurrence) on its own stream.
+ * profile_collect synchronises on the recorded events, sums their durations and resets. */
+B200VAD_API long long b200vad_launch_count(void);
+B200VAD_API void b200vad_profile_enable(int on);
+B200VAD_API int b200vad_profile_collect(double* total_ms, int* launches);
+
 /* Build the per-device constant tables (povey window, FFT twiddles, Kaldi mel triangles).
  * Allocates a few KB of device memory once per device.  Must precede any fbank call. */
 B200VAD_API int b200vad_init(int device);

@@ -35,7 +35,7 @@ def make_oracle(model_name="PyanNet2", model_dict=None, seed=42, spread=False, f
                 y = torch.nn.functional.leaky_relu(lin(y))
             z = net.classifier(y)
             mu, sd = z.mean(), z.std().clamp_min(1e-6)
-            scale = 2.0 / sd
+            scale = 0.5 / sd     # logits ~ N(0, 0.5): p spans about (0.2, 0.8)
             net.classifier.weight.mul_(scale)
             net.classifier.bias.copy_((net.classifier.bias - mu) * scale)
     return m

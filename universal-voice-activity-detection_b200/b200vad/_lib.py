@@ -22,6 +22,9 @@ c_void_p, c_int, c_int64, c_size_t, c_float, c_double = C.c_void_p, C.c_int, C.c
 PROTOTYPES = {
     "b200vad_abi_version": (c_int, []),
     "b200vad_last_error": (C.c_char_p, []),
+    "b200vad_launch_count": (C.c_longlong, []),
+    "b200vad_profile_enable": (None, [c_int]),
+    "b200vad_profile_collect": (c_int, [C.POINTER(c_double), C.POINTER(c_int)]),
     "b200vad_init": (c_int, [c_int]),
     "b200vad_fbank_num_frames": (c_int64, [c_int64]),
     "b200vad_fbank_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),

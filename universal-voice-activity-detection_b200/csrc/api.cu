@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 namespace b200vad {
@@ -14,6 +17,31 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+static std::mutex g_prof_mu;
+void prof_begin(cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_used == g_prof_events.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        g_prof_events.emplace_back(a, b);
+    }
+    cudaEventRecord(g_prof_events[g_prof_used].first, st);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof_events[g_prof_used].second, st);
+    ++g_prof_used;
 }
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -53,8 +81,8 @@ static ModelLayout model_layout(int D, int L) {
     return m;
 }
 
-// bytes of workspace per (sequence, frame): xg fp32 [1024] + two fp16 layer buffers [256]
-constexpr size_t kModelBytesPerFrame = sizeof(float) * 2 * kGates + 2 * sizeof(__half) * 2 * kHidden;
+// bytes of workspace per (sequence, frame): xg fp32 [1024] + two fp32 layer buffers [256]
+constexpr size_t kModelBytesPerFrame = sizeof(float) * 2 * kGates + 2 * sizeof(float) * 2 * kHidden;
 
 static int model_forward(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
@@ -65,7 +93,7 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
     B200VAD_CHECK_ARG(T < (1 << 24), "T too large");
     const ModelLayout m = model_layout(D, L);
     const char* pk = reinterpret_cast<const char*>(packed);
-    const size_t per_row = align_up((size_t)T * kModelBytesPerFrame) + 512;
+    const size_t per_row = align_up((size_t)T * kModelBytesPerFrame) + 768;
     int64_t Bc = (int64_t)(ws_bytes / per_row);
     // one GEMM launch handles < 65535*128 rows
     Bc = std::min<int64_t>(Bc, (int64_t)(65000LL * 128 / T));
@@ -79,11 +107,10 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
         const int64_t rows = (int64_t)bc * T;
         char* w = reinterpret_cast<char*>(ws);
         float* xg = reinterpret_cast<float*>(w);
-        __half* y0 = reinterpret_cast<__half*>(w + align_up(sizeof(float) * 2 * kGates * rows));
-        __half* y1 = reinterpret_cast<__half*>(reinterpret_cast<char*>(y0) + align_up(sizeof(__half) * 2 * kHidden * rows));
+        float* y0 = reinterpret_cast<float*>(w + align_up(sizeof(float) * 2 * kGates * rows));
+        float* y1 = reinterpret_cast<float*>(reinterpret_cast<char*>(y0) + align_up(sizeof(float) * 2 * kHidden * rows));
         const void* in = x + b0 * T * D;
-        int in_half = 0;
-        __half* out = y0;
+        float* out = y0;
         for (int l = 0; l < L; ++l) {
             const LayerOff& lo = m.layers[l];
             GemmArgs g;
@@ -93,11 +120,11 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
             g.W_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
             g.bias = reinterpret_cast<const float*>(pk + lo.bias);
             g.C = xg; g.ldc = 2 * kGates; g.c_half = 0; g.act = 0;
-            int rc = gemm_launch(g, in_half, in_half ? 2 : 3, st);
+            int rc = gemm_launch(g, 0, 3, st);
             if (rc) return rc;
             rc = lstm_recurrent_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), out, bc, (int)T, st);
             if (rc) return rc;
-            in = out; in_half = 1;
+            in = out;
             out = (out == y0) ? y1 : y0;
         }
         // head: Linear(256,128)+lrelu -> Linear(128,128)+lrelu -> Linear(128,1)+sigmoid; z buffers alias xg
@@ -109,7 +136,7 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
         g.W_hi = reinterpret_cast<const __half*>(pk + m.w1_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w1_lo);
         g.bias = reinterpret_cast<const float*>(pk + m.b1);
         g.C = z1; g.ldc = kHidden; g.c_half = 0; g.act = 1;
-        int rc = gemm_launch(g, 1, 2, st);
+        int rc = gemm_launch(g, 0, 3, st);
         if (rc) return rc;
         g.A = z1; g.lda = kHidden; g.K = kHidden; g.Kp = kHidden;
         g.W_hi = reinterpret_cast<const __half*>(pk + m.w2_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w2_lo);
@@ -182,6 +209,29 @@ extern "C" {
 int b200vad_abi_version(void) { return B200VAD_ABI_VERSION; }
 const char* b200vad_last_error(void) { return g_err; }
 
+long long b200vad_launch_count(void) { return g_launches.load(); }
+
+void b200vad_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    g_prof_used = 0;
+}
+
+int b200vad_profile_collect(double* total_ms, int* launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double tot = 0.0;
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        B200VAD_CUDA(cudaEventSynchronize(g_prof_events[i].second));
+        float ms = 0.f;
+        B200VAD_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = (int)g_prof_used;
+    g_prof_used = 0;
+    return B200VAD_OK;
+}
+
 int b200vad_init(int device) {
     int n = 0;
     B200VAD_CUDA(cudaGetDeviceCount(&n));
@@ -253,7 +303,7 @@ int b200vad_model_pack_head(void* packed, int D, int L, const float* w1, const f
 
 size_t b200vad_model_workspace_bytes(int B, int64_t T) {
     if (B <= 0 || T <= 0) return 0;
-    return (size_t)B * (align_up((size_t)T * kModelBytesPerFrame) + 512) + 4096;
+    return (size_t)B * (align_up((size_t)T * kModelBytesPerFrame) + 768) + 4096;
 }
 
 int b200vad_model_forward_f32(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,

@@ -14,6 +14,11 @@
 namespace b200vad {
 
 void set_error(const char* fmt, ...);
+void count_launch();                       // bumps the process-wide kernel-launch counter
+// live timing of the dominant kernel (bench.py roofline): when enabled, every launch of the
+// recurrent kernel is bracketed by CUDA events on its own stream
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st);
 
 #define B200VAD_CHECK_ARG(cond, msg)                                   \
     do {                                                               \
@@ -39,6 +44,7 @@ void set_error(const char* fmt, ...);
             b200vad::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
             return B200VAD_ECUDA;                                      \
         }                                                              \
+        b200vad::count_launch();                                       \
     } while (0)
 
 // model / feature constants (reference: lhotse FbankConfig defaults; PyanNet2.py:60-67)

@@ -23,7 +23,7 @@ int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, 
 int fbank_tables_init(int device);
 int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, int64_t T_out,
                  double* row_sums, int device, cudaStream_t stream);
-int lstm_recurrent_launch(const float* xg, const __half* whh, __half* y, int B, int T, cudaStream_t stream);
+int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, int T, cudaStream_t stream);
 int classifier_launch(const float* z, int64_t rows, const float* wc, const float* bc, float* prob, cudaStream_t stream);
 int pack_whh(const float* w, __half* out, cudaStream_t stream);
 int add_bias(const float* a, const float* b, float* out, int n, cudaStream_t stream);

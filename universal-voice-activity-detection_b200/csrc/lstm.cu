@@ -8,7 +8,8 @@
 // W_hh (512x128 fp16) stays resident in shared memory for all T steps, each of 16 warps owns
 // 8 hidden units x 4 gates so that i,f,g,o of a cell land in the same thread's accumulators,
 // the cell state lives in registers (fp32), h_t goes to shared memory (fp16 operand of the
-// next step) and to HBM (fp16 layer output).  xg for step t+1 is prefetched during step t.
+// next step) and to HBM (fp32 layer output: rounding the layer outputs to fp16 is the
+// dominant error term of the stack, see DESIGN.md 'precision').  xg for step t+1 is prefetched during step t.
 #include "kernels.cuh"
 
 namespace b200vad {
@@ -22,9 +23,9 @@ struct RecSmem {
     __half h[2][RB * RLD];             // double-buffered hidden state
 };
 
-// xg: [B][T][2][512] fp32;  y: [B][T][256] fp16;  whh: [2][512][128] fp16
+// xg: [B][T][2][512] fp32;  y: [B][T][256] fp32;  whh: [2][512][128] fp16
 __global__ void __launch_bounds__(RTHREADS, 1)
-lstm_recurrent_kernel(const float* __restrict__ xg, const __half* __restrict__ whh, __half* __restrict__ y, int B, int T) {
+lstm_recurrent_kernel(const float* __restrict__ xg, const __half* __restrict__ whh, float* __restrict__ y, int B, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RecSmem& sm = *reinterpret_cast<RecSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -127,20 +128,23 @@ lstm_recurrent_kernel(const float* __restrict__ xg, const __half* __restrict__ w
                 int r = mt * 16 + g + hh * 8;
                 *reinterpret_cast<__half2*>(&hn[r * RLD + u0 + 2 * t4]) = h2;
                 if (rowok[mt][hh])
-                    *reinterpret_cast<__half2*>(&y[(rowbase[mt][hh] + t) * (2 * kHidden) + dir * kHidden + u0 + 2 * t4]) = h2;
+                    *reinterpret_cast<float2*>(&y[(rowbase[mt][hh] + t) * (2 * kHidden) + dir * kHidden + u0 + 2 * t4]) =
+                        make_float2(hv[0], hv[1]);
             }
         __syncthreads();
     }
 }
 
-int lstm_recurrent_launch(const float* xg, const __half* whh, __half* y, int B, int T, cudaStream_t stream) {
+int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, int T, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         B200VAD_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RecSmem)));
         attr_set = true;
     }
     dim3 grid((B + RB - 1) / RB, 2);
+    prof_begin(stream);
     lstm_recurrent_kernel<<<grid, RTHREADS, sizeof(RecSmem), stream>>>(xg, whh, y, B, T);
+    prof_end(stream);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }
