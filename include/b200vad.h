@@ -45,7 +45,13 @@ B200VAD_API const char* b200vad_last_error(void);
  * profile_collect synchronises on the recorded events, sums their durations and resets. */
 B200VAD_API long long b200vad_launch_count(void);
 B200VAD_API void b200vad_profile_enable(int on);
-B200VAD_API int b200vad_profile_collect(double* total_ms, int* launches);
+B200VAD_API int b200vad_profile_collect(int kind /* 0 = LSTM recurrence, 1 = projection GEMM */, double* total_ms, int* launches);
+/* 2 = tcgen05 kernels (default); 1 = the warp-MMA kernels kept for cross-validation of the tcgen05 path */
+B200VAD_API int b200vad_set_impl(int impl);
+/* Split-precision linear layer on the tcgen05 GEMM: c[M,N] = a[M,K] . w[N,K]^T + bias, fp32 in / out, operands
+ * split into fp16 (hi, lo) planes in `ws` (K % 8 == 0, N % 128 == 0; weights must fit in shared memory). */
+B200VAD_API int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo,
+                             float* c, void* ws, size_t ws_bytes, void* stream);
 
 /* Build the per-device constant tables (povey window, FFT twiddles, Kaldi mel triangles).
  * Allocates a few KB of device memory once per device.  Must precede any fbank call. */

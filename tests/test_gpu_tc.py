@@ -1,0 +1,73 @@
+"""GPU tests of the tcgen05 kernels in isolation: the split-precision GEMM against an fp64 matmul and
+the tcgen05 model path against the warp-MMA path and the oracle."""
+import ctypes as C
+
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import b200vad
+    b200vad._lib.init(0)
+    return torch.device("cuda:0")
+
+
+def _linear(dev, a, w, bias, use_lo):
+    import b200vad
+    L = b200vad.lib()
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty((M, N), dtype=torch.float32, device=dev)
+    ws = torch.empty(4 * (M * K + N * (K + 64)) + 4096, dtype=torch.uint8, device=dev)
+    b200vad._lib.check(L.b200vad_linear_split_f32(a.data_ptr(), M, K, w.data_ptr(), N, bias.data_ptr(), int(use_lo), c.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "linear_split")
+    torch.cuda.synchronize()
+    return c
+
+
+@pytest.mark.parametrize("M,K,N,use_lo", [(128, 64, 256, 1), (1000, 80, 1024, 1), (4096, 256, 1024, 0), (333, 128, 128, 1),
+                                          (70000, 256, 1024, 0)])
+def test_gemm_tc_matches_fp64(dev, M, K, N, use_lo):
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g) * (5.0 if K == 80 else 0.3)
+    w = (torch.rand(N, K, generator=g) - 0.5) * 0.17
+    bias = torch.randn(N, generator=g) * 0.1
+    ref = a.double() @ w.double().t() + bias.double()
+    c = _linear(dev, a.to(dev), w.to(dev), bias.to(dev), use_lo).cpu().double()
+    scale = (a.double().abs() @ w.double().abs().t()).clamp_min(1e-6)
+    err = ((c - ref).abs() / scale).max().item()
+    # 3-term split: ~2^-21 relative to sum |a||w|; 2-term (no W_lo): weight rounding 2^-12 remains
+    assert err < (2e-6 if use_lo else 3e-4), err
+
+
+@pytest.mark.parametrize("B,T", [(3, 50), (64, 100), (130, 333)])
+def test_tc_model_matches_warp_mma_and_oracle(dev, B, T):
+    import b200vad
+    import oracle
+    wav = util.synth_wave(min(B, 4), T * 160, seed=T)
+    feats = oracle.lhotse_fbank(wav)
+    feats = feats.repeat((B + feats.shape[0] - 1) // feats.shape[0], 1, 1)[:B]
+    feats = feats + 0.01 * torch.randn(feats.shape, generator=torch.Generator().manual_seed(B))
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=feats)
+    with torch.no_grad():
+        ref = o(feats).squeeze(-1)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    L = b200vad.lib()
+    try:
+        b200vad._lib.check(L.b200vad_set_impl(1), "set_impl")
+        p1 = torch.ops.b200vad.lstm_head(feats.to(dev), blob, 4).cpu()
+        b200vad._lib.check(L.b200vad_set_impl(2), "set_impl")
+        p2 = torch.ops.b200vad.lstm_head(feats.to(dev), blob, 4).cpu()
+    finally:
+        L.b200vad_set_impl(2)
+    e1, e2 = util.prob_err(p1, ref), util.prob_err(p2, ref)
+    print(f"B={B} T={T}: warp-MMA rel err {e1:.2e}, tcgen05 rel err {e2:.2e}")
+    assert e2 <= util.PROB_RTOL, e2
+    assert e1 <= util.PROB_RTOL, e1

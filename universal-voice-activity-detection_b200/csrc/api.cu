@@ -23,29 +23,45 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static bool g_prof_on = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct ProfRec { cudaEvent_t a, b; int kind; };
+static std::vector<ProfRec> g_prof_events;
 static size_t g_prof_used = 0;
 static std::mutex g_prof_mu;
-void prof_begin(cudaStream_t st) {
+void prof_begin(int kind, cudaStream_t st) {
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (g_prof_used == g_prof_events.size()) {
-        cudaEvent_t a, b;
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
-        g_prof_events.emplace_back(a, b);
+        ProfRec r;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        r.kind = 0;
+        g_prof_events.push_back(r);
     }
-    cudaEventRecord(g_prof_events[g_prof_used].first, st);
+    g_prof_events[g_prof_used].kind = kind;
+    cudaEventRecord(g_prof_events[g_prof_used].a, st);
 }
-void prof_end(cudaStream_t st) {
+void prof_end(int kind, cudaStream_t st) {
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    cudaEventRecord(g_prof_events[g_prof_used].second, st);
+    (void)kind;
+    cudaEventRecord(g_prof_events[g_prof_used].b, st);
     ++g_prof_used;
 }
 
+static int g_impl = 2;        // 2 = tcgen05 kernels (default), 1 = warp-MMA kernels (validation only)
+static int num_sms_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-static inline int round32(int k) { return (k + 31) / 32 * 32; }
+static inline int round64(int k) { return (k + 63) / 64 * 64; }
 
 // ---------------------------------------------------------------- packed model layout
 struct LayerOff {
@@ -62,7 +78,7 @@ static ModelLayout model_layout(int D, int L) {
     for (int l = 0; l < L; ++l) {
         LayerOff o;
         o.D = (l == 0) ? D : 2 * kHidden;
-        o.Kp = round32(o.D);
+        o.Kp = round64(o.D);
         o.wih_hi = off; off = align_up(off + sizeof(__half) * 2 * kGates * o.Kp);
         o.wih_lo = off; off = align_up(off + sizeof(__half) * 2 * kGates * o.Kp);
         o.bias = off;   off = align_up(off + sizeof(float) * 2 * kGates);
@@ -81,8 +97,33 @@ static ModelLayout model_layout(int D, int L) {
     return m;
 }
 
-// bytes of workspace per (sequence, frame): xg fp32 [1024] + two fp32 layer buffers [256]
-constexpr size_t kModelBytesPerFrame = sizeof(float) * 2 * kGates + 2 * sizeof(float) * 2 * kHidden;
+// Workspace per (sequence, frame): xg fp32 [1024] + two layer buffers of 1024 bytes each (either a
+// fp32 [256] row or the fp16 hi / lo planes [256] + [256]) + the fp16 hi / lo planes of the layer-0 input.
+static inline size_t round8(size_t d) { return (d + 7) / 8 * 8; }
+static inline size_t model_bytes_per_frame(int D) {
+    return sizeof(float) * 2 * kGates + 2 * sizeof(float) * 2 * kHidden + 2 * sizeof(__half) * round8(D);
+}
+static inline size_t model_per_row(int D, int64_t T) { return align_up((size_t)T * model_bytes_per_frame(D)) + 1536; }
+
+static int head_forward(const ModelLayout& m, const char* pk, const float* y, int64_t rows, float* z1, float* z2, float* prob,
+                        cudaStream_t st) {
+    // Linear(256,128)+lrelu -> Linear(128,128)+lrelu -> Linear(128,1)+sigmoid (PyanNet2.py:183-187)
+    GemmArgs g;
+    g.A = y; g.lda = 2 * kHidden; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
+    g.N = kHidden; g.K = 2 * kHidden; g.Kp = 2 * kHidden;
+    g.W_hi = reinterpret_cast<const __half*>(pk + m.w1_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w1_lo);
+    g.bias = reinterpret_cast<const float*>(pk + m.b1);
+    g.C = z1; g.ldc = kHidden; g.c_half = 0; g.act = 1;
+    int rc = gemm_launch(g, 0, 3, st);
+    if (rc) return rc;
+    g.A = z1; g.lda = kHidden; g.K = kHidden; g.Kp = kHidden;
+    g.W_hi = reinterpret_cast<const __half*>(pk + m.w2_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w2_lo);
+    g.bias = reinterpret_cast<const float*>(pk + m.b2);
+    g.C = z2;
+    rc = gemm_launch(g, 0, 3, st);
+    if (rc) return rc;
+    return classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc), prob, st);
+}
 
 static int model_forward(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
@@ -93,60 +134,88 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
     B200VAD_CHECK_ARG(T < (1 << 24), "T too large");
     const ModelLayout m = model_layout(D, L);
     const char* pk = reinterpret_cast<const char*>(packed);
-    const size_t per_row = align_up((size_t)T * kModelBytesPerFrame) + 768;
+    const size_t per_row = model_per_row(D, T);
     int64_t Bc = (int64_t)(ws_bytes / per_row);
-    // one GEMM launch handles < 65535*128 rows
-    Bc = std::min<int64_t>(Bc, (int64_t)(65000LL * 128 / T));
+    Bc = std::min<int64_t>(Bc, (int64_t)(65000LL * 128 / T));   // one warp-MMA GEMM launch handles < 65535*128 rows
     Bc = std::min<int64_t>(Bc, B);
+    if (Bc >= 64) Bc = Bc / 64 * 64;                            // whole recurrent CTAs
     if (Bc < 1) {
         set_error("model_forward: workspace too small (%zu bytes; need >= %zu per sequence)", ws_bytes, per_row);
         return B200VAD_ENOMEM;
     }
+    const int D8 = (int)round8(D);
+    const int sms = num_sms_cached();
     for (int64_t b0 = 0; b0 < B; b0 += Bc) {
         const int bc = (int)std::min<int64_t>(Bc, B - b0);
         const int64_t rows = (int64_t)bc * T;
         char* w = reinterpret_cast<char*>(ws);
-        float* xg = reinterpret_cast<float*>(w);
-        float* y0 = reinterpret_cast<float*>(w + align_up(sizeof(float) * 2 * kGates * rows));
-        float* y1 = reinterpret_cast<float*>(reinterpret_cast<char*>(y0) + align_up(sizeof(float) * 2 * kHidden * rows));
-        const void* in = x + b0 * T * D;
-        float* out = y0;
+        float* xg = reinterpret_cast<float*>(w);                 w += align_up(sizeof(float) * 2 * kGates * rows);
+        char* buf0 = w;                                          w += align_up(sizeof(float) * 2 * kHidden * rows);
+        char* buf1 = w;                                          w += align_up(sizeof(float) * 2 * kHidden * rows);
+        __half* x_hi = reinterpret_cast<__half*>(w);             w += align_up(sizeof(__half) * D8 * rows);
+        __half* x_lo = reinterpret_cast<__half*>(w);
+        const float* xin = x + b0 * T * D;
+        int rc;
+        if (g_impl == 1) {
+            // ---- warp-MMA validation path: fp32 activations between layers
+            const float* in = xin;
+            float* out = reinterpret_cast<float*>(buf0);
+            for (int l = 0; l < L; ++l) {
+                const LayerOff& lo = m.layers[l];
+                GemmArgs g;
+                g.A = in; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
+                g.N = 2 * kGates; g.K = lo.D; g.Kp = lo.Kp;
+                g.W_hi = reinterpret_cast<const __half*>(pk + lo.wih_hi);
+                g.W_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
+                g.bias = reinterpret_cast<const float*>(pk + lo.bias);
+                g.C = xg; g.ldc = 2 * kGates; g.c_half = 0; g.act = 0;
+                if ((rc = gemm_launch(g, 0, 3, st))) return rc;
+                if ((rc = lstm_recurrent_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), out, bc, (int)T, st))) return rc;
+                in = out;
+                out = (out == reinterpret_cast<float*>(buf0)) ? reinterpret_cast<float*>(buf1) : reinterpret_cast<float*>(buf0);
+            }
+            if ((rc = head_forward(m, pk, in, rows, xg, xg + rows * kHidden, prob + b0 * T, st))) return rc;
+            continue;
+        }
+        // ---- tcgen05 path: activations travel between layers as fp16 (hi, lo) planes
+        const bool d_ok = (D % 8 == 0);
+        if (d_ok) {
+            if ((rc = split_planes_launch(xin, rows * D, x_hi, x_lo, st))) return rc;
+        }
+        const __half* a_hi = x_hi;
+        const __half* a_lo = x_lo;
+        int64_t lda = D;
+        char* outbuf = buf0;
+        const float* y_last = nullptr;
         for (int l = 0; l < L; ++l) {
             const LayerOff& lo = m.layers[l];
-            GemmArgs g;
-            g.A = in; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
-            g.N = 2 * kGates; g.K = lo.D; g.Kp = lo.Kp;
-            g.W_hi = reinterpret_cast<const __half*>(pk + lo.wih_hi);
-            g.W_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
-            g.bias = reinterpret_cast<const float*>(pk + lo.bias);
-            g.C = xg; g.ldc = 2 * kGates; g.c_half = 0; g.act = 0;
-            int rc = gemm_launch(g, 0, 3, st);
-            if (rc) return rc;
-            rc = lstm_recurrent_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), out, bc, (int)T, st);
-            if (rc) return rc;
-            in = out;
-            out = (out == y0) ? y1 : y0;
+            const __half* w_hi = reinterpret_cast<const __half*>(pk + lo.wih_hi);
+            const __half* w_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
+            const float* bias = reinterpret_cast<const float*>(pk + lo.bias);
+            // hi + lo weight planes stay resident in smem (128- or 256-column ranges, chosen by the launcher)
+            const bool fits1 = (size_t)2 * 128 * lo.Kp * 2 <= 128 * 1024;
+            if ((l > 0 || d_ok) && fits1) {
+                if ((rc = gemm_tc_launch(a_hi, a_lo, lda, rows, lo.D, w_hi, w_lo, lo.Kp, 2 * kGates, bias, xg,
+                                         2 * kGates, sms, st))) return rc;
+            } else {
+                // shapes the resident-weight kernel cannot hold (e.g. 768-dim SSL features): warp-MMA GEMM on the fp32 input
+                if (l > 0) { set_error("model_forward: internal layer width unsupported"); return B200VAD_EINVAL; }
+                GemmArgs g;
+                g.A = xin; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
+                g.N = 2 * kGates; g.K = lo.D; g.Kp = lo.Kp; g.W_hi = w_hi; g.W_lo = w_lo; g.bias = bias;
+                g.C = xg; g.ldc = 2 * kGates; g.c_half = 0; g.act = 0;
+                if ((rc = gemm_launch(g, 0, 3, st))) return rc;
+            }
+            const bool last = (l == L - 1);
+            __half* yh = reinterpret_cast<__half*>(outbuf);
+            __half* yl = yh + rows * 2 * kHidden;
+            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), last ? nullptr : yh, last ? nullptr : yl,
+                                     last ? reinterpret_cast<float*>(outbuf) : nullptr, bc, (int)T, st))) return rc;
+            if (last) y_last = reinterpret_cast<const float*>(outbuf);
+            a_hi = yh; a_lo = yl; lda = 2 * kHidden;
+            outbuf = (outbuf == buf0) ? buf1 : buf0;
         }
-        // head: Linear(256,128)+lrelu -> Linear(128,128)+lrelu -> Linear(128,1)+sigmoid; z buffers alias xg
-        float* z1 = xg;
-        float* z2 = xg + rows * kHidden;
-        GemmArgs g;
-        g.A = in; g.lda = 2 * kHidden; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
-        g.N = kHidden; g.K = 2 * kHidden; g.Kp = 2 * kHidden;
-        g.W_hi = reinterpret_cast<const __half*>(pk + m.w1_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w1_lo);
-        g.bias = reinterpret_cast<const float*>(pk + m.b1);
-        g.C = z1; g.ldc = kHidden; g.c_half = 0; g.act = 1;
-        int rc = gemm_launch(g, 0, 3, st);
-        if (rc) return rc;
-        g.A = z1; g.lda = kHidden; g.K = kHidden; g.Kp = kHidden;
-        g.W_hi = reinterpret_cast<const __half*>(pk + m.w2_hi); g.W_lo = reinterpret_cast<const __half*>(pk + m.w2_lo);
-        g.bias = reinterpret_cast<const float*>(pk + m.b2);
-        g.C = z2;
-        rc = gemm_launch(g, 0, 3, st);
-        if (rc) return rc;
-        rc = classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc),
-                               prob + b0 * T, st);
-        if (rc) return rc;
+        if ((rc = head_forward(m, pk, y_last, rows, xg, xg + rows * kHidden, prob + b0 * T, st))) return rc;
     }
     return B200VAD_OK;
 }
@@ -214,21 +283,29 @@ long long b200vad_launch_count(void) { return g_launches.load(); }
 void b200vad_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = on != 0;
-    g_prof_used = 0;
+    g_prof_used = 0;      // (re)starts a collection window
 }
 
-int b200vad_profile_collect(double* total_ms, int* launches) {
+int b200vad_profile_collect(int kind, double* total_ms, int* launches) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     double tot = 0.0;
+    int n = 0;
     for (size_t i = 0; i < g_prof_used; ++i) {
-        B200VAD_CUDA(cudaEventSynchronize(g_prof_events[i].second));
+        if (g_prof_events[i].kind != kind) continue;
+        B200VAD_CUDA(cudaEventSynchronize(g_prof_events[i].b));
         float ms = 0.f;
-        B200VAD_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+        B200VAD_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].a, g_prof_events[i].b));
         tot += ms;
+        ++n;
     }
     if (total_ms) *total_ms = tot;
-    if (launches) *launches = (int)g_prof_used;
-    g_prof_used = 0;
+    if (launches) *launches = n;
+    return B200VAD_OK;
+}
+
+int b200vad_set_impl(int impl) {
+    B200VAD_CHECK_ARG(impl == 1 || impl == 2, "impl must be 1 (warp-MMA) or 2 (tcgen05)");
+    g_impl = impl;
     return B200VAD_OK;
 }
 
@@ -303,12 +380,35 @@ int b200vad_model_pack_head(void* packed, int D, int L, const float* w1, const f
 
 size_t b200vad_model_workspace_bytes(int B, int64_t T) {
     if (B <= 0 || T <= 0) return 0;
-    return (size_t)B * (align_up((size_t)T * kModelBytesPerFrame) + 768) + 4096;
+    return (size_t)B * model_per_row(768, T) + 4096;   /* sized for the widest supported input (D <= 768) */
 }
 
 int b200vad_model_forward_f32(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
                               size_t ws_bytes, void* stream) {
     return model_forward(packed, D, L, x, B, T, prob, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo, float* c,
+                             void* ws, size_t ws_bytes, void* stream) {
+    B200VAD_CHECK_ARG(a && w && c && ws, "null pointer");
+    B200VAD_CHECK_ARG(M >= 0 && K > 0 && K % 8 == 0 && N > 0 && N % 128 == 0, "need K % 8 == 0 and N % 128 == 0");
+    B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+    const int Kp = round64(K);
+    const size_t need = 2 * align_up(sizeof(__half) * M * K) + 2 * align_up(sizeof(__half) * (size_t)N * Kp);
+    if (ws_bytes < need) {
+        set_error("linear_split: workspace too small (%zu < %zu)", ws_bytes, need);
+        return B200VAD_ENOMEM;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* p = reinterpret_cast<char*>(ws);
+    __half* a_hi = reinterpret_cast<__half*>(p); p += align_up(sizeof(__half) * M * K);
+    __half* a_lo = reinterpret_cast<__half*>(p); p += align_up(sizeof(__half) * M * K);
+    __half* w_hi = reinterpret_cast<__half*>(p); p += align_up(sizeof(__half) * (size_t)N * Kp);
+    __half* w_lo = reinterpret_cast<__half*>(p);
+    int rc = split_planes_launch(a, M * K, a_hi, a_lo, st);
+    if (rc) return rc;
+    if ((rc = split_weights(w, N, K, Kp, w_hi, w_lo, st))) return rc;
+    return gemm_tc_launch(a_hi, a_lo, K, M, K, w_hi, use_w_lo ? w_lo : nullptr, Kp, N, bias, c, N, num_sms_cached(), st);
 }
 
 // ---------------------------------------------------------------- SincNet

@@ -15,10 +15,10 @@ namespace b200vad {
 
 void set_error(const char* fmt, ...);
 void count_launch();                       // bumps the process-wide kernel-launch counter
-// live timing of the dominant kernel (bench.py roofline): when enabled, every launch of the
-// recurrent kernel is bracketed by CUDA events on its own stream
-void prof_begin(cudaStream_t st);
-void prof_end(cudaStream_t st);
+// live timing of the hot kernels (bench.py roofline): when enabled, every launch of kind
+// 0 = LSTM recurrence, 1 = projection GEMM is bracketed by CUDA events on its own stream
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
 
 #define B200VAD_CHECK_ARG(cond, msg)                                   \
     do {                                                               \

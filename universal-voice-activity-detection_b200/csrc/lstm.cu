@@ -142,9 +142,9 @@ int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, i
         attr_set = true;
     }
     dim3 grid((B + RB - 1) / RB, 2);
-    prof_begin(stream);
+    prof_begin(0, stream);
     lstm_recurrent_kernel<<<grid, RTHREADS, sizeof(RecSmem), stream>>>(xg, whh, y, B, T);
-    prof_end(stream);
+    prof_end(0, stream);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }
