@@ -38,6 +38,8 @@ N_SAMPLES = int(SECONDS * 16000)
 T_FRAMES = (N_SAMPLES + 80) // 160
 # algorithmic FLOPs of the recurrence per frame: 4 layers x 2 dirs x (128 x 512 MACs) x 2 (SURVEY 8d / DESIGN.md)
 REC_FLOP_PER_FRAME = 4 * 2 * 128 * 512 * 2
+# input projections (80 + 3*256) x 1024 MACs + head (256*128 + 128*128 + 128) MACs, x2
+PROJ_FLOP_PER_FRAME = 2 * ((80 + 3 * 256) * 1024 + 256 * 128 + 128 * 128 + 128)
 MODEL_FLOP_PER_FRAME = 2.884e6
 
 
@@ -211,8 +213,11 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = L.b200vad_launch_count() - launches0
-    tot_ms, nl = C.c_double(0), C.c_int(0)
-    _lib.check(L.b200vad_profile_collect(C.byref(tot_ms), C.byref(nl)), "profile_collect")
+    prof = {}
+    for kind, name in ((0, "lstm_tc_kernel (LSTM recurrence)"), (1, "gemm_tc_kernel + gemm_kernel (input projections + head linears)")):
+        tot_ms, nl = C.c_double(0), C.c_int(0)
+        _lib.check(L.b200vad_profile_collect(kind, C.byref(tot_ms), C.byref(nl)), "profile_collect")
+        prof[kind] = (name, tot_ms.value, nl.value)
     L.b200vad_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -255,11 +260,17 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        n_launch = max(nl.value, 1)
-        # each launch = one layer over one batch chunk; total algorithmic FLOPs of all launches in the timed region:
-        total_rec_flops = REC_FLOP_PER_FRAME * T_FRAMES * (hi - lo) * steps
-        avg_launch_ms = tot_ms.value / n_launch
-        achieved = total_rec_flops / n_launch / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else 0.0
+        frames = T_FRAMES * (hi - lo) * steps
+        # algorithmic FLOPs per frame: recurrence 4 layers x 2 dirs x 512 x 128 MACs; projections + head linears
+        flops = {0: REC_FLOP_PER_FRAME, 1: PROJ_FLOP_PER_FRAME}
+        dom = max(prof, key=lambda k: prof[k][1])
+        kernels = {}
+        for k, (name, tms, n) in prof.items():
+            ach = flops[k] * frames / (tms / 1e3) / 1e12 if tms > 0 else 0.0
+            kernels[name] = {"launches": n, "total_ms": tms, "share_of_step": tms / (ms_per_step * steps), "achieved_tflops": ach}
+        name, tms, n = prof[dom]
+        avg_launch_ms = tms / max(n, 1)
+        achieved = flops[dom] * frames / (tms / 1e3) / 1e12 if tms > 0 else 0.0
         peak = peaks["tf_sustained"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -272,11 +283,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "api": "b200vad_session_run_host (pinned host waveforms -> host decisions + segments)"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "lstm_recurrent_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "launches": int(nl.value), "avg_launch_ms": avg_launch_ms,
-                         "share_of_step": tot_ms.value / (ms_per_step * steps) if ms_per_step > 0 else None,
-                         "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); kernel runs fp16 operands at the same tensor rate",
-                         "algorithmic_flops_per_frame": REC_FLOP_PER_FRAME},
+            "roofline": {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "launches": int(n), "avg_launch_ms": avg_launch_ms,
+                         "share_of_step": tms / (ms_per_step * steps) if ms_per_step > 0 else None,
+                         "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); kernels run fp16 operands at the same tensor rate",
+                         "algorithmic_flops_per_frame": flops[dom], "kernels": kernels},
             "whole_model_tflops": MODEL_FLOP_PER_FRAME * T_FRAMES * (hi - lo) / (ms_per_step / 1e3) / 1e12,
             "clocks": clocks,
         }

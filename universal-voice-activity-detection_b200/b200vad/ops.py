@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 
-_MAX_WS_BYTES = 12 << 30     # cap for per-call workspaces; larger batches are chunked inside the C call
+_MAX_WS_BYTES = 40 << 30     # cap for per-call workspaces (B200: 180 GB HBM); larger batches are chunked inside the C call
 
 
 def _stream_ptr(device) -> int:
