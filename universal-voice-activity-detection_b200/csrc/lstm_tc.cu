@@ -7,26 +7,27 @@
 // units), the BATCH is the MMA N.  So unit u of every gate lands in TMEM lane u, and the thread that
 // owns lane u reads i,f,g,o of a cell from four column ranges of its own lane -- no cross-thread
 // exchange.  One CTA = one direction x 64 sequences, 18 warps:
-//   * W_hh (512 x 128 fp16, 128 KB) is the A operand, resident in shared memory for all T steps
-//     (8 K-major 128B-swizzled tiles written once by TMA);
-//   * h_{t-1} is the B operand: a [64 x 128] K-major swizzled tile that the pointwise threads
+//   * W_hh (512 x 128 fp16) is the A operand and lives in TENSOR MEMORY for all T steps (256
+//     columns: lane = unit, two K-elements per 32-bit column), next to the 256 accumulator columns:
+//     an MMA re-reads no weights from shared memory (in SS mode every M128 K16 MMA re-reads a 4 KB
+//     A slice, which made the tensor pipe the serial bottleneck -- profiles/r01_lstm_ablation.md);
+//   * h_{t-1} is the B operand: a [64 x 128] K-major 128B-swizzled tile that the pointwise threads
 //     write directly in operand layout, as fp16 hi and lo planes (two accumulating MMAs: the
-//     recurrence sees h to ~22 bits, see DESIGN.md "precision"); the same tile is the source of the
-//     TMA store that writes the layer output planes y_hi / y_lo -- no per-cell global stores;
+//     recurrence sees h to ~22 bits, DESIGN.md "precision"); the tiles are double-buffered by step
+//     parity and are also the source of the TMA stores of the layer output planes y_hi / y_lo;
 //   * the 64 columns are two independent halves: while the pointwise warpgroups of half 0 update
-//     their cells, the tensor core (issued by warp 16) runs half 1's MMAs, so MMA latency hides
-//     under the cell update.  Each half is shared by two warpgroups of 16 columns (4 warps per
-//     scheduler keep the issue slots busy on the long ex2/rcp dependency chains);
-//   * cell state c lives in TMEM (64 columns next to the 256 accumulator columns), so the column
-//     loop is a real loop with a small instruction footprint;
+//     their cells, the tensor core (issued by warp 16) runs half 1's MMAs.  Each half is shared by
+//     two warpgroups of 16 columns (4 warps per scheduler on the ex2/rcp dependency chains);
+//   * cell state c lives in shared memory (fp32, conflict-free), so the column loop is a real loop;
 //   * xg is the only HBM read stream (4 KB per sequence-step-direction): warp 17 feeds it through a
-//     2-stage TMA ring per warpgroup (4 columns x 512 gates per stage) and issues L2 prefetches
-//     two steps ahead.
-// Per step and CTA: 2 x 64 tcgen05.mma (M128 N32 K16), 8192 cells, 5 ex2 + 2 rcp per cell.
+//     4-stage TMA ring per warpgroup (4 columns x 512 gates per stage, 128 KB in flight per SM)
+//     and issues L2 prefetches two steps ahead.
+// Per step and CTA: 2 x 64 tcgen05.mma (M128 N32 K16, A in TMEM), 8192 cells, 5 ex2 + 2 rcp per cell.
 // Algorithmic FLOPs: 2*128*512 per (sequence, frame, direction); algorithmic HBM bytes per
 // (sequence, frame, direction): 2048 (xg read) + 512 (y planes written).
 #include "kernels.cuh"
 #include "tc05.cuh"
+#include <stdlib.h>
 
 namespace b200vad {
 
@@ -38,37 +39,39 @@ constexpr int LWG = 4;                     // pointwise warpgroups
 constexpr int LWCOLS = LNB / LWG;          // 16 columns per warpgroup
 constexpr int LCH = 4;                     // columns per ring stage / inner chunk
 constexpr int LNCH = LWCOLS / LCH;         // chunks per step and warpgroup
-constexpr int LSTAGES = 2;                 // xg ring depth per warpgroup
+constexpr int LSTAGES = 4;                 // xg ring depth per warpgroup
 constexpr int LPF = 2;                     // L2 prefetch distance in steps
 constexpr int LTC_THREADS = (LWG * 4 + 2) * 32;   // 576
-constexpr int W_TILE = 128 * 64 * 2;       // 16 KB
 constexpr int H_TILE = LNB * 64 * 2;       // 8 KB
+constexpr int C_BYTES = LNB * kHidden * 4; // 32 KB cell state
 constexpr int X_HALF = LCH * 256 * 4;      // one TMA box: 4 columns x 256 gate values (fp32) = 4 KB
 constexpr int X_STAGE = 2 * X_HALF;        // (i,f) box + (g,o) box
-constexpr int TMEM_C = 4 * LNB;            // first TMEM column of the cell state
+constexpr int TMEM_W = 4 * LNB;            // first TMEM column of W_hh (gate q at TMEM_W + 64 q)
 
 struct LstmTcParams {
+    const __half* whh;     // [2][512][128]
     float* y_f32;          // [B][T][256] (fp32 mode) or null (planes mode: TMA stores through tm_yhi / tm_ylo)
     int B, T;
+    int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
 };
 
 template <bool F32OUT>
 __global__ void __launch_bounds__(LTC_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant__ CUtensorMap tm_xg,
-               const __grid_constant__ CUtensorMap tm_yhi, const __grid_constant__ CUtensorMap tm_ylo, LstmTcParams p) {
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant__ CUtensorMap tm_yhi,
+               const __grid_constant__ CUtensorMap tm_ylo, LstmTcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* const smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    const uint32_t w_base = smem_base;                       // [4 gates][2 kb] tiles 128 x 64
-    const uint32_t h_base = w_base + 8 * W_TILE;             // [hi, lo][2 kb] tiles 64 x 64
-    const uint32_t x_base = h_base + 4 * H_TILE;             // [LWG][LSTAGES] stages
-    const uint32_t bar_base = x_base + LWG * LSTAGES * X_STAGE;
-    const uint32_t bar_w = bar_base;
-    auto bar_h_ready = [&](int h) { return bar_base + 8 + 8 * h; };
-    auto bar_acc_ready = [&](int h) { return bar_base + 24 + 8 * h; };
-    auto bar_x_full = [&](int wg, int st) { return bar_base + 40 + 8 * (wg * LSTAGES + st); };
-    auto bar_x_empty = [&](int wg, int st) { return bar_base + 40 + 8 * (LWG * LSTAGES + wg * LSTAGES + st); };
-    const uint32_t tmem_slot = bar_base + 40 + 8 * 2 * LWG * LSTAGES;
+    const uint32_t h_base = smem_base;                       // [step parity][hi, lo][2 kb] tiles 64 x 64
+    const uint32_t c_off = 8 * H_TILE;                       // cell state [64 cols][128 units] fp32
+    const uint32_t x_off = c_off + C_BYTES;                  // [LWG][LSTAGES] xg stages
+    const uint32_t bar_off = x_off + LWG * LSTAGES * X_STAGE;
+    const uint32_t bar_base = smem_base + bar_off;
+    auto bar_h_ready = [&](int h) { return bar_base + 8 * h; };
+    auto bar_acc_ready = [&](int h) { return bar_base + 16 + 8 * h; };
+    auto bar_x_full = [&](int wg, int st) { return bar_base + 32 + 8 * (wg * LSTAGES + st); };
+    auto bar_x_empty = [&](int wg, int st) { return bar_base + 32 + 8 * (LWG * LSTAGES + wg * LSTAGES + st); };
+    const uint32_t tmem_slot = bar_base + 32 + 8 * 2 * LWG * LSTAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -76,7 +79,6 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
     const int T = p.T;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_w, 1);
         for (int h = 0; h < 2; ++h) { mbar_init(bar_h_ready(h), 256); mbar_init(bar_acc_ready(h), 1); }
         for (int g = 0; g < LWG; ++g)
             for (int st = 0; st < LSTAGES; ++st) { mbar_init(bar_x_full(g, st), 1); mbar_init(bar_x_empty(g, st), 4); }
@@ -91,7 +93,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
 
     if (warp == 17) {
         // ===================== xg producer: lane g feeds warpgroup g =====================
-        if (lane < LWG) {
+        if (lane < LWG && !(p.flags & 1)) {
             const int wg = lane;
             const int bcol = b0 + wg * LWCOLS;
             int st = 0;
@@ -109,7 +111,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
 #pragma unroll 1
                 for (int ch = 0; ch < LNCH; ++ch) {
                     mbar_wait(bar_x_empty(wg, st), ph ^ 1);
-                    const uint32_t dst = x_base + (wg * LSTAGES + st) * X_STAGE;
+                    const uint32_t dst = smem_base + x_off + (wg * LSTAGES + st) * X_STAGE;
                     mbar_expect_tx(bar_x_full(wg, st), X_STAGE);
                     tma_load_3d(dst, &tm_xg, dir * kGates, t, bcol + ch * LCH, bar_x_full(wg, st));
                     tma_load_3d(dst + X_HALF, &tm_xg, dir * kGates + 256, t, bcol + ch * LCH, bar_x_full(wg, st));
@@ -118,48 +120,44 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
             }
         }
     } else if (warp == 16) {
-        // ===================== weight load, MMA issue, layer-output TMA stores =====================
+        // ===================== MMA issue + layer-output TMA stores =====================
         if (elect_one()) {
-            mbar_expect_tx(bar_w, 8 * W_TILE);
-            for (int q = 0; q < 4; ++q)
-                for (int kb = 0; kb < 2; ++kb)
-                    tma_load_2d(w_base + (q * 2 + kb) * W_TILE, &tm_whh, kb * 64, dir * kGates + q * kHidden, bar_w);
-            mbar_wait(bar_w, 0);
-            tc_fence_after();
             constexpr uint32_t idesc = idesc_f16(128, LHALF);
-            // iteration s: h_ready(h) phase s = "h_{s-1} is in the tile" (phase 0 = the zero state)
+            // iteration s: h_ready(h) phase s = "h_{s-1} is in tile buffer (s & 1)" (phase 0 = zero state + W_hh in TMEM)
             for (int s = 0; s <= T; ++s) {
+                const uint32_t hbuf = h_base + (s & 1) * 4 * H_TILE;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     mbar_wait(bar_h_ready(h), s & 1);
                     tc_fence_after();
+                    if (s < T) {
+                        if (!(p.flags & 2)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t d = tmem_base + q * LNB + h * LHALF;
+#pragma unroll
+                                for (int kk = 0; kk < 8; ++kk) {
+                                    const uint32_t a = tmem_base + TMEM_W + q * 64 + kk * 8;
+                                    const uint32_t hb = hbuf + (kk >> 2) * H_TILE + h * (LHALF * 128) + (kk & 3) * 32;
+                                    if (!(p.flags & 4)) mma_f16_ts(d, a, smem_desc_sw128(hb + 2 * H_TILE), idesc, kk != 0);   // h_lo first
+                                    mma_f16_ts(d, a, smem_desc_sw128(hb), idesc, (p.flags & 4) ? (uint32_t)(kk != 0) : 1u); // h_hi
+                                }
+                            }
+                        }
+                        // once acc_ready fires the pointwise warps rewrite buffer (s+1)&1, last read by the store group of
+                        // iteration s-1 for this half: every group but the most recent one must have finished reading
+                        if (!F32OUT) tma_store_wait_read<1>();
+                        mma_commit(bar_acc_ready(h));
+                    }
                     if (!F32OUT && s > 0) {
                         // h_{s-1} of this half -> y planes at time t(s-1); rows beyond B are clipped by TMA
                         const int t = dir == 0 ? s - 1 : T - s;
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb) {
-                            tma_store_3d(&tm_yhi, dir * kHidden + kb * 64, t, b0 + h * LHALF, h_base + kb * H_TILE + h * (LHALF * 128));
-                            tma_store_3d(&tm_ylo, dir * kHidden + kb * 64, t, b0 + h * LHALF, h_base + (2 + kb) * H_TILE + h * (LHALF * 128));
+                            tma_store_3d(&tm_yhi, dir * kHidden + kb * 64, t, b0 + h * LHALF, hbuf + kb * H_TILE + h * (LHALF * 128));
+                            tma_store_3d(&tm_ylo, dir * kHidden + kb * 64, t, b0 + h * LHALF, hbuf + (2 + kb) * H_TILE + h * (LHALF * 128));
                         }
                         tma_store_commit();
-                    }
-                    if (s < T) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t d = tmem_base + q * LNB + h * LHALF;
-#pragma unroll
-                            for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t da = smem_desc_sw128(w_base + (q * 2 + kb) * W_TILE + k * 32);
-                                    const uint32_t hb = h_base + kb * H_TILE + h * (LHALF * 128) + k * 32;
-                                    mma_f16(d, da, smem_desc_sw128(hb + 2 * H_TILE), idesc, (kb | k) != 0);   // h_lo first
-                                    mma_f16(d, da, smem_desc_sw128(hb), idesc, 1);                          // h_hi
-                                }
-                        }
-                        // the pointwise warps may overwrite the tile once acc_ready fires: the TMA store must have read it
-                        if (!F32OUT) tma_store_wait_read<0>();
-                        mma_commit(bar_acc_ready(h));
                     }
                 }
             }
@@ -171,50 +169,69 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
         const int half = wg >> 1;
         const int u = (warp & 3) * 32 + lane;           // hidden unit == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // zero this warpgroup's rows of the 4 h tiles (h_{-1} = 0) and its cell-state columns
-        for (int i = threadIdx.x & 127; i < 4 * LWCOLS * 128 / 16; i += 128) {
-            int tile = i / (LWCOLS * 8), rem = i % (LWCOLS * 8);
-            *reinterpret_cast<uint4*>(smem_gen + 8 * W_TILE + tile * H_TILE + wg * LWCOLS * 128 + rem * 16) = make_uint4(0, 0, 0, 0);
-        }
+        // W_hh -> TMEM: warpgroup g stores gate g; lane u gets row (dir, g, u): 128 fp16 = 64 packed words
         {
-            const float z[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint4* wrow = reinterpret_cast<const uint4*>(p.whh + ((size_t)dir * kGates + wg * kHidden + u) * kHidden);
 #pragma unroll
-            for (int ch = 0; ch < LNCH; ++ch) tmem_st4(lane_addr + TMEM_C + wg * LWCOLS + ch * LCH, z);
+            for (int part = 0; part < 4; ++part) {
+                uint32_t r[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 v = __ldg(wrow + part * 4 + i);
+                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+                }
+                tmem_st16(lane_addr + TMEM_W + wg * 64 + part * 16, r);
+            }
             tmem_st_wait();
         }
+        // zero this warpgroup's rows of the 8 h tiles (h_{-1} = 0) and its cell-state columns
+        for (int i = threadIdx.x & 127; i < 8 * LWCOLS * 128 / 16; i += 128) {
+            int tile = i / (LWCOLS * 8), rem = i % (LWCOLS * 8);
+            *reinterpret_cast<uint4*>(smem_gen + tile * H_TILE + wg * LWCOLS * 128 + rem * 16) = make_uint4(0, 0, 0, 0);
+        }
+        float* const cst = reinterpret_cast<float*>(smem_gen + c_off) + u;      // + col * 128
+#pragma unroll
+        for (int j = 0; j < LWCOLS; ++j) cst[(wg * LWCOLS + j) * kHidden] = 0.f;
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_h_ready(half));
 
-        unsigned char* const h_hi = smem_gen + 8 * W_TILE + (u >> 6) * H_TILE + (u & 7) * 2;   // + row*128 + swizzled chunk
+        unsigned char* const h_hi0 = smem_gen + (u >> 6) * H_TILE + (u & 7) * 2;   // + row*128 + swizzled chunk
         const uint32_t uc = (u & 63) >> 3;
-        const float* const xring = reinterpret_cast<const float*>(smem_gen + 8 * W_TILE + 4 * H_TILE + wg * LSTAGES * X_STAGE) + u;
+        const float* const xring = reinterpret_cast<const float*>(smem_gen + x_off + wg * LSTAGES * X_STAGE) + u;
         int st = 0;
         uint32_t xph = 0;
         const float L2E = 1.4426950408889634f;
 
         for (int s = 0; s < T; ++s) {
             const int t = dir == 0 ? s : T - 1 - s;
+            unsigned char* const h_hi = h_hi0 + ((s + 1) & 1) * 4 * H_TILE;     // h_s goes to buffer (s+1)&1
             mbar_wait(bar_acc_ready(half), s & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < LNCH; ++ch) {
                 const int col0 = wg * LWCOLS + ch * LCH;
-                float a[4][LCH], c[LCH];
+                float a[4][LCH], x[4][LCH];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) tmem_ld4(lane_addr + g * LNB + col0, a[g]);
-                tmem_ld4(lane_addr + TMEM_C + col0, c);
-                // xg chunk from the ring: stage = [(i,f) box | (g,o) box], box = [col][256]
-                mbar_wait(bar_x_full(wg, st), xph);
-                const float* xs = xring + st * (X_STAGE / 4);
-                float x[4][LCH];
+                if (p.flags & 1) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
+                    for (int g = 0; g < 4; ++g)
 #pragma unroll
-                    for (int j = 0; j < LCH; ++j) x[g][j] = xs[(g >> 1) * (X_HALF / 4) + j * 256 + (g & 1) * 128];
+                        for (int j = 0; j < LCH; ++j) x[g][j] = 0.1f * g;
+                } else {
+                    // xg chunk from the ring: stage = [(i,f) box | (g,o) box], box = [col][256]
+                    mbar_wait(bar_x_full(wg, st), xph);
+                    const float* xs = xring + st * (X_STAGE / 4);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+#pragma unroll
+                        for (int j = 0; j < LCH; ++j) x[g][j] = xs[(g >> 1) * (X_HALF / 4) + j * 256 + (g & 1) * 128];
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < LCH; ++j) {
+                    const int n = col0 + j;
                     // one-sided clamps keep every exponential finite (<= 2^29); exp(-inf) = 0 is exact
                     float ei = fast_ex2(fminf(-L2E * (a[0][j] + x[0][j]), 29.f));
                     float ef = fast_ex2(fminf(-L2E * (a[1][j] + x[1][j]), 29.f));
@@ -223,13 +240,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
                     // c' = c/(1+ef) + (eg-1)/((1+ei)(eg+1))  with one reciprocal
                     float di = 1.f + ei, df = 1.f + ef, dg = eg + 1.f;
                     float dig = di * dg;
-                    float cn = fmaf(c[j], dig, (eg - 1.f) * df) * fast_rcp(df * dig);
-                    c[j] = cn;
+                    float cn = fmaf(cst[n * kHidden], dig, (eg - 1.f) * df) * fast_rcp(df * dig);
+                    cst[n * kHidden] = cn;
                     float ec = fast_ex2(fminf(2.f * L2E * cn, 29.f));
                     float hv = (ec - 1.f) * fast_rcp((1.f + eo) * (ec + 1.f));
                     __half hh = __float2half_rn(hv);
                     __half hl = __float2half_rn(hv - __half2float(hh));
-                    const int n = col0 + j;
                     unsigned char* dst = h_hi + n * 128 + ((uc ^ (n & 7)) << 4);
                     *reinterpret_cast<__half*>(dst) = hh;
                     *reinterpret_cast<__half*>(dst + 2 * H_TILE) = hl;
@@ -238,12 +254,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
                         if (b < p.B) p.y_f32[((int64_t)b * T + t) * (2 * kHidden) + dir * kHidden + u] = hv;
                     }
                 }
-                tmem_st4(lane_addr + TMEM_C + col0, c);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_x_empty(wg, st));
-                if (++st == LSTAGES) { st = 0; xph ^= 1; }
+                if (!(p.flags & 1)) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_x_empty(wg, st));
+                    if (++st == LSTAGES) { st = 0; xph ^= 1; }
+                }
             }
-            tmem_st_wait();
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_h_ready(half));
@@ -258,11 +274,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whh, const __grid_constant
 // Exactly one of (y_hi, y_lo: fp16 planes [B][T][256]) / y_f32 is written.
 int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, float* y_f32, int B, int T, cudaStream_t st) {
     if (B <= 0 || T <= 0) return B200VAD_OK;
-    CUtensorMap tm_w, tm_x, tm_yh, tm_yl;
-    int rc = make_tmap_2d(&tm_w, whh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, kHidden, 2 * kGates, kHidden * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    rc = make_tmap_3d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2 * kGates, (uint64_t)T, (uint64_t)B, (uint64_t)2 * kGates * 4,
-                      (uint64_t)T * 2 * kGates * 4, 256, 1, LCH, CU_TENSOR_MAP_SWIZZLE_NONE);
+    CUtensorMap tm_x, tm_yh, tm_yl;
+    int rc = make_tmap_3d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2 * kGates, (uint64_t)T, (uint64_t)B, (uint64_t)2 * kGates * 4,
+                          (uint64_t)T * 2 * kGates * 4, 256, 1, LCH, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     const void* yh = y_f32 ? (const void*)whh : (const void*)y_hi;      // unused maps still have to be valid
     const void* yl = y_f32 ? (const void*)whh : (const void*)y_lo;
@@ -273,18 +287,20 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     rc = make_tmap_3d(&tm_yl, yl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * kHidden, yT, yB, (uint64_t)2 * kHidden * 2,
                       yT * 2 * kHidden * 2, 64, 1, LHALF, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    LstmTcParams p{y_f32, B, T};
-    const int smem = 8 * W_TILE + 4 * H_TILE + LWG * LSTAGES * X_STAGE + 1024 + 256;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    LstmTcParams p{whh, y_f32, B, T, dbg};
+    const int smem = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
     dim3 grid((B + LNB - 1) / LNB, 2);
     prof_begin(0, st);
     if (y_f32) {
         static bool attr = false;
         if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        lstm_tc_kernel<true><<<grid, LTC_THREADS, smem, st>>>(tm_w, tm_x, tm_yh, tm_yl, p);
+        lstm_tc_kernel<true><<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
     } else {
         static bool attr = false;
         if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        lstm_tc_kernel<false><<<grid, LTC_THREADS, smem, st>>>(tm_w, tm_x, tm_yh, tm_yl, p);
+        lstm_tc_kernel<false><<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
     }
     prof_end(0, st);
     B200VAD_LAUNCH_CHECK();
