@@ -122,7 +122,7 @@ def cpu_reference(sample_rows, steps, warmup, threads):
     return (sample_rows * SECONDS / 3600.0) / dt, dt
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -138,11 +138,26 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample_rows} x {SECONDS:.0f} s utterances per step, torch CPU threads={threads}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
     return 0
 
 
+class _OnlyJsonOnStdout:
+    """Libraries (NCCL's version banner, warnings) may write to fd 1; the contract is ONE JSON line on stdout.
+    Everything else is diverted to stderr until `emit` writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main():
+    out = _OnlyJsonOnStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -152,7 +167,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as dist
@@ -296,7 +311,7 @@ def main():
             v, dt = cpu_reference(512, 1, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"512 x {SECONDS:.0f} s utterances (oracle: torch CPU fbank + nn.LSTM + scipy medfilt + Python RLE), {dt:.1f} s/step"}
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
