@@ -157,7 +157,7 @@ class _OnlyJsonOnStdout:
 
 
 def main():
-    out = _OnlyJsonOnStdout()
+    jout = _OnlyJsonOnStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args, out)
+        return run_reference(args, jout)
 
     import torch
     import torch.distributed as dist
@@ -311,7 +311,7 @@ def main():
             v, dt = cpu_reference(512, 1, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"512 x {SECONDS:.0f} s utterances (oracle: torch CPU fbank + nn.LSTM + scipy medfilt + Python RLE), {dt:.1f} s/step"}
-        out.emit(json.dumps(line))
+        jout.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
