@@ -17,6 +17,7 @@
 // (frames, spectrum, power) never leave the SM.
 #include "kernels.cuh"
 #include <math.h>
+#include <stdio.h>
 #include <mutex>
 
 namespace b200vad {
@@ -28,6 +29,7 @@ constexpr int kFramesPerPass = 16;                                    // 256 thr
 constexpr int kZStride = 17 * 16;                                     // padded 16x16 complex tile (float2 units)
 constexpr int kPowStride = 257;
 constexpr int kMaxMelWidth = 32;
+constexpr int kMelRows = 18;                                          // widest Kaldi triangle at 512/16 kHz spans 17 FFT bins
 
 struct FbankTables {
     float window[kFrameLen];
@@ -36,6 +38,7 @@ struct FbankTables {
     int mel_start[kNumMel];
     int mel_len[kNumMel];
     float mel_w[kNumMel][kMaxMelWidth];
+    float mel_wt[kMelRows][kNumMel];      // transposed: [k_rel][bin], zero beyond a bin's width
 };
 
 static FbankTables* g_tables_dev[64] = {nullptr};
@@ -74,6 +77,8 @@ static void build_tables(FbankTables& t) {
         t.mel_start[b] = start < 0 ? 0 : start;
         t.mel_len[b] = len;
         for (int j = len; j < kMaxMelWidth; ++j) t.mel_w[b][j] = 0.f;
+        for (int j = 0; j < kMelRows; ++j) t.mel_wt[j][b] = (j < len) ? t.mel_w[b][j] : 0.f;
+        if (len > kMelRows) fprintf(stderr, "b200vad: mel triangle %d wider than kMelRows (%d)\n", b, len);
     }
 }
 
@@ -185,6 +190,9 @@ struct FbankSmem {
     float2 tw256[256];
     float2 tw512[257];
     float window[kFrameLen];
+    float mel_wt[kMelRows][kNumMel];
+    int mel_start[kNumMel];
+    int mel_len[kNumMel];
 };
 
 __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
@@ -221,6 +229,8 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     for (int i = tid; i < 256; i += 256) sm.tw256[i] = tab->tw256[i];
     for (int i = tid; i < 257; i += 256) sm.tw512[i] = tab->tw512[i];
     for (int i = tid; i < kFrameLen; i += 256) sm.window[i] = tab->window[i];
+    for (int i = tid; i < kMelRows * kNumMel; i += 256) (&sm.mel_wt[0][0])[i] = (&tab->mel_wt[0][0])[i];
+    if (tid < kNumMel) { sm.mel_start[tid] = tab->mel_start[tid]; sm.mel_len[tid] = tab->mel_len[tid]; }
 
     // ---- stage the pre-emphasised span
     const int64_t start = f0 * kFrameShift - kPadLeft;               // original index of span[0]
@@ -318,21 +328,25 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     }
     __syncthreads();
 
-    // ---- mel triangles + log, coalesced rows of 80 floats
-    for (int idx = tid; idx < kTileFrames * kNumMel; idx += 256) {
-        int f = idx / kNumMel, m = idx - f * kNumMel;
-        int64_t fr = f0 + f;
-        if (fr >= T_out) break;
-        float val = kLogEpsilon;
-        if (f < nframes) {
-            const float* pw = sm.pw + f * kPowStride + tab->mel_start[m];
-            const float* w = tab->mel_w[m];
-            int len = tab->mel_len[m];
-            float acc = 0.f;
-            for (int k = 0; k < len; ++k) acc = fmaf(pw[k], __ldg(w + k), acc);
-            val = logf(fmaxf(acc, kEpsilon));
+    // ---- mel triangles + log: thread = (mel bin m, group of 4 frames); one weight load feeds 4 FMAs; consecutive
+    // threads = consecutive bins, so weight reads are conflict-free and the output rows are coalesced (320 B)
+    constexpr int kFrameGroup = 4;
+    for (int idx = tid; idx < (kTileFrames / kFrameGroup) * kNumMel; idx += 256) {
+        const int grp = idx / kNumMel, m = idx - grp * kNumMel;
+        const int fb = grp * kFrameGroup;
+        const int start = sm.mel_start[m], len = sm.mel_len[m];
+        const float* pw = sm.pw + fb * kPowStride + start;
+        float acc[kFrameGroup] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < len; ++k) {
+            const float w = sm.mel_wt[k][m];
+#pragma unroll
+            for (int j = 0; j < kFrameGroup; ++j) acc[j] = fmaf(pw[j * kPowStride + k], w, acc[j]);
         }
-        out_row[fr * kNumMel + m] = val;
+#pragma unroll
+        for (int j = 0; j < kFrameGroup; ++j) {
+            const int64_t fr = f0 + fb + j;
+            if (fr < T_out) out_row[fr * kNumMel + m] = (fb + j < nframes) ? logf(fmaxf(acc[j], kEpsilon)) : kLogEpsilon;
+        }
     }
 }
 

@@ -21,7 +21,7 @@
 //   * cell state c lives in shared memory (fp32, conflict-free), so the column loop is a real loop;
 //   * xg is the only HBM read stream (4 KB per sequence-step-direction): warp 17 feeds it through a
 //     4-stage TMA ring per warpgroup (4 columns x 512 gates per stage, 128 KB in flight per SM)
-//     and issues L2 prefetches two steps ahead.
+//     (optional L2 prefetch ahead of the ring measured no gain and is off by default).
 // Per step and CTA: 2 x 64 tcgen05.mma (M128 N32 K16, A in TMEM), 8192 cells, 5 ex2 + 2 rcp per cell.
 // Algorithmic FLOPs: 2*128*512 per (sequence, frame, direction); algorithmic HBM bytes per
 // (sequence, frame, direction): 2048 (xg read) + 512 (y planes written).
@@ -40,7 +40,7 @@ constexpr int LWCOLS = LNB / LWG;          // 16 columns per warpgroup
 constexpr int LCH = 4;                     // columns per ring stage / inner chunk
 constexpr int LNCH = LWCOLS / LCH;         // chunks per step and warpgroup
 constexpr int LSTAGES = 4;                 // xg ring depth per warpgroup
-constexpr int LPF = 2;                     // L2 prefetch distance in steps
+constexpr int LPF = 0;                     // L2 prefetch distance in steps (0 = off: measured no gain, profiles/r01_lstm_ablation.md)
 constexpr int LTC_THREADS = (LWG * 4 + 2) * 32;   // 576
 constexpr int H_TILE = LNB * 64 * 2;       // 8 KB
 constexpr int C_BYTES = LNB * kHidden * 4; // 32 KB cell state
@@ -53,6 +53,7 @@ struct LstmTcParams {
     float* y_f32;          // [B][T][256] (fp32 mode) or null (planes mode: TMA stores through tm_yhi / tm_ylo)
     int B, T;
     int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
+    int pf;                // L2 prefetch distance in steps (0 = off)
 };
 
 template <bool F32OUT>
@@ -100,8 +101,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
             uint32_t ph = 0;
             for (int s = 0; s < T; ++s) {
                 const int t = dir == 0 ? s : T - 1 - s;
-                if (s + LPF < T) {
-                    const int tp = dir == 0 ? t + LPF : t - LPF;
+                if (p.pf > 0 && s + p.pf < T) {
+                    const int tp = dir == 0 ? t + p.pf : t - p.pf;
 #pragma unroll 1
                     for (int ch = 0; ch < LNCH; ++ch) {
                         tma_prefetch_l2_3d(&tm_xg, dir * kGates, tp, bcol + ch * LCH);
@@ -289,7 +290,9 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     if (rc) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    LstmTcParams p{whh, y_f32, B, T, dbg};
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("B200VAD_LSTM_PF"); pf = e ? atoi(e) : LPF; }
+    LstmTcParams p{whh, y_f32, B, T, dbg, pf};
     const int smem = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
     dim3 grid((B + LNB - 1) / LNB, 2);
     prof_begin(0, st);
