@@ -123,9 +123,16 @@ B200VAD_API int b200vad_pipeline_fbank_f32(const void* packed, int num_layers, c
                                uint8_t* dec /* (B,T) */, int32_t* counts, int64_t* seg_off, int32_t* seg, int64_t cap,
                                void* workspace, size_t ws_bytes, void* stream);
 
-/* ---- host-buffer session: the same path with HOST waveforms and HOST results.  The session
- * owns pinned staging buffers, device buffers and two CUDA streams, and overlaps the H2D copy
- * of chunk i+1 with the compute of chunk i.  This is the call `e2e` times in bench.py. */
+/* ---- host-buffer session: the same path with HOST waveforms and HOST results -- what a caller holding
+ * lhotse/DataLoader batches in host memory uses (src/engines/vad_engine.py:204-211 fed by
+ * src/datasets/data_module.py:194-206).  The session owns device buffers for two batches in flight and three
+ * CUDA streams (H2D / compute / D2H).
+ *   run_host     : blocking; B rows are cut into chunks of max_chunk_rows that are pipelined internally.
+ *   submit / wait: asynchronous; submit(slot) enqueues H2D + whole path + D2H of one batch (<= max_chunk_rows
+ *                  rows) and returns; wait(slot) blocks until that batch's dec/prob are in the host buffers
+ *                  given to submit and copies its segment triples.  Keeping both slots busy overlaps the PCIe
+ *                  copies of batch i+1 / i-1 with the compute of batch i.  This is what `e2e` times in bench.py.
+ * Host buffers should be pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous. */
 typedef struct b200vad_session b200vad_session;
 B200VAD_API int b200vad_session_create(int device, const void* packed_device, int num_layers, int max_chunk_rows, int64_t N,
                            b200vad_session** out);
@@ -133,6 +140,12 @@ B200VAD_API int b200vad_session_create(int device, const void* packed_device, in
  * seg (cap,3) i32, *nseg total segments.  Blocks until results are on the host. */
 B200VAD_API int b200vad_session_run_host(b200vad_session* s, const float* wav_host, int B, float thr, int kernel, uint8_t* dec_host,
                              float* prob_host, int32_t* seg_host, int64_t cap, int64_t* nseg);
+B200VAD_API int b200vad_session_submit_host(b200vad_session* s, int slot, const float* wav_host, int B, float thr, int kernel,
+                                uint8_t* dec_host, float* prob_host);
+B200VAD_API int b200vad_session_wait(b200vad_session* s, int slot, int32_t* seg_host, int64_t cap, int64_t* nseg);
+/* Device timeline of the slot's most recent batch, in ms since the session was created:
+ * ms[0..4] = H2D begin, H2D end, compute begin, compute end, D2H end (CUDA events on the three streams). */
+B200VAD_API int b200vad_session_slot_times(b200vad_session* s, int slot, float* ms);
 B200VAD_API void b200vad_session_destroy(b200vad_session* s);
 
 #ifdef __cplusplus

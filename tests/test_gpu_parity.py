@@ -81,6 +81,23 @@ def test_pyannet2_probabilities(dev, B, T):
     assert util.prob_err(out, ref) <= util.PROB_RTOL, util.prob_err(out, ref)
 
 
+def test_pyannet2_ssl_width(dev):
+    """The reference's default configuration feeds 768-dim SSL features (config/config.py:16-18, 30-35,
+    VadModel defaults vad_engine.py:30-35): the layer-0 projection takes the wide-input kernel path."""
+    from src.engines import VadModel
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 120, 768, generator=g)
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 768}, spread=True, feats=x)
+    with torch.no_grad():
+        ref = o(x)
+    m = VadModel("PyanNet2", {"encoding_dim": 768}).eval()
+    m.load_state_dict(o.state_dict())
+    m = m.to(dev)
+    with torch.no_grad():
+        out = m(x.to(dev)).cpu()
+    assert util.prob_err(out, ref) <= util.PROB_RTOL, util.prob_err(out, ref)
+
+
 def test_pyannet2_spread_head_decisions(dev):
     """Spread-head variant: probabilities span (0,1); decisions / segments must be bit-exact except
     frames within the stated tolerance of the threshold, which are counted separately."""
@@ -214,6 +231,23 @@ def test_pipeline_and_host_session(dev):
     assert torch.equal(res["dec"][:10], dec.cpu())
     assert torch.allclose(res["prob"][:10], prob.cpu(), rtol=0, atol=0)
     assert [tuple(r) for r in res["seg"].tolist()] == want
+    sess.close()
+    # asynchronous form: two batches in flight, results identical to the device pipeline
+    sess = b200vad.HostSession(blob, 4, 80000, chunk_rows=6)
+    halves = [wav[:6].contiguous().pin_memory(), wav[6:].contiguous().pin_memory()]
+    outs = [sess.submit(i, halves[i], 0.5, 49, want_dec=True, want_prob=True) for i in range(2)]
+    with pytest.raises(b200vad.B200VadError):
+        sess.submit(0, halves[0])                 # slot 0 still holds an unwaited batch
+    for rep in range(2):                          # second round re-uses the slots
+        for i, (lo, hi) in enumerate(((0, 6), (6, 10))):
+            r = sess.wait(i, outs[i])
+            assert torch.equal(r["dec"], dec[lo:hi].cpu())
+            assert torch.equal(r["prob"], prob[lo:hi].cpu())
+            assert [(a + lo, b, c) for a, b, c in r["seg"].tolist()] == [w for w in want if lo <= w[0] < hi]
+            if rep == 0:
+                outs[i] = sess.submit(i, halves[i], 0.5, 49, want_dec=True, want_prob=True, out=outs[i])
+    with pytest.raises(b200vad.B200VadError):
+        sess.wait(0, outs[0])                     # nothing in flight
     sess.close()
 
 

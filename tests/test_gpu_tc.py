@@ -33,7 +33,7 @@ def _linear(dev, a, w, bias, use_lo):
 
 
 @pytest.mark.parametrize("M,K,N,use_lo", [(128, 64, 256, 1), (1000, 80, 1024, 1), (4096, 256, 1024, 0), (333, 128, 128, 1),
-                                          (70000, 256, 1024, 0)])
+                                          (70000, 256, 1024, 0), (20001, 256, 1024, 1), (777, 256, 128, 1)])
 def test_gemm_tc_matches_fp64(dev, M, K, N, use_lo):
     g = torch.Generator().manual_seed(M + K)
     a = torch.randn(M, K, generator=g) * (5.0 if K == 80 else 0.3)

@@ -49,6 +49,9 @@ PROTOTYPES = {
     "b200vad_session_create": (c_int, [c_int, c_void_p, c_int, c_int, c_int64, C.POINTER(c_void_p)]),
     "b200vad_session_run_host": (c_int, [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                          C.POINTER(c_int64)]),
+    "b200vad_session_submit_host": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "b200vad_session_wait": (c_int, [c_void_p, c_int, c_void_p, c_int64, C.POINTER(c_int64)]),
+    "b200vad_session_slot_times": (c_int, [c_void_p, c_int, C.POINTER(c_float)]),
     "b200vad_session_destroy": (None, [c_void_p]),
 }
 

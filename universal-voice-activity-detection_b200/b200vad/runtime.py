@@ -15,9 +15,10 @@ from .host import shard_range  # noqa: F401  (re-export)
 class HostSession:
     """waveforms on the HOST -> decisions / probabilities / segments on the HOST.
 
-    Wraps ``b200vad_session_*``: the session owns device buffers and two CUDA streams and
-    overlaps the H2D copy of chunk i+1 with the compute of chunk i.  Pass pinned tensors
-    (``tensor.pin_memory()``) for full PCIe bandwidth.
+    Wraps ``b200vad_session_*``: the session owns device buffers for two batches in flight and
+    three CUDA streams (H2D / compute / D2H).  ``run`` is the blocking form (rows are cut into
+    chunks of ``chunk_rows`` and pipelined internally); ``submit`` / ``wait`` is the asynchronous
+    form for a caller that streams batches.  Pass pinned tensors (``tensor.pin_memory()``).
     """
 
     def __init__(self, packed: torch.Tensor, num_layers: int, num_samples: int, chunk_rows: int = 1024,
@@ -55,6 +56,46 @@ class HostSession:
             out["seg_buf"].data_ptr(), cap, C.byref(nseg)), "b200vad_session_run_host")
         out["seg"] = out["seg_buf"][: nseg.value]
         return out
+
+    # ---- asynchronous form: two batches in flight (slot 0 / 1); PCIe copies overlap the other slot's compute
+    def submit(self, slot: int, wav: torch.Tensor, thr: float = 0.5, kernel: int = 49, want_dec: bool = True,
+               want_prob: bool = False, out: Optional[dict] = None) -> dict:
+        """Enqueue one batch (B <= chunk_rows rows) into ``slot`` and return at once.  ``out`` (reused across
+        calls) receives pinned ``dec`` / ``prob`` buffers that are valid after ``wait(slot, out)``."""
+        if wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2 or wav.shape[1] != self.N or not wav.is_contiguous():
+            raise _lib.B200VadError("wav must be a contiguous CPU float32 tensor of shape (B, N)")
+        B = wav.shape[0]
+        out = out if out is not None else {}
+        if want_dec and ("dec" not in out or out["dec"].shape[0] != B):
+            out["dec"] = torch.empty((B, self.T), dtype=torch.uint8).pin_memory()
+        if want_prob and ("prob" not in out or out["prob"].shape[0] != B):
+            out["prob"] = torch.empty((B, self.T), dtype=torch.float32).pin_memory()
+        cap = B * ((self.T + 2) // 3)
+        if "seg_buf" not in out or out["seg_buf"].shape[0] < cap:
+            out["seg_buf"] = torch.empty((max(cap, 1), 3), dtype=torch.int32).pin_memory()
+        out["_wav"] = wav          # keep the source alive until wait()
+        _lib.check(_lib.lib().b200vad_session_submit_host(
+            self._h, int(slot), wav.data_ptr(), B, float(thr), int(kernel),
+            out["dec"].data_ptr() if want_dec else None, out["prob"].data_ptr() if want_prob else None),
+            "b200vad_session_submit_host")
+        return out
+
+    def wait(self, slot: int, out: dict) -> dict:
+        """Block until the batch submitted into ``slot`` is on the host; fills ``out['seg']``."""
+        nseg = C.c_int64(0)
+        buf = out["seg_buf"]
+        _lib.check(_lib.lib().b200vad_session_wait(self._h, int(slot), buf.data_ptr(), buf.shape[0], C.byref(nseg)),
+                   "b200vad_session_wait")
+        out["seg"] = buf[: min(nseg.value, buf.shape[0])]
+        out.pop("_wav", None)
+        return out
+
+    def slot_times(self, slot: int):
+        """Device timeline of the slot's latest batch: ms since session creation of
+        (H2D begin, H2D end, compute begin, compute end, D2H end)."""
+        arr = (C.c_float * 5)()
+        _lib.check(_lib.lib().b200vad_session_slot_times(self._h, int(slot), arr), "b200vad_session_slot_times")
+        return list(arr)
 
     def close(self):
         if getattr(self, "_h", None):

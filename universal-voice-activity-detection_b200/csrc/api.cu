@@ -177,7 +177,7 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
             if ((rc = head_forward(m, pk, in, rows, xg, xg + rows * kHidden, prob + b0 * T, st))) return rc;
             continue;
         }
-        // ---- tcgen05 path: activations travel between layers as fp16 (hi, lo) planes
+        // ---- tcgen05 path: activations travel between layers (and into the head) as fp16 (hi, lo) planes
         const bool d_ok = (D % 8 == 0);
         if (d_ok) {
             if ((rc = split_planes_launch(xin, rows * D, x_hi, x_lo, st))) return rc;
@@ -186,36 +186,47 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
         const __half* a_lo = x_lo;
         int64_t lda = D;
         char* outbuf = buf0;
-        const float* y_last = nullptr;
         for (int l = 0; l < L; ++l) {
             const LayerOff& lo = m.layers[l];
             const __half* w_hi = reinterpret_cast<const __half*>(pk + lo.wih_hi);
             const __half* w_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
             const float* bias = reinterpret_cast<const float*>(pk + lo.bias);
-            // hi + lo weight planes stay resident in smem (128- or 256-column ranges, chosen by the launcher)
-            const bool fits1 = (size_t)2 * 128 * lo.Kp * 2 <= 128 * 1024;
-            if ((l > 0 || d_ok) && fits1) {
-                if ((rc = gemm_tc_launch(a_hi, a_lo, lda, rows, lo.D, w_hi, w_lo, lo.Kp, 2 * kGates, bias, xg,
-                                         2 * kGates, sms, st))) return rc;
+            // hi + lo weight planes stay resident in tensor memory (2 planes x Kp <= 512 fp16 per output feature)
+            if ((l > 0 || d_ok) && 2 * lo.Kp <= 512) {
+                if ((rc = gemm_ts_launch(a_hi, a_lo, lda, rows, lo.D, w_hi, w_lo, lo.Kp, 2 * kGates, bias, 0, xg, nullptr, nullptr,
+                                         128, rows * 128, sms, st))) return rc;
             } else {
                 // shapes the resident-weight kernel cannot hold (e.g. 768-dim SSL features): warp-MMA GEMM on the fp32 input
                 if (l > 0) { set_error("model_forward: internal layer width unsupported"); return B200VAD_EINVAL; }
-                GemmArgs g;
-                g.A = xin; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
-                g.N = 2 * kGates; g.K = lo.D; g.Kp = lo.Kp; g.W_hi = w_hi; g.W_lo = w_lo; g.bias = bias;
-                g.C = xg; g.ldc = 2 * kGates; g.c_half = 0; g.act = 0;
-                if ((rc = gemm_launch(g, 0, 3, st))) return rc;
+                // one launch per 128-feature block, so that xg comes out in the recurrence's blocked layout
+                for (int blk = 0; blk < 2 * kGates / 128; ++blk) {
+                    GemmArgs g;
+                    g.A = xin; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
+                    g.N = 128; g.K = lo.D; g.Kp = lo.Kp; g.W_hi = w_hi + (size_t)blk * 128 * lo.Kp;
+                    g.W_lo = w_lo + (size_t)blk * 128 * lo.Kp; g.bias = bias + blk * 128;
+                    g.C = xg + (size_t)blk * rows * 128; g.ldc = 128; g.c_half = 0; g.act = 0;
+                    if ((rc = gemm_launch(g, 0, 3, st))) return rc;
+                }
             }
-            const bool last = (l == L - 1);
             __half* yh = reinterpret_cast<__half*>(outbuf);
             __half* yl = yh + rows * 2 * kHidden;
-            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), last ? nullptr : yh, last ? nullptr : yl,
-                                     last ? reinterpret_cast<float*>(outbuf) : nullptr, bc, (int)T, st))) return rc;
-            if (last) y_last = reinterpret_cast<const float*>(outbuf);
+            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), yh, yl, nullptr, bc, (int)T, st))) return rc;
             a_hi = yh; a_lo = yl; lda = 2 * kHidden;
             outbuf = (outbuf == buf0) ? buf1 : buf0;
         }
-        if ((rc = head_forward(m, pk, y_last, rows, xg, xg + rows * kHidden, prob + b0 * T, st))) return rc;
+        // head (PyanNet2.py:183-187) on the same GEMM: planes -> lrelu -> planes -> lrelu -> fp32 -> classifier.
+        // z1 planes and z2 live in the xg buffer (free after the last recurrence).
+        __half* z1_hi = reinterpret_cast<__half*>(xg);
+        __half* z1_lo = z1_hi + rows * kHidden;
+        float* z2 = reinterpret_cast<float*>(z1_lo + rows * kHidden);
+        if ((rc = gemm_ts_launch(a_hi, a_lo, 2 * kHidden, rows, 2 * kHidden, reinterpret_cast<const __half*>(pk + m.w1_hi),
+                                 reinterpret_cast<const __half*>(pk + m.w1_lo), 2 * kHidden, kHidden,
+                                 reinterpret_cast<const float*>(pk + m.b1), 1, nullptr, z1_hi, z1_lo, kHidden, 0, sms, st))) return rc;
+        if ((rc = gemm_ts_launch(z1_hi, z1_lo, kHidden, rows, kHidden, reinterpret_cast<const __half*>(pk + m.w2_hi),
+                                 reinterpret_cast<const __half*>(pk + m.w2_lo), kHidden, kHidden,
+                                 reinterpret_cast<const float*>(pk + m.b2), 2, z2, nullptr, nullptr, kHidden, 0, sms, st))) return rc;
+        if ((rc = classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc),
+                                    prob + b0 * T, st))) return rc;
     }
     return B200VAD_OK;
 }
@@ -392,6 +403,7 @@ int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, i
                              void* ws, size_t ws_bytes, void* stream) {
     B200VAD_CHECK_ARG(a && w && c && ws, "null pointer");
     B200VAD_CHECK_ARG(M >= 0 && K > 0 && K % 8 == 0 && N > 0 && N % 128 == 0, "need K % 8 == 0 and N % 128 == 0");
+    B200VAD_CHECK_ARG((use_w_lo ? 2 : 1) * round64(K) <= 512, "weights must fit in tensor memory: planes x K <= 512");
     B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
     const int Kp = round64(K);
     const size_t need = 2 * align_up(sizeof(__half) * M * K) + 2 * align_up(sizeof(__half) * (size_t)N * Kp);
@@ -408,7 +420,7 @@ int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, i
     int rc = split_planes_launch(a, M * K, a_hi, a_lo, st);
     if (rc) return rc;
     if ((rc = split_weights(w, N, K, Kp, w_hi, w_lo, st))) return rc;
-    return gemm_tc_launch(a_hi, a_lo, K, M, K, w_hi, use_w_lo ? w_lo : nullptr, Kp, N, bias, c, N, num_sms_cached(), st);
+    return gemm_ts_launch(a_hi, a_lo, K, M, K, w_hi, use_w_lo ? w_lo : nullptr, Kp, N, bias, 0, c, nullptr, nullptr, N, 0, num_sms_cached(), st);
 }
 
 // ---------------------------------------------------------------- SincNet
@@ -594,25 +606,31 @@ int b200vad_pipeline_fbank_f32(const void* packed, int L, const float* wav, cons
 }
 
 // ---------------------------------------------------------------- host-buffer session
+// Two slots, three streams (H2D / compute / D2H).  submit() only enqueues; wait() blocks on the slot's D2H
+// event.  With a batch in flight in each slot the H2D copy of batch i+1 and the D2H of batch i-1 overlap
+// the compute of batch i.
+struct SessionSlot {
+    float* wav_dev;
+    float* prob_dev;
+    uint8_t* dec_dev;
+    int32_t* counts_dev;
+    int64_t* seg_off_dev;
+    int32_t* seg_dev;
+    int64_t* total_host;    // pinned
+    cudaEvent_t copy_begin, copied, compute_begin, computed, drained;
+    int B;                  // rows in flight (0 = free)
+};
 struct b200vad_session {
     int device;
     const void* packed;
     int L;
     int chunk;
     int64_t N, T, max_seg_per_row;
-    cudaStream_t copy_stream, compute_stream;
-    cudaEvent_t copied[2], consumed[2];
-    float* wav_dev[2];
-    float* prob_dev[2];
-    uint8_t* dec_dev[2];
-    int32_t* counts_dev;
-    int64_t* seg_off_dev;
-    int32_t* seg_dev;       // grows with B
-    int64_t seg_dev_rows;
+    cudaStream_t copy_stream, compute_stream, d2h_stream, seg_stream;
+    cudaEvent_t epoch;      // recorded at creation; slot event times are reported relative to it
+    SessionSlot slot[2];
     void* ws;
     size_t ws_bytes;
-    int64_t* totals_host;   // pinned, one per chunk
-    int64_t totals_cap;
 };
 
 int b200vad_session_create(int device, const void* packed_device, int num_layers, int max_chunk_rows, int64_t N,
@@ -630,19 +648,27 @@ int b200vad_session_create(int device, const void* packed_device, int num_layers
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     ok(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&s->compute_stream, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&s->d2h_stream, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&s->seg_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        ok(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
-        ok(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
-        ok(cudaMalloc(&s->wav_dev[i], sizeof(float) * (size_t)s->chunk * N));
-        ok(cudaMalloc(&s->prob_dev[i], sizeof(float) * (size_t)s->chunk * s->T));
-        ok(cudaMalloc(&s->dec_dev[i], (size_t)s->chunk * s->T));
+        SessionSlot& sl = s->slot[i];
+        ok(cudaEventCreate(&sl.copy_begin));
+        ok(cudaEventCreate(&sl.copied));
+        ok(cudaEventCreate(&sl.compute_begin));
+        ok(cudaEventCreate(&sl.computed));
+        ok(cudaEventCreate(&sl.drained));
+        ok(cudaMalloc(&sl.wav_dev, sizeof(float) * (size_t)s->chunk * N));
+        ok(cudaMalloc(&sl.prob_dev, sizeof(float) * (size_t)s->chunk * s->T));
+        ok(cudaMalloc(&sl.dec_dev, (size_t)s->chunk * s->T));
+        ok(cudaMalloc(&sl.counts_dev, sizeof(int32_t) * s->chunk));
+        ok(cudaMalloc(&sl.seg_off_dev, sizeof(int64_t) * (s->chunk + 1)));
+        ok(cudaMalloc(&sl.seg_dev, sizeof(int32_t) * 3 * (size_t)s->chunk * s->max_seg_per_row));
+        ok(cudaMallocHost(&sl.total_host, sizeof(int64_t)));
     }
-    ok(cudaMalloc(&s->counts_dev, sizeof(int32_t) * s->chunk));
-    ok(cudaMalloc(&s->seg_off_dev, sizeof(int64_t) * (s->chunk + 1)));
     s->ws_bytes = pipeline_ws_bytes(s->chunk, N);
     ok(cudaMalloc(&s->ws, s->ws_bytes));
-    s->totals_cap = 1024;
-    ok(cudaMallocHost(&s->totals_host, sizeof(int64_t) * s->totals_cap));
+    ok(cudaEventCreate(&s->epoch));
+    ok(cudaEventRecord(s->epoch, s->copy_stream));
     if (e != cudaSuccess) {
         set_error("b200vad_session_create: %s", cudaGetErrorString(e));
         b200vad_session_destroy(s);
@@ -652,61 +678,113 @@ int b200vad_session_create(int device, const void* packed_device, int num_layers
     return B200VAD_OK;
 }
 
+static int session_submit(b200vad_session* s, int slot, const float* wav_host, int B, int row_base, float thr, int kernel,
+                          uint8_t* dec_host, float* prob_host) {
+    SessionSlot& sl = s->slot[slot];
+    const int64_t N = s->N, T = s->T;
+    B200VAD_CUDA(cudaEventRecord(sl.copy_begin, s->copy_stream));
+    B200VAD_CUDA(cudaMemcpyAsync(sl.wav_dev, wav_host, sizeof(float) * (size_t)B * N, cudaMemcpyHostToDevice, s->copy_stream));
+    B200VAD_CUDA(cudaEventRecord(sl.copied, s->copy_stream));
+    B200VAD_CUDA(cudaStreamWaitEvent(s->compute_stream, sl.copied, 0));
+    B200VAD_CUDA(cudaEventRecord(sl.compute_begin, s->compute_stream));
+    int rc = pipeline_run(s->packed, s->L, sl.wav_dev, nullptr, B, N, N, thr, kernel, row_base, sl.prob_dev, sl.dec_dev,
+                          sl.counts_dev, sl.seg_off_dev, sl.seg_dev, (int64_t)B * s->max_seg_per_row, s->ws, s->ws_bytes,
+                          s->compute_stream);
+    if (rc) return rc;
+    B200VAD_CUDA(cudaEventRecord(sl.computed, s->compute_stream));
+    B200VAD_CUDA(cudaStreamWaitEvent(s->d2h_stream, sl.computed, 0));
+    B200VAD_CUDA(cudaMemcpyAsync(sl.total_host, sl.seg_off_dev + B, sizeof(int64_t), cudaMemcpyDeviceToHost, s->d2h_stream));
+    if (dec_host)
+        B200VAD_CUDA(cudaMemcpyAsync(dec_host, sl.dec_dev, (size_t)B * T, cudaMemcpyDeviceToHost, s->d2h_stream));
+    if (prob_host)
+        B200VAD_CUDA(cudaMemcpyAsync(prob_host, sl.prob_dev, sizeof(float) * (size_t)B * T, cudaMemcpyDeviceToHost, s->d2h_stream));
+    B200VAD_CUDA(cudaEventRecord(sl.drained, s->d2h_stream));
+    sl.B = B;
+    return B200VAD_OK;
+}
+
+// blocks until the slot's results are on the host; copies at most `cap` segment triples, *nseg = segments found
+static int session_wait(b200vad_session* s, int slot, int32_t* seg_host, int64_t cap, int64_t* nseg) {
+    SessionSlot& sl = s->slot[slot];
+    B200VAD_CUDA(cudaEventSynchronize(sl.drained));
+    const int64_t n = *sl.total_host;
+    const int64_t take = std::max<int64_t>(0, std::min<int64_t>(n, cap));
+    if (take > 0) {
+        // own stream: d2h_stream may already hold the other slot's copies, which wait for that slot's compute
+        B200VAD_CUDA(cudaMemcpyAsync(seg_host, sl.seg_dev, sizeof(int32_t) * 3 * take, cudaMemcpyDeviceToHost, s->seg_stream));
+        B200VAD_CUDA(cudaStreamSynchronize(s->seg_stream));
+    }
+    sl.B = 0;
+    *nseg = n;
+    return B200VAD_OK;
+}
+
+int b200vad_session_submit_host(b200vad_session* s, int slot, const float* wav_host, int B, float thr, int kernel,
+                                uint8_t* dec_host, float* prob_host) {
+    B200VAD_CHECK_ARG(s && wav_host, "null pointer");
+    B200VAD_CHECK_ARG(slot == 0 || slot == 1, "slot must be 0 or 1");
+    B200VAD_CHECK_ARG(B >= 1 && B <= s->chunk, "B must be in [1, max_chunk_rows]");
+    if (s->slot[slot].B != 0) {
+        set_error("session_submit_host: slot %d still holds an unwaited batch", slot);
+        return B200VAD_ESTATE;
+    }
+    B200VAD_CUDA(cudaSetDevice(s->device));
+    return session_submit(s, slot, wav_host, B, 0, thr, kernel, dec_host, prob_host);
+}
+
+int b200vad_session_wait(b200vad_session* s, int slot, int32_t* seg_host, int64_t cap, int64_t* nseg) {
+    B200VAD_CHECK_ARG(s && nseg && (seg_host || cap == 0), "null pointer");
+    B200VAD_CHECK_ARG((slot == 0 || slot == 1) && cap >= 0, "bad slot / cap");
+    if (s->slot[slot].B == 0) {
+        set_error("session_wait: slot %d has no batch in flight", slot);
+        return B200VAD_ESTATE;
+    }
+    B200VAD_CUDA(cudaSetDevice(s->device));
+    return session_wait(s, slot, seg_host, cap, nseg);
+}
+
+int b200vad_session_slot_times(b200vad_session* s, int slot, float* ms) {
+    B200VAD_CHECK_ARG(s && ms && (slot == 0 || slot == 1), "bad argument");
+    SessionSlot& sl = s->slot[slot];
+    cudaEvent_t ev[5] = {sl.copy_begin, sl.copied, sl.compute_begin, sl.computed, sl.drained};
+    B200VAD_CUDA(cudaEventSynchronize(sl.drained));
+    for (int i = 0; i < 5; ++i) B200VAD_CUDA(cudaEventElapsedTime(ms + i, s->epoch, ev[i]));
+    return B200VAD_OK;
+}
+
 int b200vad_session_run_host(b200vad_session* s, const float* wav_host, int B, float thr, int kernel, uint8_t* dec_host,
                              float* prob_host, int32_t* seg_host, int64_t cap, int64_t* nseg) {
     B200VAD_CHECK_ARG(s && wav_host && nseg && (seg_host || cap == 0), "null pointer");
     B200VAD_CHECK_ARG(B >= 0 && cap >= 0, "bad size");
     *nseg = 0;
     if (B == 0) return B200VAD_OK;
+    if (s->slot[0].B != 0 || s->slot[1].B != 0) {
+        set_error("session_run_host: a submitted batch is still in flight");
+        return B200VAD_ESTATE;
+    }
     B200VAD_CUDA(cudaSetDevice(s->device));
     const int nchunks = (B + s->chunk - 1) / s->chunk;
-    if (nchunks > s->totals_cap) {
-        set_error("session_run_host: too many chunks (%d)", nchunks);
-        return B200VAD_EINVAL;
-    }
-    if (s->seg_dev_rows < B) {
-        if (s->seg_dev) cudaFree(s->seg_dev);
-        s->seg_dev = nullptr;
-        B200VAD_CUDA(cudaMalloc(&s->seg_dev, sizeof(int32_t) * 3 * (size_t)B * s->max_seg_per_row));
-        s->seg_dev_rows = B;
-    }
     const int64_t N = s->N, T = s->T;
-    for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        const int b0 = c * s->chunk, bc = std::min(s->chunk, B - b0);
-        // wait until the compute of chunk c-2 released this buffer
-        if (c >= 2) B200VAD_CUDA(cudaStreamWaitEvent(s->copy_stream, s->consumed[buf], 0));
-        B200VAD_CUDA(cudaMemcpyAsync(s->wav_dev[buf], wav_host + (size_t)b0 * N, sizeof(float) * (size_t)bc * N,
-                                     cudaMemcpyHostToDevice, s->copy_stream));
-        B200VAD_CUDA(cudaEventRecord(s->copied[buf], s->copy_stream));
-        B200VAD_CUDA(cudaStreamWaitEvent(s->compute_stream, s->copied[buf], 0));
-        int32_t* seg_c = s->seg_dev + 3 * (size_t)b0 * s->max_seg_per_row;
-        int rc = pipeline_run(s->packed, s->L, s->wav_dev[buf], nullptr, bc, N, N, thr, kernel, b0, s->prob_dev[buf],
-                              s->dec_dev[buf], s->counts_dev, s->seg_off_dev, seg_c, (int64_t)bc * s->max_seg_per_row, s->ws,
-                              s->ws_bytes, s->compute_stream);
-        if (rc) return rc;
-        B200VAD_CUDA(cudaMemcpyAsync(&s->totals_host[c], s->seg_off_dev + bc, sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                     s->compute_stream));
-        if (dec_host)
-            B200VAD_CUDA(cudaMemcpyAsync(dec_host + (size_t)b0 * T, s->dec_dev[buf], (size_t)bc * T, cudaMemcpyDeviceToHost,
-                                         s->compute_stream));
-        if (prob_host)
-            B200VAD_CUDA(cudaMemcpyAsync(prob_host + (size_t)b0 * T, s->prob_dev[buf], sizeof(float) * (size_t)bc * T,
-                                         cudaMemcpyDeviceToHost, s->compute_stream));
-        B200VAD_CUDA(cudaEventRecord(s->consumed[buf], s->compute_stream));
-    }
-    B200VAD_CUDA(cudaStreamSynchronize(s->compute_stream));
     int64_t total = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * s->chunk;
-        int64_t n = s->totals_host[c];
-        int64_t take = std::max<int64_t>(0, std::min<int64_t>(n, cap - total));
-        if (take > 0)
-            B200VAD_CUDA(cudaMemcpyAsync(seg_host + 3 * total, s->seg_dev + 3 * (size_t)b0 * s->max_seg_per_row,
-                                         sizeof(int32_t) * 3 * take, cudaMemcpyDeviceToHost, s->compute_stream));
+    auto drain = [&](int c) -> int {
+        int64_t n = 0;
+        int rc = session_wait(s, c & 1, seg_host ? seg_host + 3 * std::min(total, cap) : nullptr,
+                              std::max<int64_t>(0, cap - total), &n);
         total += n;
+        return rc;
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * s->chunk, bc = std::min(s->chunk, B - b0);
+        int rc;
+        if (c >= 2 && (rc = drain(c - 2))) return rc;
+        rc = session_submit(s, c & 1, wav_host + (size_t)b0 * N, bc, b0, thr, kernel,
+                            dec_host ? dec_host + (size_t)b0 * T : nullptr, prob_host ? prob_host + (size_t)b0 * T : nullptr);
+        if (rc) return rc;
     }
-    B200VAD_CUDA(cudaStreamSynchronize(s->compute_stream));
+    for (int c = std::max(0, nchunks - 2); c < nchunks; ++c) {
+        int rc = drain(c);
+        if (rc) return rc;
+    }
     *nseg = total;
     return B200VAD_OK;
 }
@@ -714,20 +792,29 @@ int b200vad_session_run_host(b200vad_session* s, const float* wav_host, int B, f
 void b200vad_session_destroy(b200vad_session* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->compute_stream) cudaStreamSynchronize(s->compute_stream);
+    if (s->d2h_stream) cudaStreamSynchronize(s->d2h_stream);
     for (int i = 0; i < 2; ++i) {
-        if (s->wav_dev[i]) cudaFree(s->wav_dev[i]);
-        if (s->prob_dev[i]) cudaFree(s->prob_dev[i]);
-        if (s->dec_dev[i]) cudaFree(s->dec_dev[i]);
-        if (s->copied[i]) cudaEventDestroy(s->copied[i]);
-        if (s->consumed[i]) cudaEventDestroy(s->consumed[i]);
+        SessionSlot& sl = s->slot[i];
+        if (sl.wav_dev) cudaFree(sl.wav_dev);
+        if (sl.prob_dev) cudaFree(sl.prob_dev);
+        if (sl.dec_dev) cudaFree(sl.dec_dev);
+        if (sl.counts_dev) cudaFree(sl.counts_dev);
+        if (sl.seg_off_dev) cudaFree(sl.seg_off_dev);
+        if (sl.seg_dev) cudaFree(sl.seg_dev);
+        if (sl.total_host) cudaFreeHost(sl.total_host);
+        if (sl.copy_begin) cudaEventDestroy(sl.copy_begin);
+        if (sl.compute_begin) cudaEventDestroy(sl.compute_begin);
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.computed) cudaEventDestroy(sl.computed);
+        if (sl.drained) cudaEventDestroy(sl.drained);
     }
-    if (s->counts_dev) cudaFree(s->counts_dev);
-    if (s->seg_off_dev) cudaFree(s->seg_off_dev);
-    if (s->seg_dev) cudaFree(s->seg_dev);
     if (s->ws) cudaFree(s->ws);
-    if (s->totals_host) cudaFreeHost(s->totals_host);
+    if (s->epoch) cudaEventDestroy(s->epoch);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->compute_stream) cudaStreamDestroy(s->compute_stream);
+    if (s->d2h_stream) cudaStreamDestroy(s->d2h_stream);
+    if (s->seg_stream) cudaStreamDestroy(s->seg_stream);
     delete s;
 }
 

@@ -6,15 +6,16 @@
 // mirror padding (snip_edges=False), 400/160 framing, povey window, zero-pad to 512,
 // real FFT, power spectrum, 80 Kaldi mel triangles, log(max(., eps)).
 //
-// One CTA = 32 consecutive frames of one utterance.  The pre-emphasised span
+// One CTA (128 threads) = 32 consecutive frames of one utterance.  The pre-emphasised span
 // (31*160+400 samples) is staged once in shared memory with float4 loads, so every
 // waveform sample is read from HBM once (plus the 5 % tile halo, an L2 hit).
 // FFT: 512-point real FFT as a 256-point complex FFT, 16 threads per frame, two
 // radix-16 passes held in registers with one padded shared-memory transpose between
-// them; then real-FFT untangling + |X|^2, the sparse mel triangles (each FFT bin feeds
-// at most two filters) and the log, written as coalesced 320-byte rows.
+// them; real-FFT untangling on conjugate pairs (k, 256-k) + |X|^2, the sparse mel
+// triangles and the log, all inside the frame's own half-warp (no CTA barriers).
 // HBM traffic per frame: 640 B in + 320 B out = 960 B (algorithmic); intermediates
-// (frames, spectrum, power) never leave the SM.
+// (frames, spectrum, power) never leave the SM.  The kernel is FP32-issue bound, not HBM
+// bound: ~13 k thread-instructions per frame.
 #include "kernels.cuh"
 #include <math.h>
 #include <stdio.h>
@@ -24,10 +25,10 @@ namespace b200vad {
 
 constexpr int kTileFrames = 32;
 constexpr int kSpan = (kTileFrames - 1) * kFrameShift + kFrameLen;   // 5360 samples
-constexpr int kFftThreads = 16;                                       // threads per frame
-constexpr int kFramesPerPass = 16;                                    // 256 threads / 16
+constexpr int kFbankThreads = 128;
+constexpr int kGroups = kFbankThreads / 16;                           // 16 threads per frame
 constexpr int kZStride = 17 * 16;                                     // padded 16x16 complex tile (float2 units)
-constexpr int kPowStride = 257;
+constexpr int kPowStride = 264;
 constexpr int kMaxMelWidth = 32;
 constexpr int kMelRows = 18;                                          // widest Kaldi triangle at 512/16 kHz spans 17 FFT bins
 
@@ -102,6 +103,20 @@ int fbank_tables_init(int device) {
 
 const FbankTables* fbank_tables(int device) {
     return (device >= 0 && device < 64) ? g_tables_dev[device] : nullptr;
+}
+
+// ---------------------------------------------------------------- zero fill
+// A kernel instead of cudaMemsetAsync: a memset may be executed by a copy engine, where it queues behind an
+// in-flight multi-GB H2D copy of the host session and stalls the whole compute stream (measured: 35 ms per step).
+__global__ void zero_f64_kernel(double* __restrict__ p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+int zero_f64_launch(double* p, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return B200VAD_OK;
+    zero_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, n);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
 }
 
 // ---------------------------------------------------------------- row sums (DC offset)
@@ -183,16 +198,16 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 }
 
 // ---------------------------------------------------------------- fused fbank kernel
+// CTA = 128 threads = 8 groups of 16 threads; a group owns one frame at a time and walks frames g, g+8, g+16, g+24 of
+// the 32-frame tile.  After the span is staged there is no CTA barrier: every hand-off (FFT transpose, conjugate
+// partners, power spectrum -> mel) stays inside the group's half-warp and needs only __syncwarp.
+// Per-thread constants (stage twiddles W256^(j k1), untangle twiddles W512^(j+16i), mel bin ranges) live in registers.
 struct FbankSmem {
     float y[kSpan];                                  // pre-emphasised samples of the tile
-    float2 z[kFramesPerPass * kZStride];             // FFT transpose scratch
-    float pw[kTileFrames * kPowStride];              // power spectra of the tile
-    float2 tw256[256];
-    float2 tw512[257];
+    float2 z[kGroups * kZStride];                    // per-group FFT transpose / partner scratch
+    float pw[kGroups * kPowStride];                  // per-group power spectrum (x4) of the frame in flight
     float window[kFrameLen];
     float mel_wt[kMelRows][kNumMel];
-    int mel_start[kNumMel];
-    int mel_len[kNumMel];
 };
 
 __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
@@ -201,7 +216,7 @@ __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
     return __fsub_rn(a, __fmul_rn(0.97f, b));
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kFbankThreads, 4)
 fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, int64_t N, int64_t stride,
              const double* __restrict__ sums, const FbankTables* __restrict__ tab,
              float* __restrict__ feats, int64_t T_out) {
@@ -215,7 +230,7 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     float* out_row = feats + ((int64_t)b * T_out) * kNumMel;
 
     if (f0 >= T) {   // tile entirely in the padding: lhotse pads features with LOG_EPSILON
-        for (int i = tid; i < kTileFrames * kNumMel; i += 256) {
+        for (int i = tid; i < kTileFrames * kNumMel; i += kFbankThreads) {
             int64_t f = f0 + i / kNumMel;
             if (f < T_out) out_row[f * kNumMel + (i % kNumMel)] = kLogEpsilon;
         }
@@ -224,13 +239,24 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     const int nframes = (int)min((int64_t)kTileFrames, T - f0);
     const float* row = wav + (int64_t)b * stride;
     const float mean = (float)(sums[b] / (double)n);
+    const int g = tid >> 4;         // group = frame slot
+    const int j = tid & 15;         // lane within the group
 
-    // constant tables -> smem
-    for (int i = tid; i < 256; i += 256) sm.tw256[i] = tab->tw256[i];
-    for (int i = tid; i < 257; i += 256) sm.tw512[i] = tab->tw512[i];
-    for (int i = tid; i < kFrameLen; i += 256) sm.window[i] = tab->window[i];
-    for (int i = tid; i < kMelRows * kNumMel; i += 256) (&sm.mel_wt[0][0])[i] = (&tab->mel_wt[0][0])[i];
-    if (tid < kNumMel) { sm.mel_start[tid] = tab->mel_start[tid]; sm.mel_len[tid] = tab->mel_len[tid]; }
+    // ---- per-thread constants (registers) and per-CTA tables (smem)
+    float2 tw[16];                  // W256^(j*k1), k1 = 1..15
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) tw[k1] = __ldg(&tab->tw256[(j * k1) & 255]);
+    float2 tq[8];                   // W512^(j + 16 i)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tq[i] = __ldg(&tab->tw512[j + 16 * i]);
+    int mstart[kNumMel / 16], mlen[kNumMel / 16];
+#pragma unroll
+    for (int i = 0; i < kNumMel / 16; ++i) {
+        mstart[i] = __ldg(&tab->mel_start[j + 16 * i]);
+        mlen[i] = __ldg(&tab->mel_len[j + 16 * i]);
+    }
+    for (int i = tid; i < kFrameLen; i += kFbankThreads) sm.window[i] = tab->window[i];
+    for (int i = tid; i < kMelRows * kNumMel; i += kFbankThreads) (&sm.mel_wt[0][0])[i] = (&tab->mel_wt[0][0])[i];
 
     // ---- stage the pre-emphasised span
     const int64_t start = f0 * kFrameShift - kPadLeft;               // original index of span[0]
@@ -239,7 +265,8 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     if (interior) {
         // start is a multiple of 8 samples -> 16-byte aligned float4 loads
         const float4* p = reinterpret_cast<const float4*>(row + start);
-        for (int i = tid; i < span / 4; i += 256) {
+#pragma unroll 4
+        for (int i = tid; i < span / 4; i += kFbankThreads) {
             float4 v = __ldg(p + i);
             float prev = __ldg(row + start + 4 * i - 1);
             float4 o;
@@ -250,7 +277,7 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
             *reinterpret_cast<float4*>(&sm.y[4 * i]) = o;
         }
     } else {
-        for (int s = tid; s < span; s += 256) {
+        for (int s = tid; s < span; s += kFbankThreads) {
             int64_t i = start + s;
             if (i < 0) i = -1 - i;                 // left mirror (edge sample repeated)
             if (i >= n) i = 2 * n - 1 - i;         // right mirror
@@ -262,12 +289,10 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     }
     __syncthreads();
 
-    // ---- FFT passes: 16 frames at a time, 16 threads per frame
-    const int fl = tid >> 4;        // frame slot within the pass
-    const int j = tid & 15;         // lane within the frame group
-    float2* zf = sm.z + fl * kZStride;
-    for (int pass = 0; pass < kTileFrames / kFramesPerPass; ++pass) {
-        const int f = pass * kFramesPerPass + fl;
+    float2* zf = sm.z + g * kZStride;
+    float* pw = sm.pw + g * kPowStride;
+    for (int pass = 0; pass < kTileFrames / kGroups; ++pass) {
+        const int f = pass * kGroups + g;
         const bool active = f < nframes;
         float2 v[16];
         if (active) {
@@ -275,8 +300,8 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
             // z[16*n1 + j] = (xw[32*n1 + 2j], xw[32*n1 + 2j + 1]); samples >= 400 are zero padding
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
-                int s = 32 * n1 + 2 * j;
-                if (s < kFrameLen) {
+                const int s = 32 * n1 + 2 * j;
+                if (n1 < 12 || (n1 == 12 && j < 8)) {
                     float2 yy = *reinterpret_cast<const float2*>(ys + s);
                     float2 ww = *reinterpret_cast<const float2*>(sm.window + s);
                     v[n1] = make_float2(yy.x * ww.x, yy.y * ww.y);
@@ -285,68 +310,59 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
                 }
             }
             fft16(v);                                                  // over n1 -> k1
+            zf[j] = v[0];
 #pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) {
-                float2 w = sm.tw256[(j * k1) & 255];
-                zf[k1 * 17 + j] = (k1 == 0) ? v[k1] : cmul(v[k1], w);
-            }
+            for (int k1 = 1; k1 < 16; ++k1) zf[k1 * 17 + j] = cmul(v[k1], tw[k1]);
         }
         __syncwarp();
         if (active) {
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) v[n2] = zf[j * 17 + n2];    // thread j := k1
+            fft16(v);                                                  // over n2 -> k2 ; v[k2] = Z[j + 16*k2]
         }
         __syncwarp();
         if (active) {
-            fft16(v);                                                  // over n2 -> k2 ; Z[k1 + 16*k2]
+            // conjugate partners: Z[256 - (j + 16 i)] = Z[(16 - j) + 16 (15 - i)] sits in the upper half (k2 >= 8) of
+            // thread 16 - j; slot (k2 - 8) * 16 + j, so the partner of (j, i) is slot (8 - i) * 16 - j (slot 128 = Z[0])
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) zf[j + 16 * k2] = v[k2];
+            for (int k2 = 8; k2 < 16; ++k2) zf[(k2 - 8) * 16 + j] = v[k2];
+            if (j == 0) zf[128] = v[0];
         }
         __syncwarp();
         if (active) {
-            // real-FFT untangle + power: X[k] = E + w^k * O,  E=(Zk+conj(Z(256-k)))/2, O=(Zk-conj(Z(256-k)))/(2i)
-            float* pw = sm.pw + f * kPowStride;
+            // real-FFT untangle, two bins per pair: 2Xe = a + conj(c), 2 w^k Xo = T,  4|X[k]|^2 = |2Xe + T|^2,
+            // 4|X[256-k]|^2 = |2Xe - T|^2   (a = Z[k], c = Z[256-k], k = j + 16 i)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                int k = j + 16 * i;
-                float2 a = zf[k];
-                float2 c = zf[(256 - k) & 255];
-                float er = 0.5f * (a.x + c.x), ei = 0.5f * (a.y - c.y);
-                float orr = 0.5f * (a.y + c.y), oi = -0.5f * (a.x - c.x);
-                float2 w = sm.tw512[k];
-                float xr = er + (w.x * orr - w.y * oi);
-                float xi = ei + (w.x * oi + w.y * orr);
-                pw[k] = xr * xr + xi * xi;
+            for (int i = 0; i < 8; ++i) {
+                const float2 a = v[i];
+                const float2 c = zf[(8 - i) * 16 - j];
+                const float sr = a.x + c.x, si = a.y - c.y;
+                const float dr = a.x - c.x, di = a.y + c.y;
+                const float tr = tq[i].x * di + tq[i].y * dr;
+                const float ti = tq[i].y * di - tq[i].x * dr;
+                const float pr = sr + tr, pi = si + ti, qr = sr - tr, qi = si - ti;
+                pw[j + 16 * i] = pr * pr + pi * pi;
+                pw[256 - j - 16 * i] = qr * qr + qi * qi;
             }
-            if (j == 0) {
-                float2 a = zf[0];
-                float x = a.x - a.y;          // X[256] = Re Z0 - Im Z0
-                pw[256] = x * x;
-            }
+            if (j == 0) pw[128] = 4.f * (v[8].x * v[8].x + v[8].y * v[8].y);   // X[128] = conj(Z[128])
         }
         __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- mel triangles + log: thread = (mel bin m, group of 4 frames); one weight load feeds 4 FMAs; consecutive
-    // threads = consecutive bins, so weight reads are conflict-free and the output rows are coalesced (320 B)
-    constexpr int kFrameGroup = 4;
-    for (int idx = tid; idx < (kTileFrames / kFrameGroup) * kNumMel; idx += 256) {
-        const int grp = idx / kNumMel, m = idx - grp * kNumMel;
-        const int fb = grp * kFrameGroup;
-        const int start = sm.mel_start[m], len = sm.mel_len[m];
-        const float* pw = sm.pw + fb * kPowStride + start;
-        float acc[kFrameGroup] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < len; ++k) {
-            const float w = sm.mel_wt[k][m];
+        // ---- mel triangles + log: lane j owns bins j, j+16, ..., j+64 of its group's frame (64-byte output runs)
+        const int64_t fr = f0 + f;
+        if (active) {
 #pragma unroll
-            for (int j = 0; j < kFrameGroup; ++j) acc[j] = fmaf(pw[j * kPowStride + k], w, acc[j]);
-        }
+            for (int i = 0; i < kNumMel / 16; ++i) {
+                const int m = j + 16 * i;
+                const float* p = pw + mstart[i];
+                float acc = 0.f;
+                for (int k = 0; k < mlen[i]; ++k) acc = fmaf(p[k], sm.mel_wt[k][m], acc);
+                out_row[fr * kNumMel + m] = __logf(fmaxf(0.25f * acc, kEpsilon));
+            }
+        } else if (fr < T_out) {
 #pragma unroll
-        for (int j = 0; j < kFrameGroup; ++j) {
-            const int64_t fr = f0 + fb + j;
-            if (fr < T_out) out_row[fr * kNumMel + m] = (fb + j < nframes) ? logf(fmaxf(acc[j], kEpsilon)) : kLogEpsilon;
+            for (int i = 0; i < kNumMel / 16; ++i) out_row[fr * kNumMel + j + 16 * i] = kLogEpsilon;
         }
+        __syncwarp();
     }
 }
 
@@ -363,12 +379,13 @@ int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_
         B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
         attr_set[device] = true;
     }
-    B200VAD_CUDA(cudaMemsetAsync(row_sums, 0, sizeof(double) * B, stream));
+    int rc = zero_f64_launch(row_sums, B, stream);
+    if (rc) return rc;
     dim3 g1((unsigned)((N + 256 * 32 - 1) / (256 * 32)), B);
     row_sum_kernel<<<g1, 256, 0, stream>>>(wav, lens, N, stride, row_sums);
     B200VAD_LAUNCH_CHECK();
     dim3 g2((unsigned)((T_out + kTileFrames - 1) / kTileFrames), B);
-    fbank_kernel<<<g2, 256, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, T_out);
+    fbank_kernel<<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, T_out);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

@@ -1,19 +1,24 @@
-// tcgen05 projection GEMM:  C[M,N] (fp32) = A_hi.W_hi^T + A_lo.W_hi^T (+ A_hi.W_lo^T) + bias
+// tcgen05 projection GEMM:  C[M,N] = X_hi.W_hi^T + X_lo.W_hi^T (+ X_hi.W_lo^T) + bias   (fp32 accumulate in TMEM)
 //
 // Computes the LSTM input projections x_t.W_ih^T + b_ih + b_hh for all timesteps and both
-// directions (nn.LSTM of PyanNet2.py:95,170) in split precision: activations arrive as two fp16
-// planes (hi, lo: hi + lo = the fp32 value to ~22 bits), weights as fp16 hi (+ lo for layer 0,
-// whose inputs are un-normalised log-mel values), accumulation in fp32 in TMEM.
+// directions (nn.LSTM of PyanNet2.py:95,170) and the head linears (PyanNet2.py:183-185) in split
+// precision: activations arrive as two fp16 planes (hi, lo: hi + lo = the fp32 value to ~22
+// bits), weights as fp16 hi + lo planes.
 //
-// Persistent, warp-specialised, one CTA per SM (grid = multiple of the number of 256-column
-// ranges): CTA c owns column range c % n_ranges and keeps that range's weights RESIDENT in shared
-// memory for its whole life (W is the B operand: K-major, 128B-swizzled, written once by TMA), and
-// streams 128-row A tiles.  Warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (single thread),
-// warps 2-5 = epilogue.  The 128x256 fp32 accumulator is double-buffered in TMEM (2 x 256 columns),
-// so the epilogue of tile i (tcgen05.ld -> +bias -> swizzled smem -> TMA store) overlaps the MMAs of
-// tile i+1.  The CTAs that share an A tile (the n_ranges column ranges of one row block) run
-// concurrently, so A is fetched from HBM once and hits L2 for the others.
-// Roofline: 2 x 13.4 GB of fp32 output per layer at B*T = 3.28 M rows -> HBM-write bound (~2 ms).
+// The OUTPUT FEATURE dimension is the MMA M: a CTA owns 128 output features for its whole life and
+// keeps their weight rows (hi and lo planes, up to K = 256) RESIDENT IN TENSOR MEMORY as the A
+// operand (lane = feature, two fp16 k-elements per column).  Activation rows are the MMA N: 128-row
+// tiles stream through a TMA ring as the (K-major, 128B-swizzled) B operand.  An SS-mode MMA would
+// re-read a 4 KB weight slice from shared memory per instruction; with the weights in TMEM the
+// shared-memory traffic is the streamed operand only (v1 of this kernel kept the weights in smem
+// and ran at 45 % tensor-pipe utilisation, bound by shared-memory bandwidth -- profiles/r01_gemm.md).
+// Persistent, warp-specialised, one CTA per SM: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
+// (single thread), warps 2-5 = epilogue.  The 128 x 128 fp32 accumulator is double-buffered in TMEM,
+// so the epilogue of tile i overlaps the MMAs of tile i+1.  In the accumulator a TMEM lane is an
+// output feature and a column is a row, so the epilogue thread of lane f writes feature f of 32
+// consecutive rows: each store instruction of a warp covers one contiguous 128-byte run of a row --
+// straight from registers, no shared-memory staging.  The n_blocks CTAs that share an activation
+// tile run concurrently, so it is fetched from HBM once and hits L2 for the others.
 #include "kernels.cuh"
 #include "tc05.cuh"
 
@@ -21,93 +26,85 @@ namespace b200vad {
 
 using namespace tc;
 
-constexpr int TBM = 128;                 // rows per tile (UMMA M)
-constexpr int TBK = 64;                  // k per smem tile (128 bytes of fp16 = one swizzle atom row)
-constexpr int A_TILE_BYTES = TBM * TBK * 2;          // 16 KB
-constexpr int EPI_CHUNK = 32;                          // fp32 columns per TMA store (128 bytes)
-constexpr int EPI_BYTES = TBM * EPI_CHUNK * 4;         // 16 KB
-constexpr int GEMM_TC_THREADS = 192;
+constexpr int SBM = 128;                 // activation rows per tile (UMMA N)
+constexpr int SBK = 64;                  // k per smem tile (128 bytes of fp16 = one swizzle atom row)
+constexpr int S_TILE_BYTES = SBM * SBK * 2;          // 16 KB
+constexpr int GEMM_TS_THREADS = 192;
+constexpr int ACC_COL = 256;             // TMEM columns [0, 256): weights, [256, 512): two 128-column accumulators
 
-struct GemmTcParams {
-    const float* bias;       // [N]
+struct GemmTsParams {
+    const __half* w_hi;      // [N][Kp] fp16, zero padded
+    const __half* w_lo;      // [N][Kp] or null
+    const float* bias;       // [N] or null
+    float* c;                // modes 0, 2: [M][ldc] fp32
+    __half* o_hi;            // mode 1: [M][ldc] fp16 planes
+    __half* o_lo;
+    int64_t ldc;
+    int64_t c_block_stride;  // mode 0: 0 = row-major [M][ldc]; else feature-blocked [N/128][M][128] (elements between blocks)
+    int64_t M;
     int num_m_tiles;
-    int n_ranges;            // N / BN
+    int n_blocks;            // N / 128
     int kb;                  // k-blocks of 64
-    int nw;                  // weight planes resident: 1 (hi) or 2 (hi, lo)
-    int stages;              // A pipeline depth
+    int nw;                  // weight planes: 1 (hi) or 2 (hi, lo)
+    int stages;              // activation pipeline depth
+    int Kp;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-               const __grid_constant__ CUtensorMap tm_c, GemmTcParams p) {
+// MODE 0: C = acc + bias (fp32)      MODE 1: leaky_relu(acc + bias) -> fp16 (hi, lo) planes      MODE 2: leaky_relu -> fp32
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_TS_THREADS, 1)
+gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo, GemmTsParams p) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    constexpr int W_TILE_BYTES = BN * TBK * 2;
-    const uint32_t w_base = smem_base;                                        // [nw][kb] tiles of BN x 64
-    const uint32_t a_base = w_base + p.nw * p.kb * W_TILE_BYTES;              // [stages][hi, lo] tiles of 128 x 64
-    const uint32_t epi_base = a_base + p.stages * 2 * A_TILE_BYTES;          // [2] staging tiles 128 x 32 fp32
-    const uint32_t bar_base = epi_base + 2 * EPI_BYTES;
-    // barriers: w_full | a_full[8] | a_empty[8] | acc_full[2] | acc_empty[2]
-    const uint32_t bar_w = bar_base;
-    auto bar_a_full = [&](int s) { return bar_base + 8 + 8 * s; };
-    auto bar_a_empty = [&](int s) { return bar_base + 8 + 64 + 8 * s; };
-    auto bar_acc_full = [&](int b) { return bar_base + 8 + 128 + 8 * b; };
-    auto bar_acc_empty = [&](int b) { return bar_base + 8 + 144 + 8 * b; };
-    const uint32_t tmem_slot = bar_base + 8 + 160;
-    const uint32_t bias_smem = bar_base + 256;                                // BN floats (16-byte aligned)
+    const uint32_t a_base = smem_base;                                        // [stages][hi, lo] tiles of 128 x 64
+    const uint32_t bar_base = a_base + p.stages * 2 * S_TILE_BYTES;
+    auto bar_a_full = [&](int s) { return bar_base + 8 * s; };
+    auto bar_a_empty = [&](int s) { return bar_base + 64 + 8 * s; };
+    auto bar_acc_full = [&](int b) { return bar_base + 128 + 8 * b; };
+    auto bar_acc_empty = [&](int b) { return bar_base + 144 + 8 * b; };
+    const uint32_t bar_w = bar_base + 160;
+    const uint32_t tmem_slot = bar_base + 168;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int range = blockIdx.x % p.n_ranges;
-    const int n0 = range * BN;
-    const int tile0 = blockIdx.x / p.n_ranges;
-    const int tile_step = gridDim.x / p.n_ranges;
+    const int blk = blockIdx.x % p.n_blocks;
+    const int tile0 = blockIdx.x / p.n_blocks;
+    const int tile_step = gridDim.x / p.n_blocks;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_w, 1);
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 128); }
+        mbar_init(bar_w, 128);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < BN; i += 128) {
-            float b = p.bias ? p.bias[n0 + i] : 0.f;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4 * i), "f"(b) : "memory");
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int wcols = p.Kp >> 1;                                              // TMEM columns per weight plane
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer: activation tiles =====================
         if (elect_one()) {
-            tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_c);
-            mbar_expect_tx(bar_w, p.nw * p.kb * W_TILE_BYTES);
-            for (int w = 0; w < p.nw; ++w)
-                for (int kb = 0; kb < p.kb; ++kb)
-                    tma_load_2d(w_base + (w * p.kb + kb) * W_TILE_BYTES, w == 0 ? &tm_w_hi : &tm_w_lo, kb * TBK, n0, bar_w);
+            tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
             int s = 0;
             uint32_t ph = 0;
             for (int t = tile0; t < p.num_m_tiles; t += tile_step) {
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_a_empty(s), ph ^ 1);
-                    mbar_expect_tx(bar_a_full(s), 2 * A_TILE_BYTES);
-                    tma_load_2d(a_base + (2 * s) * A_TILE_BYTES, &tm_a_hi, kb * TBK, t * TBM, bar_a_full(s));
-                    tma_load_2d(a_base + (2 * s + 1) * A_TILE_BYTES, &tm_a_lo, kb * TBK, t * TBM, bar_a_full(s));
+                    mbar_expect_tx(bar_a_full(s), 2 * S_TILE_BYTES);
+                    tma_load_2d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, t * SBM, bar_a_full(s));
+                    tma_load_2d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, t * SBM, bar_a_full(s));
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer: D[out, row] += W[out, k] . X[row, k] =====================
         if (elect_one()) {
-            constexpr uint32_t idesc = idesc_f16(TBM, BN);
-            mbar_wait(bar_w, 0);
+            constexpr uint32_t idesc = idesc_f16(128, SBM);
+            mbar_wait(bar_w, 0);                                                // weights are in TMEM
             tc_fence_after();
             int s = 0;
             uint32_t ph = 0;
@@ -117,71 +114,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const uint32_t acc_ph = (it >> 1) & 1;
                 mbar_wait(bar_acc_empty(ab), acc_ph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + ab * BN;
+                const uint32_t d_tmem = tmem_base + ACC_COL + ab * SBM;
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_a_full(s), ph);
                     tc_fence_after();
-                    const uint32_t a_hi = a_base + (2 * s) * A_TILE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t w_hi = w_base + kb * W_TILE_BYTES, w_lo = w_base + (p.kb + kb) * W_TILE_BYTES;
+                    const uint32_t x_hi = a_base + (2 * s) * S_TILE_BYTES, x_lo = x_hi + S_TILE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k) {
-                        const uint64_t da_hi = smem_desc_sw128(a_hi + k * 32), da_lo = smem_desc_sw128(a_lo + k * 32);
-                        const uint64_t dw_hi = smem_desc_sw128(w_hi + k * 32);
-                        mma_f16(d_tmem, da_lo, dw_hi, idesc, (kb | k) != 0);          // small terms first
-                        if (p.nw == 2) mma_f16(d_tmem, da_hi, smem_desc_sw128(w_lo + k * 32), idesc, 1);
-                        mma_f16(d_tmem, da_hi, dw_hi, idesc, 1);
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_lo = w_hi + wcols;
+                        const uint64_t dx_hi = smem_desc_sw128(x_hi + k * 32), dx_lo = smem_desc_sw128(x_lo + k * 32);
+                        mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);            // small terms first
+                        if (p.nw == 2) mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        mma_f16_ts(d_tmem, w_hi, dx_hi, idesc, 1);
                     }
-                    mma_commit(bar_a_empty(s));                                 // frees the A stage when the MMAs retire
+                    mma_commit(bar_a_empty(s));                                 // frees the stage when the MMAs retire
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
                 mma_commit(bar_acc_full(ab));                                   // accumulator ready for the epilogue
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+        // ===================== weights -> TMEM, then epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
         const int q = warp & 3;
-        const int row = q * 32 + lane;                                          // row of the tile == TMEM lane
-        const int et = threadIdx.x - 64;                                        // 0..127
+        const int out = blk * 128 + q * 32 + lane;                              // output feature == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int w = 0; w < p.nw; ++w) {
+            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.Kp);
+            for (int part = 0; part < p.Kp / 32; ++part) {                      // 32 fp16 = 16 packed columns
+                uint32_t r[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 v = __ldg(wrow + part * 4 + i);
+                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+                }
+                tmem_st16(lane_addr + w * wcols + part * 16, r);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_w);
+        const float bias = p.bias ? __ldg(p.bias + out) : 0.f;
+        // blocked output: this CTA's 128 features of consecutive rows are contiguous (64 KB per tile, one DRAM stream)
+        const int64_t col_off = (MODE == 0 && p.c_block_stride) ? (int64_t)blk * p.c_block_stride + q * 32 + lane : out;
         int it = 0;
-        int chunk_ctr = 0;
         for (int t = tile0; t < p.num_m_tiles; t += tile_step, ++it) {
             const int ab = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
             mbar_wait(bar_acc_full(ab), acc_ph);
             tc_fence_after();
+            const int64_t row0 = (int64_t)t * SBM;
+            const int nrows = (int)min((int64_t)SBM, p.M - row0);
 #pragma unroll 1
-            for (int c = 0; c < BN / EPI_CHUNK; ++c, ++chunk_ctr) {
+            for (int c = 0; c < SBM / 32; ++c) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + c * EPI_CHUNK, v);
+                tmem_ld32(lane_addr + ACC_COL + ab * SBM + c * 32, v);
                 tmem_ld_wait();
-                if (c == BN / EPI_CHUNK - 1) {
+                if (c == SBM / 32 - 1) {
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(ab));                             // 128 arrivals release the accumulator
                 }
-                const int buf = chunk_ctr & 1;
-                // the TMA store that last read staging[buf] (two chunks ago) must have finished reading
-                if (et == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
-                const uint32_t stage = epi_base + buf * EPI_BYTES + row * 128;
+                // lane = output feature, register j = row: every store instruction writes one contiguous run per warp
+                const int64_t base = (row0 + c * 32) * p.ldc + col_off;
+                const int lim = nrows - c * 32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 o;
-                    float4 bb;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
-                                 : "r"(bias_smem + 4 * (c * EPI_CHUNK + 4 * j)));
-                    o.x = v[4 * j] + bb.x; o.y = v[4 * j + 1] + bb.y; o.z = v[4 * j + 2] + bb.z; o.w = v[4 * j + 3] + bb.w;
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + ((j ^ (row & 7)) << 4)), "f"(o.x), "f"(o.y),
-                                 "f"(o.z), "f"(o.w) : "memory");
-                }
-                fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (et == 0) {
-                    tma_store_2d(&tm_c, n0 + c * EPI_CHUNK, t * TBM, epi_base + buf * EPI_BYTES);
-                    tma_store_commit();
+                for (int j = 0; j < 32; ++j) {
+                    if (j < lim) {
+                        float x = v[j] + bias;
+                        if (MODE != 0) x = x > 0.f ? x : 0.01f * x;
+                        if (MODE == 1) {
+                            __half hh, hl;
+                            split_f16(x, hh, hl);
+                            p.o_hi[base + j * p.ldc] = hh;
+                            p.o_lo[base + j * p.ldc] = hl;
+                        } else {
+                            p.c[base + j * p.ldc] = x;
+                        }
+                    }
                 }
             }
         }
-        if (et == 0) tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -270,58 +281,67 @@ int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
     return B200VAD_OK;
 }
 
+int make_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, const uint64_t dims[4], const uint64_t pitch_bytes[3],
+                 const uint32_t box[4], CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return B200VAD_ESTATE;
+    }
+    cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t st[3] = {pitch_bytes[0], pitch_bytes[1], pitch_bytes[2]};
+    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, dtype, 4, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
+        return B200VAD_ECUDA;
+    }
+    return B200VAD_OK;
+}
+
 // ---------------------------------------------------------------- launcher
 // a_hi/a_lo: [M, K] fp16 (row pitch lda elements, lda % 8 == 0);  w_hi/w_lo: [N, Kp] fp16 (Kp % 64 == 0, zero padded);
-// c: [M, N] fp32 (ldc % 4 == 0).  N must be a multiple of 128.  w_lo may be null (2-term product).
-int gemm_tc_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
-                   int Kp, int N, const float* bias, float* c, int64_t ldc, int num_sms, cudaStream_t st) {
+// N must be a multiple of 128 and planes * Kp <= 512 (weights resident in 256 TMEM columns).  w_lo may be null.
+// mode 0: c fp32 = acc + bias, row-major [M][ldc] or (c_block_stride != 0, ldc = 128) feature-blocked [N/128][M][128];  mode 1: leaky_relu -> fp16 planes o_hi / o_lo [M, ldc];  mode 2: leaky_relu -> c fp32.
+int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
+                   int Kp, int N, const float* bias, int mode, float* c, __half* o_hi, __half* o_lo, int64_t ldc,
+                   int64_t c_block_stride, int num_sms, cudaStream_t st) {
     if (M <= 0) return B200VAD_OK;
-    if (N % 128 != 0 || Kp % 64 != 0 || lda % 8 != 0 || ldc % 4 != 0 || K > Kp) {
-        set_error("gemm_tc: unsupported shape N=%d K=%d Kp=%d lda=%lld ldc=%lld", N, K, Kp, (long long)lda, (long long)ldc);
+    const int nw = w_lo ? 2 : 1;
+    if (N % 128 != 0 || Kp % 64 != 0 || lda % 8 != 0 || K > Kp || nw * Kp > 512 || mode < 0 || mode > 2) {
+        set_error("gemm_ts: unsupported shape N=%d K=%d Kp=%d planes=%d lda=%lld mode=%d", N, K, Kp, nw, (long long)lda, mode);
         return B200VAD_EINVAL;
     }
-    GemmTcParams p;
-    p.bias = bias;
-    p.num_m_tiles = (int)((M + TBM - 1) / TBM);
-    p.kb = Kp / TBK;
-    p.nw = w_lo ? 2 : 1;
-    // widest column range whose weights (all planes, all of K) stay resident and leave >= 2 A stages
-    const int max_smem = 227 * 1024;
-    int BN = 0, fixed = 0, w_bytes = 0;
-    for (int cand : {256, 128}) {
-        if (N % cand) continue;
-        w_bytes = p.nw * p.kb * cand * TBK * 2;
-        fixed = w_bytes + 2 * EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/ + cand * 4 + 256;
-        if ((max_smem - fixed) / (2 * A_TILE_BYTES) >= 2) { BN = cand; break; }
-    }
-    if (!BN) {
-        set_error("gemm_tc: weights (%d planes x %d x K=%d) do not fit in shared memory", p.nw, N, Kp);
-        return B200VAD_EINVAL;
-    }
-    p.n_ranges = N / BN;
-    p.stages = (max_smem - fixed) / (2 * A_TILE_BYTES);
-    if (p.stages > 8) p.stages = 8;
-    const int smem = fixed + p.stages * 2 * A_TILE_BYTES;
-    CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, tm_c;
+    GemmTsParams p;
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = c; p.o_hi = o_hi; p.o_lo = o_lo; p.ldc = ldc; p.c_block_stride = c_block_stride; p.M = M;
+    p.num_m_tiles = (int)((M + SBM - 1) / SBM);
+    p.n_blocks = N / 128;
+    p.kb = Kp / SBK;
+    p.nw = nw;
+    p.Kp = Kp;
+    p.stages = 6;
+    const int smem = 1024 + p.stages * 2 * S_TILE_BYTES + 256;
+    CUtensorMap tm_a_hi, tm_a_lo;
     int rc;
-    if ((rc = make_tmap_2d(&tm_a_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, TBK, TBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_2d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, TBK, TBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_2d(&tm_w_hi, w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kp, N, (uint64_t)Kp * 2, TBK, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_2d(&tm_w_lo, w_lo ? w_lo : w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kp, N, (uint64_t)Kp * 2, TBK, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_2d(&tm_c, c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N, M, ldc * 4, EPI_CHUNK, TBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    int grid = (num_sms / p.n_ranges) * p.n_ranges;
-    if (grid < p.n_ranges) grid = p.n_ranges;
-    int max_grid = p.num_m_tiles * p.n_ranges;
-    if (grid > max_grid) grid = max_grid;
+    if ((rc = make_tmap_2d(&tm_a_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_2d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    int grid = (num_sms / p.n_blocks) * p.n_blocks;
+    if (grid < p.n_blocks) grid = p.n_blocks;
+    const int64_t max_grid = (int64_t)p.num_m_tiles * p.n_blocks;
+    if (grid > max_grid) grid = (int)max_grid;
+    static bool attr[3] = {false, false, false};
     prof_begin(1, st);
-    if (BN == 256) {
-        static bool attr = false;
-        if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); attr = true; }
-        gemm_tc_kernel<256><<<grid, GEMM_TC_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, tm_c, p);
+    if (mode == 0) {
+        if (!attr[0]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
+        gemm_ts_kernel<0><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
+    } else if (mode == 1) {
+        if (!attr[1]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
+        gemm_ts_kernel<1><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
     } else {
-        static bool attr = false;
-        if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); attr = true; }
-        gemm_tc_kernel<128><<<grid, GEMM_TC_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo, tm_c, p);
+        if (!attr[2]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[2] = true; }
+        gemm_ts_kernel<2><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
     }
     prof_end(1, st);
     B200VAD_LAUNCH_CHECK();

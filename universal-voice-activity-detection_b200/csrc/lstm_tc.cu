@@ -20,8 +20,9 @@
 //     two warpgroups of 16 columns (4 warps per scheduler on the ex2/rcp dependency chains);
 //   * cell state c lives in shared memory (fp32, conflict-free), so the column loop is a real loop;
 //   * xg is the only HBM read stream (4 KB per sequence-step-direction): warp 17 feeds it through a
-//     4-stage TMA ring per warpgroup (4 columns x 512 gates per stage, 128 KB in flight per SM)
-//     (optional L2 prefetch ahead of the ring measured no gain and is off by default).
+//     4-stage TMA ring per warpgroup (4 columns x 512 gates per stage, 128 KB in flight per SM); xg is stored
+//     feature-blocked ([dir, gate][B][T][128]) so that the GEMM writes, and this kernel reads, long DRAM runs
+//     (an L2 prefetch ahead of the ring measured no gain -- profiles/r01_lstm_ablation.md).
 // Per step and CTA: 2 x 64 tcgen05.mma (M128 N32 K16, A in TMEM), 8192 cells, 5 ex2 + 2 rcp per cell.
 // Algorithmic FLOPs: 2*128*512 per (sequence, frame, direction); algorithmic HBM bytes per
 // (sequence, frame, direction): 2048 (xg read) + 512 (y planes written).
@@ -40,7 +41,6 @@ constexpr int LWCOLS = LNB / LWG;          // 16 columns per warpgroup
 constexpr int LCH = 4;                     // columns per ring stage / inner chunk
 constexpr int LNCH = LWCOLS / LCH;         // chunks per step and warpgroup
 constexpr int LSTAGES = 4;                 // xg ring depth per warpgroup
-constexpr int LPF = 0;                     // L2 prefetch distance in steps (0 = off: measured no gain, profiles/r01_lstm_ablation.md)
 constexpr int LTC_THREADS = (LWG * 4 + 2) * 32;   // 576
 constexpr int H_TILE = LNB * 64 * 2;       // 8 KB
 constexpr int C_BYTES = LNB * kHidden * 4; // 32 KB cell state
@@ -53,7 +53,6 @@ struct LstmTcParams {
     float* y_f32;          // [B][T][256] (fp32 mode) or null (planes mode: TMA stores through tm_yhi / tm_ylo)
     int B, T;
     int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
-    int pf;                // L2 prefetch distance in steps (0 = off)
 };
 
 template <bool F32OUT>
@@ -101,21 +100,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
             uint32_t ph = 0;
             for (int s = 0; s < T; ++s) {
                 const int t = dir == 0 ? s : T - 1 - s;
-                if (p.pf > 0 && s + p.pf < T) {
-                    const int tp = dir == 0 ? t + p.pf : t - p.pf;
-#pragma unroll 1
-                    for (int ch = 0; ch < LNCH; ++ch) {
-                        tma_prefetch_l2_3d(&tm_xg, dir * kGates, tp, bcol + ch * LCH);
-                        tma_prefetch_l2_3d(&tm_xg, dir * kGates + 256, tp, bcol + ch * LCH);
-                    }
-                }
 #pragma unroll 1
                 for (int ch = 0; ch < LNCH; ++ch) {
                     mbar_wait(bar_x_empty(wg, st), ph ^ 1);
                     const uint32_t dst = smem_base + x_off + (wg * LSTAGES + st) * X_STAGE;
                     mbar_expect_tx(bar_x_full(wg, st), X_STAGE);
-                    tma_load_3d(dst, &tm_xg, dir * kGates, t, bcol + ch * LCH, bar_x_full(wg, st));
-                    tma_load_3d(dst + X_HALF, &tm_xg, dir * kGates + 256, t, bcol + ch * LCH, bar_x_full(wg, st));
+                    tma_load_4d(dst, &tm_xg, 0, t, bcol + ch * LCH, dir * 4, bar_x_full(wg, st));
+                    tma_load_4d(dst + X_HALF, &tm_xg, 0, t, bcol + ch * LCH, dir * 4 + 2, bar_x_full(wg, st));
                     if (++st == LSTAGES) { st = 0; ph ^= 1; }
                 }
             }
@@ -221,13 +212,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < LCH; ++j) x[g][j] = 0.1f * g;
                 } else {
-                    // xg chunk from the ring: stage = [(i,f) box | (g,o) box], box = [col][256]
+                    // xg chunk from the ring: stage = [(i,f) box | (g,o) box], box = [gate block (2)][col (4)][128]
                     mbar_wait(bar_x_full(wg, st), xph);
                     const float* xs = xring + st * (X_STAGE / 4);
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
 #pragma unroll
-                        for (int j = 0; j < LCH; ++j) x[g][j] = xs[(g >> 1) * (X_HALF / 4) + j * 256 + (g & 1) * 128];
+                        for (int j = 0; j < LCH; ++j) x[g][j] = xs[(g >> 1) * (X_HALF / 4) + (g & 1) * (LCH * 128) + j * 128];
                 }
                 tmem_ld_wait();
 #pragma unroll
@@ -271,13 +262,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     if (warp == 16) tmem_dealloc<512>(tmem_base);
 }
 
-// xg: [B][T][2][512] fp32; whh: [2][512][128] fp16 (gate-major rows, as nn.LSTM stores weight_hh).
+// xg: feature-blocked [8][B][T][128] fp32 (block = dir * 4 + gate, as gemm_ts writes it); whh: [2][512][128] fp16 (gate-major rows, as nn.LSTM stores weight_hh).
 // Exactly one of (y_hi, y_lo: fp16 planes [B][T][256]) / y_f32 is written.
 int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, float* y_f32, int B, int T, cudaStream_t st) {
     if (B <= 0 || T <= 0) return B200VAD_OK;
     CUtensorMap tm_x, tm_yh, tm_yl;
-    int rc = make_tmap_3d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2 * kGates, (uint64_t)T, (uint64_t)B, (uint64_t)2 * kGates * 4,
-                          (uint64_t)T * 2 * kGates * 4, 256, 1, LCH, CU_TENSOR_MAP_SWIZZLE_NONE);
+    // xg is feature-blocked: [8 blocks = (dir, gate)][B][T][128] fp32; one box = 2 gate blocks x LCH sequences of one step
+    const uint64_t xdims[4] = {128, (uint64_t)T, (uint64_t)B, 8};
+    const uint64_t xpitch[3] = {128 * 4, (uint64_t)T * 128 * 4, (uint64_t)B * T * 128 * 4};
+    const uint32_t xbox[4] = {128, 1, LCH, 2};
+    int rc = make_tmap_4d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, xdims, xpitch, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     const void* yh = y_f32 ? (const void*)whh : (const void*)y_hi;      // unused maps still have to be valid
     const void* yl = y_f32 ? (const void*)whh : (const void*)y_lo;
@@ -290,9 +284,7 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     if (rc) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("B200VAD_LSTM_PF"); pf = e ? atoi(e) : LPF; }
-    LstmTcParams p{whh, y_f32, B, T, dbg, pf};
+    LstmTcParams p{whh, y_f32, B, T, dbg};
     const int smem = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
     dim3 grid((B + LNB - 1) / LNB, 2);
     prof_begin(0, st);

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) wave_norm_kernel(const float* __restrict_
 }
 int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, const float* gamma, const float* beta,
                          double* stats, float* out, cudaStream_t s) {
-    B200VAD_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B, s));
+    { int rc = zero_f64_launch(stats, (int64_t)2 * B, s); if (rc) return rc; }
     dim3 g1((unsigned)((N + 8191) / 8192), B);
     wave_stats_kernel<<<g1, 256, 0, s>>>(wav, N, stride, stats);
     B200VAD_LAUNCH_CHECK();
@@ -179,7 +179,7 @@ int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pool
     }
     const int64_t P = L / 3;
     if (P <= 0 || B == 0) return B200VAD_OK;
-    B200VAD_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, s));
+    { int rc = zero_f64_launch(stats, (int64_t)2 * B * C, s); if (rc) return rc; }
     dim3 g1((unsigned)((P + kPoolRows - 1) / kPoolRows), B);
     pool_stats_kernel<<<g1, 256, 0, s>>>(in, L, C, P, pooled, stats);
     B200VAD_LAUNCH_CHECK();
