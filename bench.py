@@ -36,10 +36,25 @@ UNIT = "audio-hours/s"
 ROWS, SECONDS = 4096, 8.0
 N_SAMPLES = int(SECONDS * 16000)
 T_FRAMES = (N_SAMPLES + 80) // 160
-# algorithmic FLOPs of the recurrence per frame: 4 layers x 2 dirs x (128 x 512 MACs) x 2 (SURVEY 8d / DESIGN.md)
-REC_FLOP_PER_FRAME = 4 * 2 * 128 * 512 * 2
-# input projections (80 + 3*256) x 1024 MACs + head (256*128 + 128*128 + 128) MACs, x2
-PROJ_FLOP_PER_FRAME = 2 * ((80 + 3 * 256) * 1024 + 256 * 128 + 128 * 128 + 128)
+# Per-kernel algorithmic work per FRAME (10 ms of one utterance; 3 276 800 frames per launch at 4096 x 8 s), DESIGN.md
+# section 4.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture
+# (profiles/r01_ncu_full_summary.md), null where no capture exists.  `executed_over_algorithmic`: the split-precision
+# products execute 3 (GEMM) / 2 (recurrence: h_hi, h_lo) fp16 MMAs per algorithmic one.
+KERNELS = {
+    0: {"name": "lstm_tc_kernel (LSTM recurrence, 4 launches/step)", "bound": "hbm", "tensor": True,
+        # per layer: xg read 2 x 512 x 4 B + y planes written 2 x 128 x (2 + 2) B
+        "bytes_per_frame": 4096 + 1024, "flop_per_frame": 2 * 2 * 512 * 128, "executed_over_algorithmic": 2.0, "traffic": None},
+    1: {"name": "gemm_ts_kernel<0> (input projections, 4 launches/step)", "bound": "hbm", "tensor": True,
+        # per layer (1-3): x planes read 256 x 4 B + xg written 1024 x 4 B; layer 0 reads 80 x 4 B
+        "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
+        "executed_over_algorithmic": 3.0, "traffic": None},
+    2: {"name": "gemm_ts_kernel<1,2> (head linears, 2 launches/step)", "bound": "hbm", "tensor": True,
+        # y planes 1024 B -> z1 planes 512 B -> z2 fp32 512 B
+        "bytes_per_frame": (1024 + 512 + 512 + 512) / 2.0, "flop_per_frame": 2 * (256 * 128 + 128 * 128) / 2.0,
+        "executed_over_algorithmic": 3.0, "traffic": None},
+    3: {"name": "fbank_kernel (frame/window/FFT/mel/log, 1 launch/step)", "bound": "hbm", "tensor": False,
+        "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": None},
+}
 MODEL_FLOP_PER_FRAME = 2.884e6
 
 
@@ -229,10 +244,10 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = L.b200vad_launch_count() - launches0
     prof = {}
-    for kind, name in ((0, "lstm_tc_kernel (LSTM recurrence)"), (1, "gemm_tc_kernel + gemm_kernel (input projections + head linears)")):
+    for kind in KERNELS:
         tot_ms, nl = C.c_double(0), C.c_int(0)
         _lib.check(L.b200vad_profile_collect(kind, C.byref(tot_ms), C.byref(nl)), "profile_collect")
-        prof[kind] = (name, tot_ms.value, nl.value)
+        prof[kind] = (tot_ms.value, nl.value)
     L.b200vad_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -284,18 +299,38 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        frames = T_FRAMES * (hi - lo) * steps
-        # algorithmic FLOPs per frame: recurrence 4 layers x 2 dirs x 512 x 128 MACs; projections + head linears
-        flops = {0: REC_FLOP_PER_FRAME, 1: PROJ_FLOP_PER_FRAME}
-        dom = max(prof, key=lambda k: prof[k][1])
+        frames_per_launch = T_FRAMES * (hi - lo)
         kernels = {}
-        for k, (name, tms, n) in prof.items():
-            ach = flops[k] * frames / (tms / 1e3) / 1e12 if tms > 0 else 0.0
-            kernels[name] = {"launches": n, "total_ms": tms, "share_of_step": tms / (ms_per_step * steps), "achieved_tflops": ach}
-        name, tms, n = prof[dom]
-        avg_launch_ms = tms / max(n, 1)
-        achieved = flops[dom] * frames / (tms / 1e3) / 1e12 if tms > 0 else 0.0
-        peak = peaks["tf_sustained"]
+        for k, (tms, n) in prof.items():
+            spec = KERNELS[k]
+            if tms <= 0 or n == 0:
+                continue
+            ent = {"launches": n, "avg_launch_ms": tms / n, "share_of_step": tms / (ms_per_step * steps)}
+            gbs = spec["bytes_per_frame"] * frames_per_launch * n / (tms / 1e3) / 1e9
+            tfs = spec["flop_per_frame"] * frames_per_launch * n / (tms / 1e3) / 1e12
+            ent["algorithmic_bytes_per_frame"] = spec["bytes_per_frame"]
+            ent["algorithmic_flop_per_frame"] = spec["flop_per_frame"]
+            ent["hbm_gbs"] = gbs
+            ent["hbm_frac"] = gbs / peaks["hbm_gbs"]
+            ent["tflops"] = tfs
+            ent["tensor_frac"] = tfs * spec["executed_over_algorithmic"] / peaks["tf_sustained"] if spec["tensor"] else None
+            ent["bound"] = spec["bound"]
+            ent["traffic"] = spec["traffic"]
+            kernels[spec["name"]] = ent
+        dom = max(prof, key=lambda k: prof[k][0])
+        dspec, (tms, n) = KERNELS[dom], prof[dom]
+        dent = kernels[dspec["name"]]
+        if dspec["bound"] == "hbm":
+            roof = {"kernel": dspec["name"], "bound": "hbm", "achieved": dent["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": dent["hbm_frac"], "traffic": dspec["traffic"],
+                    "peak_source": f"{peaks['src']} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"}
+        else:
+            roof = {"kernel": dspec["name"], "bound": "tensor", "achieved": dent["tflops"], "peak": peaks["tf_sustained"],
+                    "unit": "TFLOP/s", "frac": dent["tflops"] / peaks["tf_sustained"], "traffic": dspec["traffic"],
+                    "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json)"}
+        roof.update({"launches": int(n), "avg_launch_ms": tms / max(n, 1), "share_of_step": dent["share_of_step"],
+                     "algorithmic_per_launch": "bytes (or FLOPs) per frame below x 3 276 800 frames per launch (DESIGN.md section 4)",
+                     "kernels": kernels})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -307,11 +342,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "api": "b200vad_session_submit_host / b200vad_session_wait, 2 steps in flight (pinned host waveforms -> host decisions + segments)"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "launches": int(n), "avg_launch_ms": avg_launch_ms,
-                         "share_of_step": tms / (ms_per_step * steps) if ms_per_step > 0 else None,
-                         "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); kernels run fp16 operands at the same tensor rate",
-                         "algorithmic_flops_per_frame": flops[dom], "kernels": kernels},
+            "roofline": roof,
             "whole_model_tflops": MODEL_FLOP_PER_FRAME * T_FRAMES * (hi - lo) / (ms_per_step / 1e3) / 1e12,
             "clocks": clocks,
         }

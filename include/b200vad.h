@@ -45,7 +45,7 @@ B200VAD_API const char* b200vad_last_error(void);
  * profile_collect synchronises on the recorded events, sums their durations and resets. */
 B200VAD_API long long b200vad_launch_count(void);
 B200VAD_API void b200vad_profile_enable(int on);
-B200VAD_API int b200vad_profile_collect(int kind /* 0 = LSTM recurrence, 1 = projection GEMM */, double* total_ms, int* launches);
+B200VAD_API int b200vad_profile_collect(int kind /* 0 = LSTM recurrence, 1 = input-projection GEMM, 2 = head / warp-MMA GEMMs, 3 = fbank */, double* total_ms, int* launches);
 /* 2 = tcgen05 kernels (default); 1 = the warp-MMA kernels kept for cross-validation of the tcgen05 path */
 B200VAD_API int b200vad_set_impl(int impl);
 /* Split-precision linear layer on the tcgen05 GEMM: c[M,N] = a[M,K] . w[N,K]^T + bias, fp32 in / out, operands
@@ -116,6 +116,25 @@ B200VAD_API int b200vad_threshold_median(const float* prob, int B, int64_t T, fl
 B200VAD_API int b200vad_segments(const uint8_t* dec, const int64_t* offsets, int R, int64_t T, int min_run, int32_t* counts,
                      int64_t* seg_off, int32_t* seg, int64_t cap, void* stream);
 
+/* ---- 8f-1 scoring.  VadModel.test_step stat scores (src/engines/vad_engine.py:167-202): out4 (device, i64) =
+ * tp, fp, tn, fn of dec (u8, != 0 is speech) against labels (u8) over n frames. */
+B200VAD_API int b200vad_stat_scores(const uint8_t* dec, const uint8_t* labels, int64_t n, int64_t* out4, void* stream);
+/* get_binary_tensor / get_false_alarm / get_missed_detection (src/scripts/predict.py:654-673) on bit masks.
+ * Intervals are (recording, start_frame, end_frame_exclusive) i32 triples, already int(t / frame_shift) as the
+ * reference computes them; recording r has nframes[r] = ceil(duration / frame_shift) frames and its mask starts at
+ * word word_off[r] (word_off: (R+1) i64, 32 frames per word, total_words = word_off[R]).  fa / md: (R) i64 frame
+ * counts (pred & ~gt, gt & ~pred); the caller divides by nframes like the reference.  All pointers device. */
+B200VAD_API size_t b200vad_score_workspace_bytes(int64_t total_words);
+B200VAD_API int b200vad_score_intervals(const int32_t* gt_iv, int64_t n_gt, const int32_t* pred_iv, int64_t n_pred,
+                            const int64_t* word_off, const int32_t* nframes, int R, int64_t total_words, int max_words_per_rec,
+                            void* workspace, int64_t* fa, int64_t* md, void* stream);
+
+/* ---- long-form audio with OVERLAPPING windows (BASELINE config 3; the reference itself only cuts hop = window,
+ * src/datasets/ami/utils.py:107, which needs no stitching): prob (num_windows, frames_per_window) f32, window w
+ * starting at global frame w * hop_frames -> out (L) f32, every frame taken from the window whose centre is nearest. */
+B200VAD_API int b200vad_stitch_center(const float* prob, int num_windows, int frames_per_window, int hop_frames, float* out, int64_t L,
+                          void* stream);
+
 /* ---- whole path on device buffers: fbank -> PyanNet2 -> threshold/median -> segments */
 B200VAD_API size_t b200vad_pipeline_workspace_bytes(int B, int64_t N);
 B200VAD_API int b200vad_pipeline_fbank_f32(const void* packed, int num_layers, const float* wav, const int32_t* lens, int B,
@@ -147,6 +166,21 @@ B200VAD_API int b200vad_session_wait(b200vad_session* s, int slot, int32_t* seg_
  * ms[0..4] = H2D begin, H2D end, compute begin, compute end, D2H end (CUDA events on the three streams). */
 B200VAD_API int b200vad_session_slot_times(b200vad_session* s, int slot, float* ms);
 B200VAD_API void b200vad_session_destroy(b200vad_session* s);
+
+/* ---- streaming session (BASELINE config 5): num_streams ring buffers of the last window_samples samples.
+ * push() appends hop_samples new samples per stream (chunk: (num_streams, hop_samples) f32, host or device),
+ * runs fbank -> PyanNet2 -> threshold/median on every buffered window (one CUDA graph replay when use_graph),
+ * and returns the newest hop_samples/160 frames of every stream on the host: prob_new (S, nf) f32, dec_new (S, nf)
+ * u8.  These equal the batch path applied to the same window (there is no reference streaming mode: the BiLSTM is
+ * non-causal).  device_ms (optional) = CUDA-event time of the push.  Blocking. */
+typedef struct b200vad_stream b200vad_stream;
+B200VAD_API int b200vad_stream_create(int device, const void* packed_device, int num_layers, int num_streams, int64_t window_samples,
+                          int hop_samples, int use_graph, b200vad_stream** out);
+B200VAD_API int b200vad_stream_push(b200vad_stream* s, const float* chunk, int chunk_on_host, float thr, int kernel, float* prob_new_host,
+                        uint8_t* dec_new_host, float* device_ms);
+/* parity / debugging: current windows (S, window) f32 and all frame outputs (S, T) of the last push, to host buffers */
+B200VAD_API int b200vad_stream_snapshot(b200vad_stream* s, float* window_host, float* prob_host, uint8_t* dec_host);
+B200VAD_API void b200vad_stream_destroy(b200vad_stream* s);
 
 #ifdef __cplusplus
 }

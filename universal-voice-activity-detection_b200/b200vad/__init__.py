@@ -11,6 +11,9 @@ from . import ops  # noqa: F401  (registers torch.ops.b200vad.*)
 from .packing import pack_model, pack_sincnet  # noqa: F401
 from .runtime import HostSession, gather_segments, shard_range  # noqa: F401
 from . import synth  # noqa: F401
+from . import score  # noqa: F401
+from .longform import LongFormVad  # noqa: F401
+from .streaming import StreamingVad  # noqa: F401
 
-__all__ = ["ops", "host", "synth", "pack_model", "pack_sincnet", "HostSession", "gather_segments", "shard_range",
+__all__ = ["ops", "host", "synth", "pack_model", "pack_sincnet", "HostSession", "LongFormVad", "StreamingVad", "score", "gather_segments", "shard_range",
            "B200VadError", "lib", "LIB_PATH"]

@@ -43,6 +43,15 @@ PROTOTYPES = {
     "b200vad_median_window": (c_int, [c_double, c_double]),
     "b200vad_threshold_median": (c_int, [c_void_p, c_int, c_int64, c_float, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p]),
     "b200vad_segments": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b200vad_stat_scores": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200vad_score_workspace_bytes": (c_size_t, [c_int64]),
+    "b200vad_score_intervals": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "b200vad_stitch_center": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "b200vad_stream_create": (c_int, [c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, C.POINTER(c_void_p)]),
+    "b200vad_stream_push": (c_int, [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, C.POINTER(c_float)]),
+    "b200vad_stream_snapshot": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200vad_stream_destroy": (None, [c_void_p]),
     "b200vad_pipeline_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "b200vad_pipeline_fbank_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_float, c_int,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

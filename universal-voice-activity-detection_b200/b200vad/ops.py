@@ -34,6 +34,18 @@ def _prep(t: torch.Tensor, dtype, what: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _prep_rows(t: torch.Tensor, what: str) -> torch.Tensor:
+    """(B, N) float32 CUDA rows with unit inner stride; the row stride may be anything >= 1 (overlapping
+    long-form windows are passed as an as_strided view, no copy)."""
+    if not t.is_cuda:
+        raise _lib.B200VadError(f"{what} must be a CUDA tensor (there is no CPU implementation of this path)")
+    if t.dtype != torch.float32:
+        raise _lib.B200VadError(f"{what} must be torch.float32, got {t.dtype}")
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= 1:
+        return t
+    return t.contiguous()
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -47,7 +59,7 @@ def _ensure(device) -> int:
 # ------------------------------------------------------------------ fbank
 @torch.library.custom_op("b200vad::fbank", mutates_args=(), device_types="cuda")
 def fbank(wav: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
-    wav = _prep(wav, torch.float32, "wav")
+    wav = _prep_rows(wav, "wav")
     if wav.dim() != 2:
         raise _lib.B200VadError("wav must be (B, N)")
     B, N = wav.shape
@@ -65,7 +77,7 @@ def fbank(wav: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tenso
         sums = torch.empty(B, dtype=torch.float64, device=wav.device)
         for b0 in range(0, B, 32768):
             b1 = min(B, b0 + 32768)
-            _lib.check(L.b200vad_fbank_f32(wav[b0:b1].data_ptr(), None if lens_ptr is None else lens[b0:b1].data_ptr(),
+            _lib.check(L.b200vad_fbank_f32(wav.data_ptr() + 4 * b0 * wav.stride(0), None if lens_ptr is None else lens[b0:b1].data_ptr(),
                                            b1 - b0, N, wav.stride(0), feats[b0:b1].data_ptr(), T,
                                            sums[b0:b1].data_ptr(), _stream_ptr(wav.device)), "b200vad_fbank_f32")
     return feats
@@ -207,7 +219,7 @@ def _(dec, offsets=None, min_run=2):
 @torch.library.custom_op("b200vad::vad_pipeline", mutates_args=(), device_types="cuda")
 def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.Tensor, num_layers: int, thr: float,
                  kernel: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    wav = _prep(wav, torch.float32, "wav")
+    wav = _prep_rows(wav, "wav")
     if wav.dim() != 2:
         raise _lib.B200VadError("wav must be (B, N)")
     B, N = wav.shape
@@ -251,3 +263,75 @@ def _(wav, lens, packed, num_layers, thr, kernel):
     T = (N + 80) // 160
     return (wav.new_empty((B, T)), wav.new_empty((B, T), dtype=torch.uint8), wav.new_empty((n, 3), dtype=torch.int32),
             wav.new_empty((B,), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------ scoring
+@torch.library.custom_op("b200vad::stat_scores", mutates_args=(), device_types="cuda")
+def stat_scores(dec: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """(tp, fp, tn, fn) int64 of decisions (uint8, != 0 is speech) against labels (uint8)."""
+    dec = _prep(dec, torch.uint8, "dec").reshape(-1)
+    labels = _prep(labels, torch.uint8, "labels").reshape(-1)
+    if dec.numel() != labels.numel():
+        raise _lib.B200VadError("dec and labels must have the same number of frames")
+    out = torch.empty(4, dtype=torch.int64, device=dec.device)
+    with torch.cuda.device(dec.device):
+        _lib.check(_lib.lib().b200vad_stat_scores(dec.data_ptr(), labels.data_ptr(), dec.numel(), out.data_ptr(),
+                                                  _stream_ptr(dec.device)), "b200vad_stat_scores")
+    return out
+
+
+@stat_scores.register_fake
+def _(dec, labels):
+    return dec.new_empty((4,), dtype=torch.int64)
+
+
+@torch.library.custom_op("b200vad::score_intervals", mutates_args=(), device_types="cuda")
+def score_intervals(gt_iv: torch.Tensor, pred_iv: torch.Tensor, word_off: torch.Tensor, nframes: torch.Tensor,
+                    total_words: int, max_words_per_rec: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """gt_iv / pred_iv: (n, 3) int32 (recording, start_frame, end_frame_exclusive); word_off (R+1) int64;
+    nframes (R) int32 -> per-recording false-alarm and missed frame counts (R) int64."""
+    gt_iv = _prep(gt_iv, torch.int32, "gt_iv")
+    pred_iv = _prep(pred_iv, torch.int32, "pred_iv")
+    word_off = _prep(word_off, torch.int64, "word_off")
+    nframes = _prep(nframes, torch.int32, "nframes")
+    dev = nframes.device
+    R = nframes.numel()
+    fa = torch.zeros(R, dtype=torch.int64, device=dev)
+    md = torch.zeros(R, dtype=torch.int64, device=dev)
+    if R == 0:
+        return fa, md
+    L = _lib.lib()
+    ws = _ws(L.b200vad_score_workspace_bytes(total_words), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.b200vad_score_intervals(gt_iv.data_ptr() if gt_iv.numel() else None, gt_iv.shape[0],
+                                             pred_iv.data_ptr() if pred_iv.numel() else None, pred_iv.shape[0],
+                                             word_off.data_ptr(), nframes.data_ptr(), R, int(total_words), int(max_words_per_rec),
+                                             ws.data_ptr(), fa.data_ptr(), md.data_ptr(), _stream_ptr(dev)),
+                   "b200vad_score_intervals")
+    return fa, md
+
+
+@score_intervals.register_fake
+def _(gt_iv, pred_iv, word_off, nframes, total_words, max_words_per_rec):
+    R = nframes.shape[0]
+    return nframes.new_empty((R,), dtype=torch.int64), nframes.new_empty((R,), dtype=torch.int64)
+
+
+# ------------------------------------------------------------------ long-form stitching (BASELINE config 3)
+@torch.library.custom_op("b200vad::stitch_center", mutates_args=(), device_types="cuda")
+def stitch_center(prob: torch.Tensor, hop_frames: int, total_frames: int) -> torch.Tensor:
+    """prob (W, Tw) of windows starting every hop_frames frames -> stitched (total_frames,) stream."""
+    prob = _prep(prob, torch.float32, "prob")
+    if prob.dim() != 2:
+        raise _lib.B200VadError("prob must be (W, Tw)")
+    W, Tw = prob.shape
+    out = torch.empty(int(total_frames), dtype=torch.float32, device=prob.device)
+    with torch.cuda.device(prob.device):
+        _lib.check(_lib.lib().b200vad_stitch_center(prob.data_ptr(), W, Tw, int(hop_frames), out.data_ptr(), int(total_frames),
+                                                    _stream_ptr(prob.device)), "b200vad_stitch_center")
+    return out
+
+
+@stitch_center.register_fake
+def _(prob, hop_frames, total_frames):
+    return prob.new_empty((total_frames,))

@@ -341,7 +341,7 @@ int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, i
     B200VAD_CHECK_ARG(B >= 0 && N >= 0 && T >= 0, "negative size");
     if (B == 0 || T == 0) return B200VAD_OK;
     B200VAD_CHECK_ARG(wav && feats && row_sum_ws, "null pointer");
-    B200VAD_CHECK_ARG(N >= 1 && wav_stride >= N, "need N >= 1 and wav_stride >= N");
+    B200VAD_CHECK_ARG(N >= 1 && wav_stride >= 1, "need N >= 1 and wav_stride >= 1 (rows may overlap: long-form windows)");
     B200VAD_CHECK_ARG(B <= 65535, "B must be <= 65535 per call");
     int dev = 0;
     B200VAD_CUDA(cudaGetDevice(&dev));
@@ -560,6 +560,35 @@ int b200vad_segments(const uint8_t* dec, const int64_t* offsets, int R, int64_t 
     return segments_launch(dec, offsets, T, R, min_run, 0, counts, seg_off, seg, cap, st);
 }
 
+// ---------------------------------------------------------------- scoring
+int b200vad_stat_scores(const uint8_t* dec, const uint8_t* labels, int64_t n, int64_t* out4, void* stream) {
+    B200VAD_CHECK_ARG(n >= 0 && out4 && ((dec && labels) || n == 0), "bad argument");
+    return stat_scores_launch(dec, labels, n, out4, (cudaStream_t)stream);
+}
+
+size_t b200vad_score_workspace_bytes(int64_t total_words) { return total_words <= 0 ? 256 : (size_t)total_words * 8 + 256; }
+
+int b200vad_score_intervals(const int32_t* gt_iv, int64_t n_gt, const int32_t* pred_iv, int64_t n_pred, const int64_t* word_off,
+                            const int32_t* nframes, int R, int64_t total_words, int max_words_per_rec, void* workspace,
+                            int64_t* fa, int64_t* md, void* stream) {
+    B200VAD_CHECK_ARG(R >= 0 && n_gt >= 0 && n_pred >= 0 && total_words >= 0, "negative size");
+    if (R == 0) return B200VAD_OK;
+    B200VAD_CHECK_ARG(word_off && nframes && workspace && fa && md, "null pointer");
+    B200VAD_CHECK_ARG((gt_iv || n_gt == 0) && (pred_iv || n_pred == 0), "null interval list");
+    B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+    return score_intervals_launch(gt_iv, n_gt, pred_iv, n_pred, word_off, nframes, R, total_words,
+                                  reinterpret_cast<uint32_t*>(workspace), fa, md, max_words_per_rec, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- long-form stitching (BASELINE config 3)
+int b200vad_stitch_center(const float* prob, int num_windows, int frames_per_window, int hop_frames, float* out, int64_t L,
+                          void* stream) {
+    B200VAD_CHECK_ARG(num_windows >= 1 && frames_per_window >= 1 && hop_frames >= 1 && hop_frames <= frames_per_window && L >= 0,
+                      "need 1 <= hop_frames <= frames_per_window");
+    B200VAD_CHECK_ARG(prob && (out || L == 0), "null pointer");
+    return stitch_center_launch(prob, num_windows, frames_per_window, hop_frames, out, L, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- fused device pipeline
 static size_t pipeline_ws_bytes(int B, int64_t N) {
     int64_t T = b200vad_fbank_num_frames(N);
@@ -600,7 +629,7 @@ static int pipeline_run(const void* packed, int L, const float* wav, const int32
 int b200vad_pipeline_fbank_f32(const void* packed, int L, const float* wav, const int32_t* lens, int B, int64_t N,
                                int64_t stride, float thr, int kernel, float* prob, uint8_t* dec, int32_t* counts,
                                int64_t* seg_off, int32_t* seg, int64_t cap, void* ws, size_t ws_bytes, void* stream) {
-    B200VAD_CHECK_ARG(B >= 0 && B <= 65535 && N >= 1 && stride >= N, "bad shape");
+    B200VAD_CHECK_ARG(B >= 0 && B <= 65535 && N >= 1 && stride >= 1, "bad shape");
     return pipeline_run(packed, L, wav, lens, B, N, stride, thr, kernel, 0, prob, dec, counts, seg_off, seg, cap, ws, ws_bytes,
                         (cudaStream_t)stream);
 }
@@ -815,6 +844,161 @@ void b200vad_session_destroy(b200vad_session* s) {
     if (s->compute_stream) cudaStreamDestroy(s->compute_stream);
     if (s->d2h_stream) cudaStreamDestroy(s->d2h_stream);
     if (s->seg_stream) cudaStreamDestroy(s->seg_stream);
+    delete s;
+}
+
+// ---------------------------------------------------------------- streaming session (BASELINE config 5)
+// Every stream keeps its last `window` samples in a double-write ring; push() appends `hop` new samples per
+// stream and runs the whole path on the buffered windows, so the newest frames equal the batch path applied to
+// the same window (the BiLSTM is non-causal: there is no cheaper exact update, SURVEY 8a "streaming").
+// The per-push kernel sequence is fixed, so it is captured once into a CUDA graph and replayed.
+struct b200vad_stream {
+    int device;
+    const void* packed;
+    int L, S, hop, nf, pos;
+    int64_t W, T;
+    float thr;
+    int kernel;
+    bool use_graph;
+    cudaStream_t st;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    cudaEvent_t e0, e1;
+    float *ring, *lin, *chunk, *feats, *prob, *prob_new, *prob_new_host;
+    double* sums;
+    uint8_t *dec, *dec_new, *dec_new_host;
+    void* ws;
+    size_t ws_bytes;
+};
+
+static int stream_forward(b200vad_stream* s) {
+    int rc = fbank_launch(s->lin, nullptr, s->S, s->W, s->W, s->feats, s->T, s->sums, s->device, s->st);
+    if (rc) return rc;
+    rc = model_forward(s->packed, kNumMel, s->L, s->feats, s->S, s->T, s->prob, s->ws, s->ws_bytes, s->st);
+    if (rc) return rc;
+    rc = threshold_median_launch(s->prob, s->S, s->T, s->thr, s->kernel, s->dec, 1, nullptr, 0.f, s->st);
+    if (rc) return rc;
+    return stream_newest_launch(s->prob, s->dec, s->S, s->T, s->nf, s->prob_new, s->dec_new, s->st);
+}
+
+static int stream_capture(b200vad_stream* s) {
+    if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+    int rc = stream_forward(s);                         // warm-up: one-time function attributes, table init
+    if (rc) return rc;
+    B200VAD_CUDA(cudaStreamSynchronize(s->st));
+    B200VAD_CUDA(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+    rc = stream_forward(s);
+    cudaError_t e = cudaStreamEndCapture(s->st, &s->graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error("stream capture failed: %s", cudaGetErrorString(e)); return B200VAD_ECUDA; }
+    B200VAD_CUDA(cudaGraphInstantiate(&s->exec, s->graph, 0));
+    return B200VAD_OK;
+}
+
+int b200vad_stream_create(int device, const void* packed_device, int num_layers, int num_streams, int64_t window_samples,
+                          int hop_samples, int use_graph, b200vad_stream** out) {
+    B200VAD_CHECK_ARG(out && packed_device, "null pointer");
+    B200VAD_CHECK_ARG(num_layers > 0 && num_streams > 0 && num_streams <= 65535, "bad shape");
+    B200VAD_CHECK_ARG(hop_samples > 0 && hop_samples % kFrameShift == 0 && window_samples % kFrameShift == 0 &&
+                          window_samples >= hop_samples && window_samples <= (1 << 30),
+                      "window and hop must be multiples of 160 samples, hop <= window");
+    int rc = b200vad_init(device);
+    if (rc) return rc;
+    b200vad_stream* s = new b200vad_stream();
+    memset(s, 0, sizeof(*s));
+    s->device = device; s->packed = packed_device; s->L = num_layers; s->S = num_streams; s->hop = hop_samples;
+    s->W = window_samples; s->T = b200vad_fbank_num_frames(window_samples); s->nf = hop_samples / kFrameShift;
+    s->thr = 0.5f; s->kernel = 49; s->use_graph = use_graph != 0;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    const size_t S = s->S, W = s->W, T = s->T;
+    ok(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&s->e0)); ok(cudaEventCreate(&s->e1));
+    ok(cudaMalloc(&s->ring, sizeof(float) * S * 2 * W));
+    ok(cudaMalloc(&s->lin, sizeof(float) * S * W));
+    ok(cudaMalloc(&s->chunk, sizeof(float) * S * s->hop));
+    ok(cudaMalloc(&s->feats, sizeof(float) * S * T * kNumMel));
+    ok(cudaMalloc(&s->sums, sizeof(double) * S));
+    ok(cudaMalloc(&s->prob, sizeof(float) * S * T));
+    ok(cudaMalloc(&s->dec, S * T));
+    ok(cudaMalloc(&s->prob_new, sizeof(float) * S * s->nf));
+    ok(cudaMalloc(&s->dec_new, S * s->nf));
+    ok(cudaMallocHost(&s->prob_new_host, sizeof(float) * S * s->nf));
+    ok(cudaMallocHost(&s->dec_new_host, S * s->nf));
+    s->ws_bytes = b200vad_model_workspace_bytes(s->S, s->T);
+    ok(cudaMalloc(&s->ws, s->ws_bytes));
+    if (e == cudaSuccess) ok(cudaMemsetAsync(s->ring, 0, sizeof(float) * S * 2 * W, s->st));
+    if (e == cudaSuccess) ok(cudaMemsetAsync(s->lin, 0, sizeof(float) * S * W, s->st));
+    if (e != cudaSuccess) {
+        set_error("b200vad_stream_create: %s", cudaGetErrorString(e));
+        b200vad_stream_destroy(s);
+        return e == cudaErrorMemoryAllocation ? B200VAD_ENOMEM : B200VAD_ECUDA;
+    }
+    if (s->use_graph && (rc = stream_capture(s))) { b200vad_stream_destroy(s); return rc; }
+    *out = s;
+    return B200VAD_OK;
+}
+
+int b200vad_stream_push(b200vad_stream* s, const float* chunk, int chunk_on_host, float thr, int kernel, float* prob_new_host,
+                        uint8_t* dec_new_host, float* device_ms) {
+    B200VAD_CHECK_ARG(s && chunk, "null pointer");
+    B200VAD_CHECK_ARG(kernel >= 1 && (kernel & 1), "median kernel must be odd");
+    B200VAD_CUDA(cudaSetDevice(s->device));
+    int rc;
+    if (thr != s->thr || kernel != s->kernel) {
+        s->thr = thr; s->kernel = kernel;
+        if (s->use_graph && (rc = stream_capture(s))) return rc;
+    }
+    B200VAD_CUDA(cudaEventRecord(s->e0, s->st));
+    const float* src = chunk;
+    if (chunk_on_host) {
+        B200VAD_CUDA(cudaMemcpyAsync(s->chunk, chunk, sizeof(float) * (size_t)s->S * s->hop, cudaMemcpyHostToDevice, s->st));
+        src = s->chunk;
+    }
+    if ((rc = stream_append_launch(s->ring, src, s->lin, s->S, (int)s->W, s->hop, s->pos, s->st))) return rc;
+    s->pos += s->hop;
+    if (s->pos >= s->W) s->pos -= (int)s->W;
+    if (s->use_graph) {
+        B200VAD_CUDA(cudaGraphLaunch(s->exec, s->st));
+    } else if ((rc = stream_forward(s))) {
+        return rc;
+    }
+    const size_t n = (size_t)s->S * s->nf;
+    B200VAD_CUDA(cudaMemcpyAsync(s->prob_new_host, s->prob_new, sizeof(float) * n, cudaMemcpyDeviceToHost, s->st));
+    B200VAD_CUDA(cudaMemcpyAsync(s->dec_new_host, s->dec_new, n, cudaMemcpyDeviceToHost, s->st));
+    B200VAD_CUDA(cudaEventRecord(s->e1, s->st));
+    B200VAD_CUDA(cudaEventSynchronize(s->e1));
+    if (prob_new_host) memcpy(prob_new_host, s->prob_new_host, sizeof(float) * n);
+    if (dec_new_host) memcpy(dec_new_host, s->dec_new_host, n);
+    if (device_ms) B200VAD_CUDA(cudaEventElapsedTime(device_ms, s->e0, s->e1));
+    return B200VAD_OK;
+}
+
+/* debugging / parity: copy the current buffered windows (S, window) and all frame outputs to the host */
+int b200vad_stream_snapshot(b200vad_stream* s, float* window_host, float* prob_host, uint8_t* dec_host) {
+    B200VAD_CHECK_ARG(s, "null pointer");
+    B200VAD_CUDA(cudaSetDevice(s->device));
+    B200VAD_CUDA(cudaStreamSynchronize(s->st));
+    if (window_host) B200VAD_CUDA(cudaMemcpy(window_host, s->lin, sizeof(float) * (size_t)s->S * s->W, cudaMemcpyDeviceToHost));
+    if (prob_host) B200VAD_CUDA(cudaMemcpy(prob_host, s->prob, sizeof(float) * (size_t)s->S * s->T, cudaMemcpyDeviceToHost));
+    if (dec_host) B200VAD_CUDA(cudaMemcpy(dec_host, s->dec, (size_t)s->S * s->T, cudaMemcpyDeviceToHost));
+    return B200VAD_OK;
+}
+
+void b200vad_stream_destroy(b200vad_stream* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->exec) cudaGraphExecDestroy(s->exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    void* dev_ptrs[] = {s->ring, s->lin, s->chunk, s->feats, s->sums, s->prob, s->dec, s->prob_new, s->dec_new, s->ws};
+    for (void* p : dev_ptrs) if (p) cudaFree(p);
+    if (s->prob_new_host) cudaFreeHost(s->prob_new_host);
+    if (s->dec_new_host) cudaFreeHost(s->dec_new_host);
+    if (s->e0) cudaEventDestroy(s->e0);
+    if (s->e1) cudaEventDestroy(s->e1);
+    if (s->st) cudaStreamDestroy(s->st);
     delete s;
 }
 

@@ -16,7 +16,8 @@ namespace b200vad {
 void set_error(const char* fmt, ...);
 void count_launch();                       // bumps the process-wide kernel-launch counter
 // live timing of the hot kernels (bench.py roofline): when enabled, every launch of kind
-// 0 = LSTM recurrence, 1 = projection GEMM is bracketed by CUDA events on its own stream
+// 0 = LSTM recurrence, 1 = input-projection GEMM, 2 = head GEMMs / warp-MMA GEMMs, 3 = fbank
+// is bracketed by CUDA events on its own stream
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);
 

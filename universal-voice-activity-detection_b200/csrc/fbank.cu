@@ -385,7 +385,9 @@ int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_
     row_sum_kernel<<<g1, 256, 0, stream>>>(wav, lens, N, stride, row_sums);
     B200VAD_LAUNCH_CHECK();
     dim3 g2((unsigned)((T_out + kTileFrames - 1) / kTileFrames), B);
+    prof_begin(3, stream);
     fbank_kernel<<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, T_out);
+    prof_end(3, stream);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

@@ -211,9 +211,9 @@ int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, 
 template <int BN, int TERMS, typename AT, int VEC>
 static int launch_one(const GemmArgs& a, cudaStream_t stream) {
     dim3 grid((a.N + BN - 1) / BN, (unsigned)((a.M + GBM - 1) / GBM));
-    prof_begin(1, stream);
+    prof_begin(2, stream);
     gemm_kernel<BN, TERMS, AT, VEC><<<grid, 256, 0, stream>>>(a);
-    prof_end(1, stream);
+    prof_end(2, stream);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

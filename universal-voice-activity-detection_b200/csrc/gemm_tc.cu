@@ -332,7 +332,8 @@ int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t 
     const int64_t max_grid = (int64_t)p.num_m_tiles * p.n_blocks;
     if (grid > max_grid) grid = (int)max_grid;
     static bool attr[3] = {false, false, false};
-    prof_begin(1, st);
+    const int prof_kind = mode == 0 ? 1 : 2;
+    prof_begin(prof_kind, st);
     if (mode == 0) {
         if (!attr[0]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
         gemm_ts_kernel<0><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
@@ -343,7 +344,7 @@ int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t 
         if (!attr[2]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[2] = true; }
         gemm_ts_kernel<2><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
     }
-    prof_end(1, st);
+    prof_end(prof_kind, st);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

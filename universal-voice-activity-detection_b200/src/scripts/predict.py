@@ -40,6 +40,35 @@ def get_segments(test_preds: torch.Tensor, durations: Optional[Sequence[float]] 
     return out
 
 
+def get_binary_tensor(intervals, total_duration, frame_shift, device="cuda"):
+    """predict.py:654-663: 0/1 float tensor of ceil(total_duration / frame_shift) frames, on the GPU."""
+    import math
+    n = math.ceil(total_duration / frame_shift)
+    t = torch.zeros(n, device=device)
+    for start, end in intervals:
+        t[int(start / frame_shift): int(end / frame_shift)] = 1
+    return t
+
+
+def get_false_alarm(gt_tensor, pred_tensor):
+    """predict.py:666-668 (frames with gt == 0 and pred == 1, over len(gt)); counts come from the stat-score kernel."""
+    tp, fp, tn, fn = torch.ops.b200vad.stat_scores((pred_tensor == 1).to(torch.uint8), (gt_tensor != 0).to(torch.uint8))
+    return fp.cpu() / len(gt_tensor)
+
+
+def get_missed_detection(gt_tensor, pred_tensor):
+    """predict.py:671-673 (frames with gt == 1 and pred == 0, over len(gt))."""
+    tp, fp, tn, fn = torch.ops.b200vad.stat_scores((pred_tensor != 0).to(torch.uint8), (gt_tensor == 1).to(torch.uint8))
+    return fn.cpu() / len(gt_tensor)
+
+
+def score_predictions(gt_intervals, pred_intervals, durations, frame_shift=0.01, device="cuda"):
+    """The accumulation of predict.py:500-509 / 590-600 for all recordings in one pass of the bit-mask kernels.
+    Returns (detection_error_rate, false_alarm_rate, missed_detection_rate) averaged over recordings."""
+    r = b200vad.score.detection_error(gt_intervals, pred_intervals, durations, frame_shift, device)
+    return r["detection_error"], r["false_alarm"], r["missed_detection"]
+
+
 @torch.no_grad()
 def predict_vad(model, waveforms: torch.Tensor, frame_shift: float = 0.01, max_rows: int = 4096, **kwargs):
     """waveforms (rows, samples) CUDA float32 -> (decisions (rows, T, 1) int64, per-row intervals).
