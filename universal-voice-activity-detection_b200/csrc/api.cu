@@ -99,11 +99,13 @@ static ModelLayout model_layout(int D, int L) {
 
 // Workspace per (sequence, frame): xg fp32 [1024] + two layer buffers of 1024 bytes each (either a
 // fp32 [256] row or the fp16 hi / lo planes [256] + [256]) + the fp16 hi / lo planes of the layer-0 input.
+// xg is laid out in blocks of 64 sequences (lstm_tc.cu), so sequence counts are rounded up to 64.
 static inline size_t round8(size_t d) { return (d + 7) / 8 * 8; }
 static inline size_t model_bytes_per_frame(int D) {
     return sizeof(float) * 2 * kGates + 2 * sizeof(float) * 2 * kHidden + 2 * sizeof(__half) * round8(D);
 }
 static inline size_t model_per_row(int D, int64_t T) { return align_up((size_t)T * model_bytes_per_frame(D)) + 1536; }
+static inline int64_t ceil64(int64_t b) { return (b + 63) / 64 * 64; }
 
 static int head_forward(const ModelLayout& m, const char* pk, const float* y, int64_t rows, float* z1, float* z2, float* prob,
                         cudaStream_t st) {
@@ -135,12 +137,11 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
     const ModelLayout m = model_layout(D, L);
     const char* pk = reinterpret_cast<const char*>(packed);
     const size_t per_row = model_per_row(D, T);
-    int64_t Bc = (int64_t)(ws_bytes / per_row);
-    Bc = std::min<int64_t>(Bc, (int64_t)(65000LL * 128 / T));   // one warp-MMA GEMM launch handles < 65535*128 rows
-    Bc = std::min<int64_t>(Bc, B);
-    if (Bc >= 64) Bc = Bc / 64 * 64;                            // whole recurrent CTAs
-    if (Bc < 1) {
-        set_error("model_forward: workspace too small (%zu bytes; need >= %zu per sequence)", ws_bytes, per_row);
+    int64_t Bc = (int64_t)(ws_bytes / per_row) / 64 * 64;       // whole 64-sequence blocks (recurrent CTAs, xg records)
+    if (g_impl == 1) Bc = std::min<int64_t>(Bc, std::max<int64_t>(64, (int64_t)(65000LL * 128 / T) / 64 * 64));   // warp-MMA GEMM grid limit
+    Bc = std::min<int64_t>(Bc, ceil64(B));
+    if (Bc < 64) {
+        set_error("model_forward: workspace too small (%zu bytes; need >= %zu = 64 sequences)", ws_bytes, 64 * per_row);
         return B200VAD_ENOMEM;
     }
     const int D8 = (int)round8(D);
@@ -149,7 +150,7 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
         const int bc = (int)std::min<int64_t>(Bc, B - b0);
         const int64_t rows = (int64_t)bc * T;
         char* w = reinterpret_cast<char*>(ws);
-        float* xg = reinterpret_cast<float*>(w);                 w += align_up(sizeof(float) * 2 * kGates * rows);
+        float* xg = reinterpret_cast<float*>(w);                 w += align_up(sizeof(float) * 2 * kGates * ceil64(bc) * T);
         char* buf0 = w;                                          w += align_up(sizeof(float) * 2 * kHidden * rows);
         char* buf1 = w;                                          w += align_up(sizeof(float) * 2 * kHidden * rows);
         __half* x_hi = reinterpret_cast<__half*>(w);             w += align_up(sizeof(__half) * D8 * rows);
@@ -178,35 +179,24 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
             continue;
         }
         // ---- tcgen05 path: activations travel between layers (and into the head) as fp16 (hi, lo) planes
-        const bool d_ok = (D % 8 == 0);
-        if (d_ok) {
-            if ((rc = split_planes_launch(xin, rows * D, x_hi, x_lo, st))) return rc;
-        }
+        if (D % 8 == 0) rc = split_planes_launch(xin, rows * D, x_hi, x_lo, st);
+        else rc = split_planes_pad_launch(xin, rows, D, D8, x_hi, x_lo, st);       // e.g. the 60 SincNet channels -> pitch 64
+        if (rc) return rc;
         const __half* a_hi = x_hi;
         const __half* a_lo = x_lo;
-        int64_t lda = D;
+        int64_t lda = D8;
         char* outbuf = buf0;
         for (int l = 0; l < L; ++l) {
             const LayerOff& lo = m.layers[l];
             const __half* w_hi = reinterpret_cast<const __half*>(pk + lo.wih_hi);
             const __half* w_lo = reinterpret_cast<const __half*>(pk + lo.wih_lo);
             const float* bias = reinterpret_cast<const float*>(pk + lo.bias);
-            // hi + lo weight planes stay resident in tensor memory (2 planes x Kp <= 512 fp16 per output feature)
-            if ((l > 0 || d_ok) && 2 * lo.Kp <= 512) {
-                if ((rc = gemm_ts_launch(a_hi, a_lo, lda, rows, lo.D, w_hi, w_lo, lo.Kp, 2 * kGates, bias, 0, xg, nullptr, nullptr,
-                                         128, rows * 128, sms, st))) return rc;
-            } else {
-                // shapes the resident-weight kernel cannot hold (e.g. 768-dim SSL features): warp-MMA GEMM on the fp32 input
-                if (l > 0) { set_error("model_forward: internal layer width unsupported"); return B200VAD_EINVAL; }
-                // one launch per 128-feature block, so that xg comes out in the recurrence's blocked layout
-                for (int blk = 0; blk < 2 * kGates / 128; ++blk) {
-                    GemmArgs g;
-                    g.A = xin; g.lda = lo.D; g.rows_per_batch = rows; g.a_batch_stride = 0; g.M = rows;
-                    g.N = 128; g.K = lo.D; g.Kp = lo.Kp; g.W_hi = w_hi + (size_t)blk * 128 * lo.Kp;
-                    g.W_lo = w_lo + (size_t)blk * 128 * lo.Kp; g.bias = bias + blk * 128;
-                    g.C = xg + (size_t)blk * rows * 128; g.ldc = 128; g.c_half = 0; g.act = 0;
-                    if ((rc = gemm_launch(g, 0, 3, st))) return rc;
-                }
+            // hi + lo weight planes stay resident in tensor memory: 256 k-values per launch; wider inputs (768-dim SSL
+            // features on layer 0) are split along K and accumulated into xg
+            for (int k0 = 0; k0 < lo.D; k0 += 256) {
+                const int kc = std::min(256, lo.D - k0);
+                if ((rc = gemm_ts_xg_launch(a_hi + k0, a_lo + k0, lda, bc, (int)T, kc, w_hi + k0, w_lo + k0, round64(kc), lo.Kp, bias,
+                                            k0 > 0, xg, sms, st))) return rc;
             }
             __half* yh = reinterpret_cast<__half*>(outbuf);
             __half* yl = yh + rows * 2 * kHidden;
@@ -220,11 +210,11 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
         __half* z1_lo = z1_hi + rows * kHidden;
         float* z2 = reinterpret_cast<float*>(z1_lo + rows * kHidden);
         if ((rc = gemm_ts_launch(a_hi, a_lo, 2 * kHidden, rows, 2 * kHidden, reinterpret_cast<const __half*>(pk + m.w1_hi),
-                                 reinterpret_cast<const __half*>(pk + m.w1_lo), 2 * kHidden, kHidden,
-                                 reinterpret_cast<const float*>(pk + m.b1), 1, nullptr, z1_hi, z1_lo, kHidden, 0, sms, st))) return rc;
+                                 reinterpret_cast<const __half*>(pk + m.w1_lo), 2 * kHidden, 2 * kHidden, kHidden,
+                                 reinterpret_cast<const float*>(pk + m.b1), 1, 0, nullptr, z1_hi, z1_lo, kHidden, sms, st))) return rc;
         if ((rc = gemm_ts_launch(z1_hi, z1_lo, kHidden, rows, kHidden, reinterpret_cast<const __half*>(pk + m.w2_hi),
-                                 reinterpret_cast<const __half*>(pk + m.w2_lo), kHidden, kHidden,
-                                 reinterpret_cast<const float*>(pk + m.b2), 2, z2, nullptr, nullptr, kHidden, 0, sms, st))) return rc;
+                                 reinterpret_cast<const __half*>(pk + m.w2_lo), kHidden, kHidden, kHidden,
+                                 reinterpret_cast<const float*>(pk + m.b2), 2, 0, z2, nullptr, nullptr, kHidden, sms, st))) return rc;
         if ((rc = classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc),
                                     prob + b0 * T, st))) return rc;
     }
@@ -362,7 +352,7 @@ int b200vad_model_pack_lstm(void* packed, int D, int L, int layer, int dir, cons
     char* pk = reinterpret_cast<char*>(packed);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = split_weights(w_ih, kGates, lo.D, lo.Kp, reinterpret_cast<__half*>(pk + lo.wih_hi) + (size_t)dir * kGates * lo.Kp,
-                           reinterpret_cast<__half*>(pk + lo.wih_lo) + (size_t)dir * kGates * lo.Kp, st);
+                           reinterpret_cast<__half*>(pk + lo.wih_lo) + (size_t)dir * kGates * lo.Kp, st, 1);
     if (rc) return rc;
     rc = add_bias(b_ih, b_hh, reinterpret_cast<float*>(pk + lo.bias) + dir * kGates, kGates, st);
     if (rc) return rc;
@@ -391,7 +381,7 @@ int b200vad_model_pack_head(void* packed, int D, int L, const float* w1, const f
 
 size_t b200vad_model_workspace_bytes(int B, int64_t T) {
     if (B <= 0 || T <= 0) return 0;
-    return (size_t)B * model_per_row(768, T) + 4096;   /* sized for the widest supported input (D <= 768) */
+    return (size_t)ceil64(B) * model_per_row(768, T) + 4096;   /* whole 64-sequence blocks, widest supported input (D <= 768) */
 }
 
 int b200vad_model_forward_f32(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
@@ -420,7 +410,8 @@ int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, i
     int rc = split_planes_launch(a, M * K, a_hi, a_lo, st);
     if (rc) return rc;
     if ((rc = split_weights(w, N, K, Kp, w_hi, w_lo, st))) return rc;
-    return gemm_ts_launch(a_hi, a_lo, K, M, K, w_hi, use_w_lo ? w_lo : nullptr, Kp, N, bias, 0, c, nullptr, nullptr, N, 0, num_sms_cached(), st);
+    return gemm_ts_launch(a_hi, a_lo, K, M, K, w_hi, use_w_lo ? w_lo : nullptr, Kp, Kp, N, bias, 0, 0, c, nullptr, nullptr, N,
+                          num_sms_cached(), st);
 }
 
 // ---------------------------------------------------------------- SincNet

@@ -190,20 +190,21 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
 
 // weights fp32 [N][K] -> fp16 hi / lo [N][Kp], zero padded
 __global__ void split_weights_kernel(const float* __restrict__ w, int N, int K, int Kp, __half* __restrict__ hi,
-                                     __half* __restrict__ lo) {
+                                     __half* __restrict__ lo, int gate_scale) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * Kp) return;
     int n = (int)(idx / Kp), k = (int)(idx % Kp);
     float x = (k < K) ? w[(int64_t)n * K + k] : 0.f;
+    if (gate_scale) x *= lstm_gate_scale(n);
     __half h, l;
     split_f16(x, h, l);
     hi[idx] = h;
     if (lo) lo[idx] = l;
 }
 
-int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, cudaStream_t stream) {
+int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, cudaStream_t stream, int gate_scale) {
     int64_t tot = (int64_t)N * Kp;
-    split_weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(w, N, K, Kp, hi, lo);
+    split_weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(w, N, K, Kp, hi, lo, gate_scale);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

@@ -40,9 +40,11 @@ struct GemmTsParams {
     __half* o_hi;            // mode 1: [M][ldc] fp16 planes
     __half* o_lo;
     int64_t ldc;
-    int64_t c_block_stride;  // mode 0: 0 = row-major [M][ldc]; else feature-blocked [N/128][M][128] (elements between blocks)
     int64_t M;
     int num_m_tiles;
+    int ldw;                 // weight row pitch in elements (>= Kp)
+    int accumulate;          // modes 0, 3: add to the existing C (K split over several launches); bias is then ignored
+    int T, tiles_per_blk;    // mode 3: rows are (sequence, step) pairs; a tile = 64 sequences x 2 steps
     int n_blocks;            // N / 128
     int kb;                  // k-blocks of 64
     int nw;                  // weight planes: 1 (hi) or 2 (hi, lo)
@@ -51,6 +53,11 @@ struct GemmTsParams {
 };
 
 // MODE 0: C = acc + bias (fp32)      MODE 1: leaky_relu(acc + bias) -> fp16 (hi, lo) planes      MODE 2: leaky_relu -> fp32
+// MODE 3: LSTM input projection in the recurrence's step-blocked layout.  Activations are a (B, T, K) tensor; a
+//   tile is 64 sequences x 2 steps (tile row j = sequence * 2 + step, fetched as one 3-D TMA box), and
+//   C = xg[sequence block][direction][t][gate][column group 16][unit 128][4 columns] fp32, feature = (direction,
+//   gate, unit): every (block, direction, t) is one contiguous 128 KB record, which is what one recurrence CTA
+//   consumes per step; the epilogue thread of a unit writes 4 sequences of one step as one 16-byte store.
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_TS_THREADS, 1)
 gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo, GemmTsParams p) {
@@ -94,8 +101,14 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 for (int kb = 0; kb < p.kb; ++kb) {
                     mbar_wait(bar_a_empty(s), ph ^ 1);
                     mbar_expect_tx(bar_a_full(s), 2 * S_TILE_BYTES);
-                    tma_load_2d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, t * SBM, bar_a_full(s));
-                    tma_load_2d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, t * SBM, bar_a_full(s));
+                    if (MODE == 3) {
+                        const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
+                        tma_load_3d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, tp * 2, bblk * 64, bar_a_full(s));
+                        tma_load_3d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, tp * 2, bblk * 64, bar_a_full(s));
+                    } else {
+                        tma_load_2d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, t * SBM, bar_a_full(s));
+                        tma_load_2d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, t * SBM, bar_a_full(s));
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -139,7 +152,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int out = blk * 128 + q * 32 + lane;                              // output feature == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int w = 0; w < p.nw; ++w) {
-            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.Kp);
+            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.ldw);
             for (int part = 0; part < p.Kp / 32; ++part) {                      // 32 fp16 = 16 packed columns
                 uint32_t r[16];
 #pragma unroll
@@ -153,15 +166,49 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_w);
-        const float bias = p.bias ? __ldg(p.bias + out) : 0.f;
-        // blocked output: this CTA's 128 features of consecutive rows are contiguous (64 KB per tile, one DRAM stream)
-        const int64_t col_off = (MODE == 0 && p.c_block_stride) ? (int64_t)blk * p.c_block_stride + q * 32 + lane : out;
+        const float bias = (p.bias && !p.accumulate) ? __ldg(p.bias + out) : 0.f;
         int it = 0;
         for (int t = tile0; t < p.num_m_tiles; t += tile_step, ++it) {
             const int ab = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
             mbar_wait(bar_acc_full(ab), acc_ph);
             tc_fence_after();
+            if (MODE == 3) {
+                // feature = (dir, gate, unit): blk = dir * 4 + gate, unit = q * 32 + lane
+                const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
+                const int dir = blk >> 2, gate = blk & 3;
+                const int t0 = tp * 2;
+                // float offset of (bblk, dir, t0, gate, cgrp 0, unit, 0); one step further = 4 * 8192 floats
+                float* base = p.c + ((((int64_t)bblk * 2 + dir) * p.T + t0) * 4 + gate) * 8192 + (q * 32 + lane) * 4;
+                const bool t1_ok = t0 + 1 < p.T;
+#pragma unroll 1
+                for (int c = 0; c < SBM / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(lane_addr + ACC_COL + ab * SBM + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == SBM / 32 - 1) {
+                        tc_fence_before();
+                        mbar_arrive(bar_acc_empty(ab));
+                    }
+                    // accumulator column j = sequence * 2 + step; 8 columns = 4 sequences (one column group) x 2 steps
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+#pragma unroll
+                        for (int tl = 0; tl < 2; ++tl) {
+                            if (tl == 1 && !t1_ok) continue;
+                            float4* dst = reinterpret_cast<float4*>(base + (int64_t)tl * 4 * 8192 + ((c * 4 + g4) * 128) * 4);
+                            float4 o = make_float4(v[8 * g4 + tl] + bias, v[8 * g4 + 2 + tl] + bias, v[8 * g4 + 4 + tl] + bias,
+                                                   v[8 * g4 + 6 + tl] + bias);
+                            if (p.accumulate) {
+                                const float4 old = *dst;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *dst = o;
+                        }
+                    }
+                }
+                continue;
+            }
             const int64_t row0 = (int64_t)t * SBM;
             const int nrows = (int)min((int64_t)SBM, p.M - row0);
 #pragma unroll 1
@@ -174,12 +221,13 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     mbar_arrive(bar_acc_empty(ab));                             // 128 arrivals release the accumulator
                 }
                 // lane = output feature, register j = row: every store instruction writes one contiguous run per warp
-                const int64_t base = (row0 + c * 32) * p.ldc + col_off;
+                const int64_t base = (row0 + c * 32) * p.ldc + out;
                 const int lim = nrows - c * 32;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (j < lim) {
                         float x = v[j] + bias;
+                        if (MODE == 0 && p.accumulate) x += p.c[base + j * p.ldc];
                         if (MODE != 0) x = x > 0.f ? x : 0.01f * x;
                         if (MODE == 1) {
                             __half hh, hl;
@@ -212,6 +260,24 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     } else {
         for (; i < n; ++i) split_f16(x[i], hi[i], lo[i]);
     }
+}
+// rows of D values -> planes with row pitch D8 (D rounded up to 8: 16-byte rows for TMA), padding zeroed
+__global__ void __launch_bounds__(256) split_planes_pad_kernel(const float* __restrict__ x, int64_t rows, int D, int D8,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * D8) return;
+    const int64_t r = i / D8;
+    const int k = (int)(i - r * D8);
+    __half h = __float2half_rn(0.f), l = h;
+    if (k < D) split_f16(x[r * D + k], h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+int split_planes_pad_launch(const float* x, int64_t rows, int D, int D8, __half* hi, __half* lo, cudaStream_t st) {
+    if (rows <= 0) return B200VAD_OK;
+    split_planes_pad_kernel<<<(unsigned)((rows * D8 + 255) / 256), 256, 0, st>>>(x, rows, D, D8, hi, lo);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
 }
 int split_planes_launch(const float* x, int64_t n, __half* hi, __half* lo, cudaStream_t st) {
     if (n <= 0) return B200VAD_OK;
@@ -301,52 +367,78 @@ int make_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
     return B200VAD_OK;
 }
 
-// ---------------------------------------------------------------- launcher
-// a_hi/a_lo: [M, K] fp16 (row pitch lda elements, lda % 8 == 0);  w_hi/w_lo: [N, Kp] fp16 (Kp % 64 == 0, zero padded);
-// N must be a multiple of 128 and planes * Kp <= 512 (weights resident in 256 TMEM columns).  w_lo may be null.
-// mode 0: c fp32 = acc + bias, row-major [M][ldc] or (c_block_stride != 0, ldc = 128) feature-blocked [N/128][M][128];  mode 1: leaky_relu -> fp16 planes o_hi / o_lo [M, ldc];  mode 2: leaky_relu -> c fp32.
-int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
-                   int Kp, int N, const float* bias, int mode, float* c, __half* o_hi, __half* o_lo, int64_t ldc,
-                   int64_t c_block_stride, int num_sms, cudaStream_t st) {
-    if (M <= 0) return B200VAD_OK;
-    const int nw = w_lo ? 2 : 1;
-    if (N % 128 != 0 || Kp % 64 != 0 || lda % 8 != 0 || K > Kp || nw * Kp > 512 || mode < 0 || mode > 2) {
-        set_error("gemm_ts: unsupported shape N=%d K=%d Kp=%d planes=%d lda=%lld mode=%d", N, K, Kp, nw, (long long)lda, mode);
-        return B200VAD_EINVAL;
-    }
-    GemmTsParams p;
-    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = c; p.o_hi = o_hi; p.o_lo = o_lo; p.ldc = ldc; p.c_block_stride = c_block_stride; p.M = M;
-    p.num_m_tiles = (int)((M + SBM - 1) / SBM);
+// ---------------------------------------------------------------- launchers
+static int gemm_ts_run(int mode, const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, GemmTsParams& p, int N, int num_sms,
+                       cudaStream_t st) {
     p.n_blocks = N / 128;
-    p.kb = Kp / SBK;
-    p.nw = nw;
-    p.Kp = Kp;
     p.stages = 6;
     const int smem = 1024 + p.stages * 2 * S_TILE_BYTES + 256;
-    CUtensorMap tm_a_hi, tm_a_lo;
-    int rc;
-    if ((rc = make_tmap_2d(&tm_a_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_2d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     int grid = (num_sms / p.n_blocks) * p.n_blocks;
     if (grid < p.n_blocks) grid = p.n_blocks;
     const int64_t max_grid = (int64_t)p.num_m_tiles * p.n_blocks;
     if (grid > max_grid) grid = (int)max_grid;
-    static bool attr[3] = {false, false, false};
-    const int prof_kind = mode == 0 ? 1 : 2;
+    typedef void (*KernFn)(CUtensorMap, CUtensorMap, GemmTsParams);
+    static const KernFn kerns[4] = {gemm_ts_kernel<0>, gemm_ts_kernel<1>, gemm_ts_kernel<2>, gemm_ts_kernel<3>};
+    static bool attr[4] = {false, false, false, false};
+    if (!attr[mode]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[mode] = true; }
+    const int prof_kind = (mode == 0 || mode == 3) ? 1 : 2;
     prof_begin(prof_kind, st);
-    if (mode == 0) {
-        if (!attr[0]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
-        gemm_ts_kernel<0><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
-    } else if (mode == 1) {
-        if (!attr[1]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
-        gemm_ts_kernel<1><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
-    } else {
-        if (!attr[2]) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[2] = true; }
-        gemm_ts_kernel<2><<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
-    }
+    kerns[mode]<<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
     prof_end(prof_kind, st);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
+}
+
+static int gemm_ts_check(int K, int Kp, int ldw, int N, int64_t lda, int nw) {
+    if (N % 128 != 0 || Kp % 64 != 0 || lda % 8 != 0 || K > Kp || ldw < Kp || ldw % 8 != 0 || nw * Kp > 512) {
+        set_error("gemm_ts: unsupported shape N=%d K=%d Kp=%d ldw=%d planes=%d lda=%lld", N, K, Kp, ldw, nw, (long long)lda);
+        return B200VAD_EINVAL;
+    }
+    return B200VAD_OK;
+}
+
+// a_hi/a_lo: [M, K] fp16 (row pitch lda elements, lda % 8 == 0);  w_hi/w_lo: [N, ldw] fp16, columns [K, Kp) zero (Kp % 64 == 0);
+// N must be a multiple of 128 and planes * Kp <= 512 (weights resident in 256 TMEM columns).  w_lo may be null.
+// mode 0: c[M, ldc] fp32 = acc + bias (accumulate: c += acc);  mode 1: leaky_relu -> fp16 planes o_hi / o_lo [M, ldc];
+// mode 2: leaky_relu -> c fp32.
+int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
+                   int Kp, int ldw, int N, const float* bias, int mode, int accumulate, float* c, __half* o_hi, __half* o_lo,
+                   int64_t ldc, int num_sms, cudaStream_t st) {
+    if (M <= 0) return B200VAD_OK;
+    const int nw = w_lo ? 2 : 1;
+    int rc = gemm_ts_check(K, Kp, ldw, N, lda, nw);
+    if (rc) return rc;
+    if (mode < 0 || mode > 2) { set_error("gemm_ts: bad mode %d", mode); return B200VAD_EINVAL; }
+    GemmTsParams p = {};
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = c; p.o_hi = o_hi; p.o_lo = o_lo; p.ldc = ldc; p.M = M;
+    p.num_m_tiles = (int)((M + SBM - 1) / SBM);
+    p.kb = Kp / SBK; p.nw = nw; p.Kp = Kp; p.ldw = ldw; p.accumulate = accumulate;
+    CUtensorMap tm_a_hi, tm_a_lo;
+    if ((rc = make_tmap_2d(&tm_a_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_2d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    return gemm_ts_run(mode, tm_a_hi, tm_a_lo, p, N, num_sms, st);
+}
+
+// LSTM input projection (mode 3): x planes (B, T, K) with row pitch lda -> xg in the step-blocked layout described at
+// gemm_ts_kernel (N = 1024 features = 2 directions x 4 gates x 128 units; xg holds ceil(B / 64) * 64 sequences).
+int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
+                      const __half* w_lo, int Kp, int ldw, const float* bias, int accumulate, float* xg, int num_sms,
+                      cudaStream_t st) {
+    if (B <= 0 || T <= 0) return B200VAD_OK;
+    const int nw = w_lo ? 2 : 1;
+    int rc = gemm_ts_check(K, Kp, ldw, 2 * kGates, lda, nw);
+    if (rc) return rc;
+    GemmTsParams p = {};
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = xg; p.M = (int64_t)B * T;
+    p.T = T; p.tiles_per_blk = (T + 1) / 2;
+    p.num_m_tiles = ((B + 63) / 64) * p.tiles_per_blk;
+    p.kb = Kp / SBK; p.nw = nw; p.Kp = Kp; p.ldw = ldw; p.accumulate = accumulate;
+    CUtensorMap tm_a_hi, tm_a_lo;
+    if ((rc = make_tmap_3d(&tm_a_hi, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, T, B, lda * 2, (uint64_t)T * lda * 2, SBK, 2, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_3d(&tm_a_lo, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, T, B, lda * 2, (uint64_t)T * lda * 2, SBK, 2, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    return gemm_ts_run(3, tm_a_hi, tm_a_lo, p, 2 * kGates, num_sms, st);
 }
 
 }  // namespace b200vad

@@ -19,7 +19,8 @@ struct GemmArgs {
 };
 
 int gemm_launch(const GemmArgs& a, int a_half, int terms, cudaStream_t stream);
-int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, cudaStream_t stream);
+// gate_scale != 0: rows are LSTM gate rows (i,f,g,o blocks of 128) and are pre-multiplied by lstm_gate_scale(row)
+int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, cudaStream_t stream, int gate_scale = 0);
 int fbank_tables_init(int device);
 int zero_f64_launch(double* p, int64_t n, cudaStream_t stream);
 int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, int64_t T_out,
@@ -27,8 +28,12 @@ int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_
 int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, int T, cudaStream_t stream);
 int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, float* y_f32, int B, int T, cudaStream_t st);
 int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
-                   int Kp, int N, const float* bias, int mode, float* c, __half* o_hi, __half* o_lo, int64_t ldc,
-                   int64_t c_block_stride, int num_sms, cudaStream_t st);
+                   int Kp, int ldw, int N, const float* bias, int mode, int accumulate, float* c, __half* o_hi, __half* o_lo,
+                   int64_t ldc, int num_sms, cudaStream_t st);
+int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
+                      const __half* w_lo, int Kp, int ldw, const float* bias, int accumulate, float* xg, int num_sms,
+                      cudaStream_t st);
+int split_planes_pad_launch(const float* x, int64_t rows, int D, int D8, __half* hi, __half* lo, cudaStream_t st);
 int split_planes_launch(const float* x, int64_t n, __half* hi, __half* lo, cudaStream_t st);
 int classifier_launch(const float* z, int64_t rows, const float* wc, const float* bc, float* prob, cudaStream_t stream);
 int pack_whh(const float* w, __half* out, cudaStream_t stream);

@@ -116,10 +116,10 @@ lstm_recurrent_kernel(const float* __restrict__ xg, const __half* __restrict__ w
                 float hv[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    float ig = sigmoid_acc(acc[mt][0][2 * hh + e]);
-                    float fg = sigmoid_acc(acc[mt][1][2 * hh + e]);
-                    float gg = tanh_acc(acc[mt][2][2 * hh + e]);
-                    float og = sigmoid_acc(acc[mt][3][2 * hh + e]);
+                    float ig = sigmoid_pre(acc[mt][0][2 * hh + e]);
+                    float fg = sigmoid_pre(acc[mt][1][2 * hh + e]);
+                    float gg = tanh_pre(acc[mt][2][2 * hh + e]);
+                    float og = sigmoid_pre(acc[mt][3][2 * hh + e]);
                     float c = fmaf(fg, cst[mt][hh][e], ig * gg);
                     cst[mt][hh][e] = c;
                     hv[e] = og * tanh_acc(c);
@@ -169,13 +169,14 @@ int classifier_launch(const float* z, int64_t rows, const float* wc, const float
 }
 
 // fp16 gate-major copy of W_hh
+// W_hh and the summed biases carry the gate exponent scaling (common.cuh lstm_gate_scale)
 __global__ void pack_whh_kernel(const float* __restrict__ w, __half* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2half_rn(w[i]);
+    if (i < n) out[i] = __float2half_rn(w[i] * lstm_gate_scale(i / kHidden));
 }
 __global__ void add_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = a[i] + b[i];
+    if (i < n) out[i] = (a[i] + b[i]) * lstm_gate_scale(i);
 }
 
 int pack_whh(const float* w, __half* out, cudaStream_t stream) {

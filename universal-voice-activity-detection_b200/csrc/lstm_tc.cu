@@ -18,10 +18,12 @@
 //   * the 64 columns are two independent halves: while the pointwise warpgroups of half 0 update
 //     their cells, the tensor core (issued by warp 16) runs half 1's MMAs.  Each half is shared by
 //     two warpgroups of 16 columns (4 warps per scheduler on the ex2/rcp dependency chains);
+//     warps 17..20 are the xg TMA producers, one per pointwise warpgroup;
 //   * cell state c lives in shared memory (fp32, conflict-free), so the column loop is a real loop;
 //   * xg is the only HBM read stream (4 KB per sequence-step-direction): warp 17 feeds it through a
 //     4-stage TMA ring per warpgroup (4 columns x 512 gates per stage, 128 KB in flight per SM); xg is stored
-//     feature-blocked ([dir, gate][B][T][128]) so that the GEMM writes, and this kernel reads, long DRAM runs
+//     step-blocked: the 128 KB a CTA consumes per step are one contiguous record [gate][column group][unit][4 columns],
+//     so a stage is one TMA box and a thread reads its 4 columns of a gate with one 16-byte shared-memory load
 //     (an L2 prefetch ahead of the ring measured no gain -- profiles/r01_lstm_ablation.md).
 // Per step and CTA: 2 x 64 tcgen05.mma (M128 N32 K16, A in TMEM), 8192 cells, 5 ex2 + 2 rcp per cell.
 // Algorithmic FLOPs: 2*128*512 per (sequence, frame, direction); algorithmic HBM bytes per
@@ -35,17 +37,18 @@ namespace b200vad {
 using namespace tc;
 
 constexpr int LNB = 64;                    // sequences per CTA
-constexpr int LHALF = 32;                  // columns per MMA half
+// The 64 columns are split into PARTS (2 or 4) independently pipelined groups of 64 / PARTS columns: while the
+// pointwise warpgroups of one part update their cells, the tensor core runs another part's MMAs.
+constexpr int LPARTS_DEFAULT = 4;          // pipelined column groups (B200VAD_LSTM_PARTS=2 selects the two-half schedule)
 constexpr int LWG = 4;                     // pointwise warpgroups
 constexpr int LWCOLS = LNB / LWG;          // 16 columns per warpgroup
 constexpr int LCH = 4;                     // columns per ring stage / inner chunk
 constexpr int LNCH = LWCOLS / LCH;         // chunks per step and warpgroup
 constexpr int LSTAGES = 4;                 // xg ring depth per warpgroup
-constexpr int LTC_THREADS = (LWG * 4 + 2) * 32;   // 576
+constexpr int LTC_THREADS = (LWG * 4 + 1 + LWG) * 32;   // 16 pointwise warps + MMA warp + one xg producer warp per warpgroup = 672
 constexpr int H_TILE = LNB * 64 * 2;       // 8 KB
 constexpr int C_BYTES = LNB * kHidden * 4; // 32 KB cell state
-constexpr int X_HALF = LCH * 256 * 4;      // one TMA box: 4 columns x 256 gate values (fp32) = 4 KB
-constexpr int X_STAGE = 2 * X_HALF;        // (i,f) box + (g,o) box
+constexpr int X_STAGE = 4 * kHidden * LCH * 4;   // one TMA box: 4 gates x 128 units x 4 columns (fp32) = 8 KB
 constexpr int TMEM_W = 4 * LNB;            // first TMEM column of W_hh (gate q at TMEM_W + 64 q)
 
 struct LstmTcParams {
@@ -55,7 +58,7 @@ struct LstmTcParams {
     int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
 };
 
-template <bool F32OUT>
+template <bool F32OUT, int PARTS>
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant__ CUtensorMap tm_yhi,
                const __grid_constant__ CUtensorMap tm_ylo, LstmTcParams p) {
@@ -67,11 +70,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     const uint32_t x_off = c_off + C_BYTES;                  // [LWG][LSTAGES] xg stages
     const uint32_t bar_off = x_off + LWG * LSTAGES * X_STAGE;
     const uint32_t bar_base = smem_base + bar_off;
+    constexpr int LPN = LNB / PARTS;                          // columns per part (MMA N)
+    constexpr int WG_PER_PART = LWG / PARTS;
     auto bar_h_ready = [&](int h) { return bar_base + 8 * h; };
-    auto bar_acc_ready = [&](int h) { return bar_base + 16 + 8 * h; };
-    auto bar_x_full = [&](int wg, int st) { return bar_base + 32 + 8 * (wg * LSTAGES + st); };
-    auto bar_x_empty = [&](int wg, int st) { return bar_base + 32 + 8 * (LWG * LSTAGES + wg * LSTAGES + st); };
-    const uint32_t tmem_slot = bar_base + 32 + 8 * 2 * LWG * LSTAGES;
+    auto bar_acc_ready = [&](int h) { return bar_base + 32 + 8 * h; };
+    auto bar_x_full = [&](int wg, int st) { return bar_base + 64 + 8 * (wg * LSTAGES + st); };
+    auto bar_x_empty = [&](int wg, int st) { return bar_base + 64 + 8 * (LWG * LSTAGES + wg * LSTAGES + st); };
+    const uint32_t tmem_slot = bar_base + 64 + 8 * 2 * LWG * LSTAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -79,7 +84,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     const int T = p.T;
 
     if (threadIdx.x == 0) {
-        for (int h = 0; h < 2; ++h) { mbar_init(bar_h_ready(h), 256); mbar_init(bar_acc_ready(h), 1); }
+        for (int h = 0; h < PARTS; ++h) { mbar_init(bar_h_ready(h), 128 * WG_PER_PART); mbar_init(bar_acc_ready(h), 1); }
         for (int g = 0; g < LWG; ++g)
             for (int st = 0; st < LSTAGES; ++st) { mbar_init(bar_x_full(g, st), 1); mbar_init(bar_x_empty(g, st), 4); }
         mbar_fence_init();
@@ -91,11 +96,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 17) {
-        // ===================== xg producer: lane g feeds warpgroup g =====================
-        if (lane < LWG && !(p.flags & 1)) {
-            const int wg = lane;
-            const int bcol = b0 + wg * LWCOLS;
+    if (warp >= 17) {
+        // ===================== xg producers: warp 17 + g feeds warpgroup g =====================
+        // (one warp each: four lanes of one warp spinning on different barriers serialise each other)
+        if (elect_one() && !(p.flags & 1)) {
+            const int wg = warp - 17;
             int st = 0;
             uint32_t ph = 0;
             for (int s = 0; s < T; ++s) {
@@ -105,8 +110,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     mbar_wait(bar_x_empty(wg, st), ph ^ 1);
                     const uint32_t dst = smem_base + x_off + (wg * LSTAGES + st) * X_STAGE;
                     mbar_expect_tx(bar_x_full(wg, st), X_STAGE);
-                    tma_load_4d(dst, &tm_xg, 0, t, bcol + ch * LCH, dir * 4, bar_x_full(wg, st));
-                    tma_load_4d(dst + X_HALF, &tm_xg, 0, t, bcol + ch * LCH, dir * 4 + 2, bar_x_full(wg, st));
+                    // one box = 4 gates x (128 units x 4 columns) of this step's 128 KB record
+                    tma_load_4d(dst, &tm_xg, 0, wg * LNCH + ch, 0, (blockIdx.x * 2 + dir) * T + t, bar_x_full(wg, st));
                     if (++st == LSTAGES) { st = 0; ph ^= 1; }
                 }
             }
@@ -114,31 +119,31 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     } else if (warp == 16) {
         // ===================== MMA issue + layer-output TMA stores =====================
         if (elect_one()) {
-            constexpr uint32_t idesc = idesc_f16(128, LHALF);
+            constexpr uint32_t idesc = idesc_f16(128, LPN);
             // iteration s: h_ready(h) phase s = "h_{s-1} is in tile buffer (s & 1)" (phase 0 = zero state + W_hh in TMEM)
             for (int s = 0; s <= T; ++s) {
                 const uint32_t hbuf = h_base + (s & 1) * 4 * H_TILE;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < PARTS; ++h) {
                     mbar_wait(bar_h_ready(h), s & 1);
                     tc_fence_after();
                     if (s < T) {
                         if (!(p.flags & 2)) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const uint32_t d = tmem_base + q * LNB + h * LHALF;
+                                const uint32_t d = tmem_base + q * LNB + h * LPN;
 #pragma unroll
                                 for (int kk = 0; kk < 8; ++kk) {
                                     const uint32_t a = tmem_base + TMEM_W + q * 64 + kk * 8;
-                                    const uint32_t hb = hbuf + (kk >> 2) * H_TILE + h * (LHALF * 128) + (kk & 3) * 32;
+                                    const uint32_t hb = hbuf + (kk >> 2) * H_TILE + h * (LPN * 128) + (kk & 3) * 32;
                                     if (!(p.flags & 4)) mma_f16_ts(d, a, smem_desc_sw128(hb + 2 * H_TILE), idesc, kk != 0);   // h_lo first
                                     mma_f16_ts(d, a, smem_desc_sw128(hb), idesc, (p.flags & 4) ? (uint32_t)(kk != 0) : 1u); // h_hi
                                 }
                             }
                         }
                         // once acc_ready fires the pointwise warps rewrite buffer (s+1)&1, last read by the store group of
-                        // iteration s-1 for this half: every group but the most recent one must have finished reading
-                        if (!F32OUT) tma_store_wait_read<1>();
+                        // iteration s-1 for this part: every group but the PARTS-1 most recent ones must have finished reading
+                        if (!F32OUT) tma_store_wait_read<PARTS - 1>();
                         mma_commit(bar_acc_ready(h));
                     }
                     if (!F32OUT && s > 0) {
@@ -146,8 +151,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                         const int t = dir == 0 ? s - 1 : T - s;
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb) {
-                            tma_store_3d(&tm_yhi, dir * kHidden + kb * 64, t, b0 + h * LHALF, hbuf + kb * H_TILE + h * (LHALF * 128));
-                            tma_store_3d(&tm_ylo, dir * kHidden + kb * 64, t, b0 + h * LHALF, hbuf + (2 + kb) * H_TILE + h * (LHALF * 128));
+                            tma_store_3d(&tm_yhi, dir * kHidden + kb * 64, t, b0 + h * LPN, hbuf + kb * H_TILE + h * (LPN * 128));
+                            tma_store_3d(&tm_ylo, dir * kHidden + kb * 64, t, b0 + h * LPN, hbuf + (2 + kb) * H_TILE + h * (LPN * 128));
                         }
                         tma_store_commit();
                     }
@@ -158,7 +163,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     } else {
         // ===================== pointwise warpgroups =====================
         const int wg = warp >> 2;                       // columns [wg*16, wg*16+16)
-        const int half = wg >> 1;
+        const int half = wg / WG_PER_PART;              // the part this warpgroup belongs to
         const int u = (warp & 3) * 32 + lane;           // hidden unit == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         // W_hh -> TMEM: warpgroup g stores gate g; lane u gets row (dir, g, u): 128 fp16 = 64 packed words
@@ -190,7 +195,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
 
         unsigned char* const h_hi0 = smem_gen + (u >> 6) * H_TILE + (u & 7) * 2;   // + row*128 + swizzled chunk
         const uint32_t uc = (u & 63) >> 3;
-        const float* const xring = reinterpret_cast<const float*>(smem_gen + x_off + wg * LSTAGES * X_STAGE) + u;
+        const float* const xring = reinterpret_cast<const float*>(smem_gen + x_off + wg * LSTAGES * X_STAGE) + u * LCH;
         int st = 0;
         uint32_t xph = 0;
         const float L2E = 1.4426950408889634f;
@@ -212,23 +217,25 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < LCH; ++j) x[g][j] = 0.1f * g;
                 } else {
-                    // xg chunk from the ring: stage = [(i,f) box | (g,o) box], box = [gate block (2)][col (4)][128]
+                    // xg chunk from the ring: stage = [gate 4][unit 128][column 4] -> one 16-byte load per gate
                     mbar_wait(bar_x_full(wg, st), xph);
-                    const float* xs = xring + st * (X_STAGE / 4);
+                    const float4* xs = reinterpret_cast<const float4*>(xring + st * (X_STAGE / 4));
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-#pragma unroll
-                        for (int j = 0; j < LCH; ++j) x[g][j] = xs[(g >> 1) * (X_HALF / 4) + (g & 1) * (LCH * 128) + j * 128];
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 v = xs[g * 128];
+                        x[g][0] = v.x; x[g][1] = v.y; x[g][2] = v.z; x[g][3] = v.w;
+                    }
                 }
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < LCH; ++j) {
                     const int n = col0 + j;
                     // one-sided clamps keep every exponential finite (<= 2^29); exp(-inf) = 0 is exact
-                    float ei = fast_ex2(fminf(-L2E * (a[0][j] + x[0][j]), 29.f));
-                    float ef = fast_ex2(fminf(-L2E * (a[1][j] + x[1][j]), 29.f));
-                    float eg = fast_ex2(fminf(2.f * L2E * (a[2][j] + x[2][j]), 29.f));
-                    float eo = fast_ex2(fminf(-L2E * (a[3][j] + x[3][j]), 29.f));
+                    // (pre-activations arrive multiplied by -log2 e / 2 log2 e: the packed weights carry the scale)
+                    float ei = fast_ex2(fminf(a[0][j] + x[0][j], 29.f));
+                    float ef = fast_ex2(fminf(a[1][j] + x[1][j], 29.f));
+                    float eg = fast_ex2(fminf(a[2][j] + x[2][j], 29.f));
+                    float eo = fast_ex2(fminf(a[3][j] + x[3][j], 29.f));
                     // c' = c/(1+ef) + (eg-1)/((1+ei)(eg+1))  with one reciprocal
                     float di = 1.f + ei, df = 1.f + ef, dg = eg + 1.f;
                     float dig = di * dg;
@@ -262,25 +269,31 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
     if (warp == 16) tmem_dealloc<512>(tmem_base);
 }
 
-// xg: feature-blocked [8][B][T][128] fp32 (block = dir * 4 + gate, as gemm_ts writes it); whh: [2][512][128] fp16 (gate-major rows, as nn.LSTM stores weight_hh).
+// xg: step-blocked [ceil(B/64)][2][T][4][16][128][4] fp32 as gemm_ts_xg_launch writes it; whh: [2][512][128] fp16 (gate-major rows, as nn.LSTM stores weight_hh).
 // Exactly one of (y_hi, y_lo: fp16 planes [B][T][256]) / y_f32 is written.
 int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, float* y_f32, int B, int T, cudaStream_t st) {
     if (B <= 0 || T <= 0) return B200VAD_OK;
     CUtensorMap tm_x, tm_yh, tm_yl;
-    // xg is feature-blocked: [8 blocks = (dir, gate)][B][T][128] fp32; one box = 2 gate blocks x LCH sequences of one step
-    const uint64_t xdims[4] = {128, (uint64_t)T, (uint64_t)B, 8};
-    const uint64_t xpitch[3] = {128 * 4, (uint64_t)T * 128 * 4, (uint64_t)B * T * 128 * 4};
-    const uint32_t xbox[4] = {128, 1, LCH, 2};
-    int rc = make_tmap_4d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, xdims, xpitch, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+    // xg is step-blocked (gemm_ts mode 3): [sequence block][dir][t][gate 4][column group 16][unit 128][4] fp32.  Viewed as
+    // 8-byte elements: 256 per (gate, column group) run of 2 KB; one box = the 4 gates of one column group of one step.
+    const uint64_t nblk = (uint64_t)((B + LNB - 1) / LNB);
+    const uint64_t xdims[4] = {256, 16, 4, nblk * 2 * (uint64_t)T};
+    const uint64_t xpitch[3] = {2048, 32768, 131072};
+    const uint32_t xbox[4] = {256, 1, 4, 1};
+    static_assert(LCH == 4 && LNB == 64, "xg layout assumes 4-column groups and 64-sequence blocks");
+    int rc = make_tmap_4d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, xdims, xpitch, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     const void* yh = y_f32 ? (const void*)whh : (const void*)y_hi;      // unused maps still have to be valid
     const void* yl = y_f32 ? (const void*)whh : (const void*)y_lo;
     const uint64_t yT = y_f32 ? 1 : (uint64_t)T, yB = y_f32 ? 32 : (uint64_t)B;
+    static int parts = -1;
+    if (parts < 0) { const char* e = getenv("B200VAD_LSTM_PARTS"); parts = (e && atoi(e) == 2) ? 2 : LPARTS_DEFAULT; }
+    const uint32_t lpn = LNB / parts;
     rc = make_tmap_3d(&tm_yh, yh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * kHidden, yT, yB, (uint64_t)2 * kHidden * 2,
-                      yT * 2 * kHidden * 2, 64, 1, LHALF, CU_TENSOR_MAP_SWIZZLE_128B);
+                      yT * 2 * kHidden * 2, 64, 1, lpn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_tmap_3d(&tm_yl, yl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * kHidden, yT, yB, (uint64_t)2 * kHidden * 2,
-                      yT * 2 * kHidden * 2, 64, 1, LHALF, CU_TENSOR_MAP_SWIZZLE_128B);
+                      yT * 2 * kHidden * 2, 64, 1, lpn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -288,15 +301,12 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     const int smem = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
     dim3 grid((B + LNB - 1) / LNB, 2);
     prof_begin(0, st);
-    if (y_f32) {
-        static bool attr = false;
-        if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        lstm_tc_kernel<true><<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
-    } else {
-        static bool attr = false;
-        if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        lstm_tc_kernel<false><<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
-    }
+    typedef void (*KernFn)(CUtensorMap, CUtensorMap, CUtensorMap, LstmTcParams);
+    static const KernFn kerns[4] = {lstm_tc_kernel<false, 2>, lstm_tc_kernel<false, 4>, lstm_tc_kernel<true, 2>, lstm_tc_kernel<true, 4>};
+    static bool attr[4] = {false, false, false, false};
+    const int ki = (y_f32 ? 2 : 0) + (parts == 4 ? 1 : 0);
+    if (!attr[ki]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[ki] = true; }
+    kerns[ki]<<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
     prof_end(0, st);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
