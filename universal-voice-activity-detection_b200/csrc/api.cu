@@ -200,7 +200,7 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
             }
             __half* yh = reinterpret_cast<__half*>(outbuf);
             __half* yl = yh + rows * 2 * kHidden;
-            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), yh, yl, nullptr, bc, (int)T, st))) return rc;
+            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), yh, yl, bc, (int)T, st))) return rc;
             a_hi = yh; a_lo = yl; lda = 2 * kHidden;
             outbuf = (outbuf == buf0) ? buf1 : buf0;
         }

@@ -105,6 +105,43 @@ __device__ __forceinline__ float tanh_pre(float z) {
     return 1.f - 2.f * fast_rcp(e + 1.f);
 }
 
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): two columns of the recurrence per issue slot ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// elementwise 2^min(z, 29)
+__device__ __forceinline__ f32x2 ex2_clamped2(f32x2 z) {
+    float a, b;
+    unpack2(z, a, b);
+    return pack2(fast_ex2(fminf(a, 29.f)), fast_ex2(fminf(b, 29.f)));
+}
+__device__ __forceinline__ f32x2 rcp2(f32x2 z) {
+    float a, b;
+    unpack2(z, a, b);
+    return pack2(fast_rcp(a), fast_rcp(b));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -19,7 +19,9 @@
 //     their cells, the tensor core (issued by warp 16) runs half 1's MMAs.  Each half is shared by
 //     two warpgroups of 16 columns (4 warps per scheduler on the ex2/rcp dependency chains);
 //     warps 17..20 are the xg TMA producers, one per pointwise warpgroup;
-//   * cell state c lives in shared memory (fp32, conflict-free), so the column loop is a real loop;
+//   * cell state c lives in shared memory (fp32, conflict-free 8-byte accesses: two columns of a unit are adjacent),
+//     so the column loop is a real loop; the cell update runs on packed fp32 pairs (FADD2 / FMUL2 / FFMA2), two
+//     columns per issue slot -- only the MUFU ops, the clamps and the fp16 conversions are scalar;
 //   * xg is the only HBM read stream (4 KB per sequence-step-direction): warp 17 feeds it through a
 //     4-stage TMA ring per warpgroup (4 columns x 512 gates per stage, 128 KB in flight per SM); xg is stored
 //     step-blocked: the 128 KB a CTA consumes per step are one contiguous record [gate][column group][unit][4 columns],
@@ -53,12 +55,11 @@ constexpr int TMEM_W = 4 * LNB;            // first TMEM column of W_hh (gate q 
 
 struct LstmTcParams {
     const __half* whh;     // [2][512][128]
-    float* y_f32;          // [B][T][256] (fp32 mode) or null (planes mode: TMA stores through tm_yhi / tm_ylo)
     int B, T;
     int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
 };
 
-template <bool F32OUT, int PARTS>
+template <int PARTS>
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant__ CUtensorMap tm_yhi,
                const __grid_constant__ CUtensorMap tm_ylo, LstmTcParams p) {
@@ -143,10 +144,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                         }
                         // once acc_ready fires the pointwise warps rewrite buffer (s+1)&1, last read by the store group of
                         // iteration s-1 for this part: every group but the PARTS-1 most recent ones must have finished reading
-                        if (!F32OUT) tma_store_wait_read<PARTS - 1>();
+                        tma_store_wait_read<PARTS - 1>();
                         mma_commit(bar_acc_ready(h));
                     }
-                    if (!F32OUT && s > 0) {
+                    if (s > 0) {
                         // h_{s-1} of this half -> y planes at time t(s-1); rows beyond B are clipped by TMA
                         const int t = dir == 0 ? s - 1 : T - s;
 #pragma unroll
@@ -158,7 +159,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     }
                 }
             }
-            if (!F32OUT) tma_store_wait_all<0>();
+            tma_store_wait_all<0>();
         }
     } else {
         // ===================== pointwise warpgroups =====================
@@ -186,9 +187,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
             int tile = i / (LWCOLS * 8), rem = i % (LWCOLS * 8);
             *reinterpret_cast<uint4*>(smem_gen + tile * H_TILE + wg * LWCOLS * 128 + rem * 16) = make_uint4(0, 0, 0, 0);
         }
-        float* const cst = reinterpret_cast<float*>(smem_gen + c_off) + u;      // + col * 128
+        float* const cst = reinterpret_cast<float*>(smem_gen + c_off) + 2 * u;  // [column pair][unit][2]: + (col >> 1) * 256 + (col & 1)
 #pragma unroll
-        for (int j = 0; j < LWCOLS; ++j) cst[(wg * LWCOLS + j) * kHidden] = 0.f;
+        for (int j = 0; j < LWCOLS; j += 2)
+            *reinterpret_cast<float2*>(cst + ((wg * LWCOLS + j) >> 1) * (2 * kHidden)) = make_float2(0.f, 0.f);
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_h_ready(half));
@@ -201,7 +203,6 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
         const float L2E = 1.4426950408889634f;
 
         for (int s = 0; s < T; ++s) {
-            const int t = dir == 0 ? s : T - 1 - s;
             unsigned char* const h_hi = h_hi0 + ((s + 1) & 1) * 4 * H_TILE;     // h_s goes to buffer (s+1)&1
             mbar_wait(bar_acc_ready(half), s & 1);
             tc_fence_after();
@@ -227,31 +228,38 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     }
                 }
                 tmem_ld_wait();
+                // two columns per issue slot (FADD2 / FMUL2 / FFMA2); MUFU, min and the fp16 conversions stay scalar
+                const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), k2 = pack2(2.f * L2E, 2.f * L2E);
 #pragma unroll
-                for (int j = 0; j < LCH; ++j) {
-                    const int n = col0 + j;
+                for (int jp = 0; jp < LCH / 2; ++jp) {
+                    const int n = col0 + 2 * jp;
+                    // pre-activations arrive multiplied by -log2 e (i, f, o) / 2 log2 e (g): the packed weights carry the scale;
                     // one-sided clamps keep every exponential finite (<= 2^29); exp(-inf) = 0 is exact
-                    // (pre-activations arrive multiplied by -log2 e / 2 log2 e: the packed weights carry the scale)
-                    float ei = fast_ex2(fminf(a[0][j] + x[0][j], 29.f));
-                    float ef = fast_ex2(fminf(a[1][j] + x[1][j], 29.f));
-                    float eg = fast_ex2(fminf(a[2][j] + x[2][j], 29.f));
-                    float eo = fast_ex2(fminf(a[3][j] + x[3][j], 29.f));
+                    const f32x2 ei = ex2_clamped2(add2(pack2(a[0][2 * jp], a[0][2 * jp + 1]), pack2(x[0][2 * jp], x[0][2 * jp + 1])));
+                    const f32x2 ef = ex2_clamped2(add2(pack2(a[1][2 * jp], a[1][2 * jp + 1]), pack2(x[1][2 * jp], x[1][2 * jp + 1])));
+                    const f32x2 eg = ex2_clamped2(add2(pack2(a[2][2 * jp], a[2][2 * jp + 1]), pack2(x[2][2 * jp], x[2][2 * jp + 1])));
+                    const f32x2 eo = ex2_clamped2(add2(pack2(a[3][2 * jp], a[3][2 * jp + 1]), pack2(x[3][2 * jp], x[3][2 * jp + 1])));
                     // c' = c/(1+ef) + (eg-1)/((1+ei)(eg+1))  with one reciprocal
-                    float di = 1.f + ei, df = 1.f + ef, dg = eg + 1.f;
-                    float dig = di * dg;
-                    float cn = fmaf(cst[n * kHidden], dig, (eg - 1.f) * df) * fast_rcp(df * dig);
-                    cst[n * kHidden] = cn;
-                    float ec = fast_ex2(fminf(2.f * L2E * cn, 29.f));
-                    float hv = (ec - 1.f) * fast_rcp((1.f + eo) * (ec + 1.f));
-                    __half hh = __float2half_rn(hv);
-                    __half hl = __float2half_rn(hv - __half2float(hh));
-                    unsigned char* dst = h_hi + n * 128 + ((uc ^ (n & 7)) << 4);
-                    *reinterpret_cast<__half*>(dst) = hh;
-                    *reinterpret_cast<__half*>(dst + 2 * H_TILE) = hl;
-                    if (F32OUT) {
-                        const int b = b0 + n;
-                        if (b < p.B) p.y_f32[((int64_t)b * T + t) * (2 * kHidden) + dir * kHidden + u] = hv;
-                    }
+                    const f32x2 di = add2(ei, one), df = add2(ef, one), dg = add2(eg, one);
+                    const f32x2 dig = mul2(di, dg);
+                    float2* const cptr = reinterpret_cast<float2*>(cst + (n >> 1) * (2 * kHidden));
+                    const float2 cold = *cptr;
+                    const f32x2 cn = mul2(fma2(pack2(cold.x, cold.y), dig, mul2(add2(eg, mone), df)), rcp2(mul2(df, dig)));
+                    float cn0, cn1;
+                    unpack2(cn, cn0, cn1);
+                    *cptr = make_float2(cn0, cn1);
+                    const f32x2 ec = ex2_clamped2(mul2(cn, k2));
+                    const f32x2 hv2 = mul2(add2(ec, mone), rcp2(mul2(add2(eo, one), add2(ec, one))));
+                    float hv0, hv1;
+                    unpack2(hv2, hv0, hv1);
+                    const __half hh0 = __float2half_rn(hv0), hh1 = __float2half_rn(hv1);
+                    const __half hl0 = __float2half_rn(hv0 - __half2float(hh0)), hl1 = __float2half_rn(hv1 - __half2float(hh1));
+                    unsigned char* dst0 = h_hi + n * 128 + ((uc ^ (n & 7)) << 4);
+                    unsigned char* dst1 = h_hi + (n + 1) * 128 + ((uc ^ ((n + 1) & 7)) << 4);
+                    *reinterpret_cast<__half*>(dst0) = hh0;
+                    *reinterpret_cast<__half*>(dst0 + 2 * H_TILE) = hl0;
+                    *reinterpret_cast<__half*>(dst1) = hh1;
+                    *reinterpret_cast<__half*>(dst1 + 2 * H_TILE) = hl1;
                 }
                 if (!(p.flags & 1)) {
                     __syncwarp();
@@ -270,8 +278,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
 }
 
 // xg: step-blocked [ceil(B/64)][2][T][4][16][128][4] fp32 as gemm_ts_xg_launch writes it; whh: [2][512][128] fp16 (gate-major rows, as nn.LSTM stores weight_hh).
-// Exactly one of (y_hi, y_lo: fp16 planes [B][T][256]) / y_f32 is written.
-int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, float* y_f32, int B, int T, cudaStream_t st) {
+// Output: the layer output as fp16 planes y_hi / y_lo [B][T][256].
+int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
     if (B <= 0 || T <= 0) return B200VAD_OK;
     CUtensorMap tm_x, tm_yh, tm_yl;
     // xg is step-blocked (gemm_ts mode 3): [sequence block][dir][t][gate 4][column group 16][unit 128][4] fp32.  Viewed as
@@ -283,9 +291,13 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     static_assert(LCH == 4 && LNB == 64, "xg layout assumes 4-column groups and 64-sequence blocks");
     int rc = make_tmap_4d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, xdims, xpitch, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    const void* yh = y_f32 ? (const void*)whh : (const void*)y_hi;      // unused maps still have to be valid
-    const void* yl = y_f32 ? (const void*)whh : (const void*)y_lo;
-    const uint64_t yT = y_f32 ? 1 : (uint64_t)T, yB = y_f32 ? 32 : (uint64_t)B;
+    const void* yh = y_hi;
+    const void* yl = y_lo;
+    const uint64_t yT = (uint64_t)T, yB = (uint64_t)B;
+    if ((int64_t)nblk * 2 * T >= (1LL << 31)) {
+        set_error("lstm_tc: too many (sequence block, step) records for one launch (B=%d T=%d)", B, T);
+        return B200VAD_EINVAL;
+    }
     static int parts = -1;
     if (parts < 0) { const char* e = getenv("B200VAD_LSTM_PARTS"); parts = (e && atoi(e) == 2) ? 2 : LPARTS_DEFAULT; }
     const uint32_t lpn = LNB / parts;
@@ -297,14 +309,14 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     if (rc) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    LstmTcParams p{whh, y_f32, B, T, dbg};
+    LstmTcParams p{whh, B, T, dbg};
     const int smem = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
     dim3 grid((B + LNB - 1) / LNB, 2);
     prof_begin(0, st);
     typedef void (*KernFn)(CUtensorMap, CUtensorMap, CUtensorMap, LstmTcParams);
-    static const KernFn kerns[4] = {lstm_tc_kernel<false, 2>, lstm_tc_kernel<false, 4>, lstm_tc_kernel<true, 2>, lstm_tc_kernel<true, 4>};
-    static bool attr[4] = {false, false, false, false};
-    const int ki = (y_f32 ? 2 : 0) + (parts == 4 ? 1 : 0);
+    static const KernFn kerns[2] = {lstm_tc_kernel<2>, lstm_tc_kernel<4>};
+    static bool attr[2] = {false, false};
+    const int ki = parts == 4 ? 1 : 0;
     if (!attr[ki]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[ki] = true; }
     kerns[ki]<<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
     prof_end(0, st);
