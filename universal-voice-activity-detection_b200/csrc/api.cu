@@ -127,9 +127,10 @@ static int head_forward(const ModelLayout& m, const char* pk, const float* y, in
     return classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc), prob, st);
 }
 
-static int model_forward(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
-    B200VAD_CHECK_ARG(packed && x && prob && ws, "null pointer");
+// x: (B, T, D) fp32, or null with the layer-0 input already split into fp16 planes xp_hi / xp_lo (B, T, D), D % 8 == 0
+static int model_forward(const void* packed, int D, int L, const float* x, const __half* xp_hi, const __half* xp_lo, int B,
+                         int64_t T, float* prob, void* ws, size_t ws_bytes, cudaStream_t st) {
+    B200VAD_CHECK_ARG(packed && (x || (xp_hi && xp_lo && D % 8 == 0 && g_impl == 2)) && prob && ws, "null pointer");
     B200VAD_CHECK_ARG(D > 0 && L > 0 && B >= 0 && T >= 0, "bad shape");
     B200VAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
     if (B == 0 || T == 0) return B200VAD_OK;
@@ -155,7 +156,7 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
         char* buf1 = w;                                          w += align_up(sizeof(float) * 2 * kHidden * rows);
         __half* x_hi = reinterpret_cast<__half*>(w);             w += align_up(sizeof(__half) * D8 * rows);
         __half* x_lo = reinterpret_cast<__half*>(w);
-        const float* xin = x + b0 * T * D;
+        const float* xin = x ? x + b0 * T * D : nullptr;
         int rc;
         if (g_impl == 1) {
             // ---- warp-MMA validation path: fp32 activations between layers
@@ -179,11 +180,15 @@ static int model_forward(const void* packed, int D, int L, const float* x, int B
             continue;
         }
         // ---- tcgen05 path: activations travel between layers (and into the head) as fp16 (hi, lo) planes
-        if (D % 8 == 0) rc = split_planes_launch(xin, rows * D, x_hi, x_lo, st);
-        else rc = split_planes_pad_launch(xin, rows, D, D8, x_hi, x_lo, st);       // e.g. the 60 SincNet channels -> pitch 64
-        if (rc) return rc;
         const __half* a_hi = x_hi;
         const __half* a_lo = x_lo;
+        if (!xin) {
+            a_hi = xp_hi + b0 * T * D; a_lo = xp_lo + b0 * T * D;                  // planes straight from the fused fbank
+        } else {
+            if (D % 8 == 0) rc = split_planes_launch(xin, rows * D, x_hi, x_lo, st);
+            else rc = split_planes_pad_launch(xin, rows, D, D8, x_hi, x_lo, st);   // e.g. the 60 SincNet channels -> pitch 64
+            if (rc) return rc;
+        }
         int64_t lda = D8;
         char* outbuf = buf0;
         for (int l = 0; l < L; ++l) {
@@ -335,7 +340,7 @@ int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, i
     B200VAD_CHECK_ARG(B <= 65535, "B must be <= 65535 per call");
     int dev = 0;
     B200VAD_CUDA(cudaGetDevice(&dev));
-    return fbank_launch(wav, lens, B, N, wav_stride, feats, T, row_sum_ws, dev, (cudaStream_t)stream);
+    return fbank_launch(wav, lens, B, N, wav_stride, feats, nullptr, nullptr, T, row_sum_ws, dev, (cudaStream_t)stream);
 }
 
 size_t b200vad_model_packed_bytes(int D, int L) {
@@ -386,7 +391,7 @@ size_t b200vad_model_workspace_bytes(int B, int64_t T) {
 
 int b200vad_model_forward_f32(const void* packed, int D, int L, const float* x, int B, int64_t T, float* prob, void* ws,
                               size_t ws_bytes, void* stream) {
-    return model_forward(packed, D, L, x, B, T, prob, ws, ws_bytes, (cudaStream_t)stream);
+    return model_forward(packed, D, L, x, nullptr, nullptr, B, T, prob, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo, float* c,
@@ -608,9 +613,14 @@ static int pipeline_run(const void* packed, int L, const float* wav, const int32
     }
     int dev = 0;
     B200VAD_CUDA(cudaGetDevice(&dev));
-    int rc = fbank_launch(wav, lens, B, N, stride, feats, T, sums, dev, st);
+    // the tcgen05 path takes the features as fp16 (hi, lo) planes straight from the fbank kernel (same bytes as fp32)
+    __half* f_hi = reinterpret_cast<__half*>(feats);
+    __half* f_lo = f_hi + (size_t)B * T * kNumMel;
+    const bool planes = g_impl == 2;
+    int rc = fbank_launch(wav, lens, B, N, stride, planes ? nullptr : feats, planes ? f_hi : nullptr, planes ? f_lo : nullptr, T,
+                          sums, dev, st);
     if (rc) return rc;
-    rc = model_forward(packed, kNumMel, L, feats, B, T, prob, w, ws_bytes - used, st);
+    rc = model_forward(packed, kNumMel, L, planes ? nullptr : feats, f_hi, f_lo, B, T, prob, w, ws_bytes - used, st);
     if (rc) return rc;
     rc = threshold_median_launch(prob, B, T, thr, kernel, dec, 1, nullptr, 0.f, st);
     if (rc) return rc;
@@ -863,9 +873,11 @@ struct b200vad_stream {
 };
 
 static int stream_forward(b200vad_stream* s) {
-    int rc = fbank_launch(s->lin, nullptr, s->S, s->W, s->W, s->feats, s->T, s->sums, s->device, s->st);
+    __half* f_hi = reinterpret_cast<__half*>(s->feats);
+    __half* f_lo = f_hi + (size_t)s->S * s->T * kNumMel;
+    int rc = fbank_launch(s->lin, nullptr, s->S, s->W, s->W, nullptr, f_hi, f_lo, s->T, s->sums, s->device, s->st);
     if (rc) return rc;
-    rc = model_forward(s->packed, kNumMel, s->L, s->feats, s->S, s->T, s->prob, s->ws, s->ws_bytes, s->st);
+    rc = model_forward(s->packed, kNumMel, s->L, nullptr, f_hi, f_lo, s->S, s->T, s->prob, s->ws, s->ws_bytes, s->st);
     if (rc) return rc;
     rc = threshold_median_launch(s->prob, s->S, s->T, s->thr, s->kernel, s->dec, 1, nullptr, 0.f, s->st);
     if (rc) return rc;

@@ -216,10 +216,14 @@ __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
     return __fsub_rn(a, __fmul_rn(0.97f, b));
 }
 
+// PLANES = false: feats (B, T, 80) fp32 (the lhotse layout).  PLANES = true: the same values as fp16 (hi, lo) planes
+// feats_hi / feats_lo (B, T, 80) -- the operand format of the layer-0 projection GEMM, so the fused pipeline skips the
+// fp32 feature round trip and the split kernel.
+template <bool PLANES>
 __global__ void __launch_bounds__(kFbankThreads, 4)
 fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, int64_t N, int64_t stride,
              const double* __restrict__ sums, const FbankTables* __restrict__ tab,
-             float* __restrict__ feats, int64_t T_out) {
+             float* __restrict__ feats, __half* __restrict__ feats_hi, __half* __restrict__ feats_lo, int64_t T_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FbankSmem& sm = *reinterpret_cast<FbankSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -227,12 +231,22 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     const int64_t n = lens ? min((int64_t)lens[b], N) : N;
     const int64_t T = (n + kFrameShift / 2) / kFrameShift;          // valid frames of this row
     const int64_t f0 = (int64_t)blockIdx.x * kTileFrames;
-    float* out_row = feats + ((int64_t)b * T_out) * kNumMel;
+    const int64_t row_off = ((int64_t)b * T_out) * kNumMel;
+    auto put = [&](int64_t idx, float v) {
+        if (PLANES) {
+            __half h, l;
+            split_f16(v, h, l);
+            feats_hi[row_off + idx] = h;
+            feats_lo[row_off + idx] = l;
+        } else {
+            feats[row_off + idx] = v;
+        }
+    };
 
     if (f0 >= T) {   // tile entirely in the padding: lhotse pads features with LOG_EPSILON
         for (int i = tid; i < kTileFrames * kNumMel; i += kFbankThreads) {
             int64_t f = f0 + i / kNumMel;
-            if (f < T_out) out_row[f * kNumMel + (i % kNumMel)] = kLogEpsilon;
+            if (f < T_out) put(f * kNumMel + (i % kNumMel), kLogEpsilon);
         }
         return;
     }
@@ -295,7 +309,8 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
         const int f = pass * kGroups + g;
         const bool active = f < nframes;
         float2 v[16];
-        if (active) {
+        // frames beyond nframes (last tile of a row) compute on stale shared memory and are simply not stored
+        {
             const float* ys = sm.y + f * kFrameShift;
             // z[16*n1 + j] = (xw[32*n1 + 2j], xw[32*n1 + 2j + 1]); samples >= 400 are zero padding
 #pragma unroll
@@ -315,13 +330,13 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
             for (int k1 = 1; k1 < 16; ++k1) zf[k1 * 17 + j] = cmul(v[k1], tw[k1]);
         }
         __syncwarp();
-        if (active) {
+        {
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) v[n2] = zf[j * 17 + n2];    // thread j := k1
             fft16(v);                                                  // over n2 -> k2 ; v[k2] = Z[j + 16*k2]
         }
         __syncwarp();
-        if (active) {
+        {
             // conjugate partners: Z[256 - (j + 16 i)] = Z[(16 - j) + 16 (15 - i)] sits in the upper half (k2 >= 8) of
             // thread 16 - j; slot (k2 - 8) * 16 + j, so the partner of (j, i) is slot (8 - i) * 16 - j (slot 128 = Z[0])
 #pragma unroll
@@ -329,7 +344,7 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
             if (j == 0) zf[128] = v[0];
         }
         __syncwarp();
-        if (active) {
+        {
             // real-FFT untangle, two bins per pair: 2Xe = a + conj(c), 2 w^k Xo = T,  4|X[k]|^2 = |2Xe + T|^2,
             // 4|X[256-k]|^2 = |2Xe - T|^2   (a = Z[k], c = Z[256-k], k = j + 16 i)
 #pragma unroll
@@ -356,18 +371,19 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
                 const float* p = pw + mstart[i];
                 float acc = 0.f;
                 for (int k = 0; k < mlen[i]; ++k) acc = fmaf(p[k], sm.mel_wt[k][m], acc);
-                out_row[fr * kNumMel + m] = __logf(fmaxf(0.25f * acc, kEpsilon));
+                put(fr * kNumMel + m, __logf(fmaxf(0.25f * acc, kEpsilon)));
             }
         } else if (fr < T_out) {
 #pragma unroll
-            for (int i = 0; i < kNumMel / 16; ++i) out_row[fr * kNumMel + j + 16 * i] = kLogEpsilon;
+            for (int i = 0; i < kNumMel / 16; ++i) put(fr * kNumMel + j + 16 * i, kLogEpsilon);
         }
         __syncwarp();
     }
 }
 
-int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, int64_t T_out,
-                 double* row_sums, int device, cudaStream_t stream) {
+// exactly one of feats (fp32) / (feats_hi, feats_lo) (fp16 planes) is written
+int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
+                 __half* feats_lo, int64_t T_out, double* row_sums, int device, cudaStream_t stream) {
     const FbankTables* tab = fbank_tables(device);
     if (!tab) {
         set_error("fbank: b200vad_init(%d) has not been called", device);
@@ -376,7 +392,8 @@ int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_
     if (B == 0 || T_out == 0) return B200VAD_OK;
     static bool attr_set[64] = {false};
     if (!attr_set[device]) {
-        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
+        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
+        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
         attr_set[device] = true;
     }
     int rc = zero_f64_launch(row_sums, B, stream);
@@ -386,7 +403,8 @@ int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_
     B200VAD_LAUNCH_CHECK();
     dim3 g2((unsigned)((T_out + kTileFrames - 1) / kTileFrames), B);
     prof_begin(3, stream);
-    fbank_kernel<<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, T_out);
+    if (feats_hi) fbank_kernel<true><<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, nullptr, feats_hi, feats_lo, T_out);
+    else fbank_kernel<false><<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, nullptr, nullptr, T_out);
     prof_end(3, stream);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
