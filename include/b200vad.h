@@ -129,6 +129,12 @@ B200VAD_API int b200vad_score_intervals(const int32_t* gt_iv, int64_t n_gt, cons
                             const int64_t* word_off, const int32_t* nframes, int R, int64_t total_words, int max_words_per_rec,
                             void* workspace, int64_t* fa, int64_t* md, void* stream);
 
+/* ---- synthetic corpus (BASELINE config 4: 1000 h sharded across GPUs; there is no network for real corpora).
+ * wav (rows, N) f32 device <- utterances first_utt .. first_utt + rows - 1 of the corpus `seed`: 0.5 s segments of
+ * background noise or noise + a voiced burst, a pure function of (seed, utterance id, sample index), so any sharding
+ * or batching of the corpus sees identical audio. */
+B200VAD_API int b200vad_synth_corpus(float* wav, int64_t first_utt, int rows, int64_t N, uint64_t seed, void* stream);
+
 /* ---- long-form audio with OVERLAPPING windows (BASELINE config 3; the reference itself only cuts hop = window,
  * src/datasets/ami/utils.py:107, which needs no stitching): prob (num_windows, frames_per_window) f32, window w
  * starting at global frame w * hop_frames -> out (L) f32, every frame taken from the window whose centre is nearest. */

@@ -196,3 +196,25 @@ def test_detection_error_matches_reference_loop(dev):
     n = len(durations)
     der, fa, md = score_predictions(gts, preds, durations, fs)
     assert torch.equal(fa, fa_avg / n) and torch.equal(md, md_avg / n) and torch.equal(der, der_avg / n)
+
+
+# ---------------------------------------------------------------- corpus sharding (BASELINE config 4)
+def test_corpus_sharding_is_invisible(dev):
+    """Any sharding / batching of the synthetic corpus yields the same waveforms and the same global segment list."""
+    import b200vad
+    from b200vad import corpus
+    U, N = 300, 32000
+    a = corpus.synth_corpus(0, U, N, seed=7, device=dev)
+    b = torch.cat([corpus.synth_corpus(0, 100, N, 7, dev).clone(), corpus.synth_corpus(100, 200, N, 7, dev).clone()])
+    assert torch.equal(a, b) and torch.isfinite(a).all() and 0.005 < float(a.std()) < 0.2
+    assert not torch.equal(a[0], a[1]) and not torch.equal(a, corpus.synth_corpus(0, U, N, seed=8, device=dev))
+    feats = torch.ops.b200vad.fbank(a[:16], None).cpu()
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=feats)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    whole, frames = corpus.run_corpus(blob, U, N, batch_rows=128, seed=7)
+    assert frames == U * 200 and whole.shape[0] > 0
+    for world in (2, 3, 8):
+        parts = [corpus.run_corpus(blob, U, N, rank=r, world=world, batch_rows=64, seed=7, gather=False)[0] for r in range(world)]
+        assert torch.equal(torch.cat(parts), whole), world
+    ids = whole[:, 0].cpu()
+    assert bool((ids[1:] >= ids[:-1]).all()) and int(ids.max()) < U

@@ -12,6 +12,7 @@ from .packing import pack_model, pack_sincnet  # noqa: F401
 from .runtime import HostSession, gather_segments, shard_range  # noqa: F401
 from . import synth  # noqa: F401
 from . import score  # noqa: F401
+from . import corpus  # noqa: F401
 from .longform import LongFormVad  # noqa: F401
 from .streaming import StreamingVad  # noqa: F401
 

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "b200vad_score_workspace_bytes": (c_size_t, [c_int64]),
     "b200vad_score_intervals": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
+    "b200vad_synth_corpus": (c_int, [c_void_p, c_int64, c_int, c_int64, C.c_uint64, c_void_p]),
     "b200vad_stitch_center": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "b200vad_stream_create": (c_int, [c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, C.POINTER(c_void_p)]),
     "b200vad_stream_push": (c_int, [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, C.POINTER(c_float)]),

@@ -576,6 +576,13 @@ int b200vad_score_intervals(const int32_t* gt_iv, int64_t n_gt, const int32_t* p
                                   reinterpret_cast<uint32_t*>(workspace), fa, md, max_words_per_rec, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- synthetic corpus (BASELINE config 4)
+int b200vad_synth_corpus(float* wav, int64_t first_utt, int rows, int64_t N, uint64_t seed, void* stream) {
+    B200VAD_CHECK_ARG(rows >= 0 && rows <= 65535 && N >= 0 && first_utt >= 0, "bad shape");
+    B200VAD_CHECK_ARG(wav || rows == 0 || N == 0, "null pointer");
+    return synth_corpus_launch(wav, first_utt, rows, N, seed, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- long-form stitching (BASELINE config 3)
 int b200vad_stitch_center(const float* prob, int num_windows, int frames_per_window, int hop_frames, float* out, int64_t L,
                           void* stream) {

@@ -58,5 +58,6 @@ int stitch_center_launch(const float* prob, int W, int Tw, int hop, float* out, 
 int stream_append_launch(float* ring, const float* chunk, float* lin, int S, int Wn, int hop, int pos, cudaStream_t st);
 int stream_newest_launch(const float* prob, const uint8_t* dec, int S, int64_t T, int nf, float* prob_out, uint8_t* dec_out,
                          cudaStream_t st);
+int synth_corpus_launch(float* out, int64_t utt0, int rows, int64_t N, uint64_t seed, cudaStream_t st);
 
 }  // namespace b200vad
