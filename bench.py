@@ -48,9 +48,9 @@ KERNELS = {
         # per layer (1-3): x planes read 256 x 4 B + xg written 1024 x 4 B; layer 0 reads 80 x 4 B
         "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
         "executed_over_algorithmic": 3.0, "traffic": None},
-    2: {"name": "gemm_ts_kernel<1,2> (head linears, 2 launches/step)", "bound": "hbm", "tensor": True,
-        # y planes 1024 B -> z1 planes 512 B -> z2 fp32 512 B
-        "bytes_per_frame": (1024 + 512 + 512 + 512) / 2.0, "flop_per_frame": 2 * (256 * 128 + 128 * 128) / 2.0,
+    2: {"name": "gemm_ts_kernel<1,4> (head linears + classifier, 2 launches/step)", "bound": "hbm", "tensor": True,
+        # y planes 1024 B read -> z1 planes 512 B written, read again -> 4 B probability (classifier fused)
+        "bytes_per_frame": (1024 + 512 + 512 + 4) / 2.0, "flop_per_frame": 2 * (256 * 128 + 128 * 128) / 2.0,
         "executed_over_algorithmic": 3.0, "traffic": None},
     3: {"name": "fbank_kernel (frame/window/FFT/mel/log, 1 launch/step)", "bound": "hbm", "tensor": False,
         "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": None},

@@ -209,19 +209,18 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
             a_hi = yh; a_lo = yl; lda = 2 * kHidden;
             outbuf = (outbuf == buf0) ? buf1 : buf0;
         }
-        // head (PyanNet2.py:183-187) on the same GEMM: planes -> lrelu -> planes -> lrelu -> fp32 -> classifier.
-        // z1 planes and z2 live in the xg buffer (free after the last recurrence).
+        // head (PyanNet2.py:183-187) on the same GEMM: planes -> lrelu -> planes -> lrelu -> classifier -> sigmoid;
+        // the classifier + sigmoid are the epilogue of the second GEMM; the z1 planes live in the xg buffer (free after
+        // the last recurrence).
         __half* z1_hi = reinterpret_cast<__half*>(xg);
         __half* z1_lo = z1_hi + rows * kHidden;
-        float* z2 = reinterpret_cast<float*>(z1_lo + rows * kHidden);
         if ((rc = gemm_ts_launch(a_hi, a_lo, 2 * kHidden, rows, 2 * kHidden, reinterpret_cast<const __half*>(pk + m.w1_hi),
                                  reinterpret_cast<const __half*>(pk + m.w1_lo), 2 * kHidden, 2 * kHidden, kHidden,
                                  reinterpret_cast<const float*>(pk + m.b1), 1, 0, nullptr, z1_hi, z1_lo, kHidden, sms, st))) return rc;
         if ((rc = gemm_ts_launch(z1_hi, z1_lo, kHidden, rows, kHidden, reinterpret_cast<const __half*>(pk + m.w2_hi),
                                  reinterpret_cast<const __half*>(pk + m.w2_lo), kHidden, kHidden, kHidden,
-                                 reinterpret_cast<const float*>(pk + m.b2), 2, 0, z2, nullptr, nullptr, kHidden, sms, st))) return rc;
-        if ((rc = classifier_launch(z2, rows, reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc),
-                                    prob + b0 * T, st))) return rc;
+                                 reinterpret_cast<const float*>(pk + m.b2), 4, 0, prob + b0 * T, nullptr, nullptr, 1, sms, st,
+                                 reinterpret_cast<const float*>(pk + m.wc), reinterpret_cast<const float*>(pk + m.bc)))) return rc;
     }
     return B200VAD_OK;
 }

@@ -45,6 +45,8 @@ struct GemmTsParams {
     int ldw;                 // weight row pitch in elements (>= Kp)
     int accumulate;          // modes 0, 3: add to the existing C (K split over several launches); bias is then ignored
     int T, tiles_per_blk;    // mode 3: rows are (sequence, step) pairs; a tile = 64 sequences x 2 steps
+    const float* wc;         // mode 4: classifier weight [128] and bias [1]; c = prob [M]
+    const float* bc;
     int n_blocks;            // N / 128
     int kb;                  // k-blocks of 64
     int nw;                  // weight planes: 1 (hi) or 2 (hi, lo)
@@ -53,6 +55,9 @@ struct GemmTsParams {
 };
 
 // MODE 0: C = acc + bias (fp32)      MODE 1: leaky_relu(acc + bias) -> fp16 (hi, lo) planes      MODE 2: leaky_relu -> fp32
+// MODE 4: leaky_relu, then the classifier of PyanNet2.py:187 fused into the epilogue: prob[row] = sigmoid(wc . z + bc)
+//   (N must be 128: one CTA owns all features of a row; the dot product is a register transpose-reduction over the
+//   32 lanes of a warp plus a 4-warp exchange through shared memory).
 // MODE 3: LSTM input projection in the recurrence's step-blocked layout.  Activations are a (B, T, K) tensor; a
 //   tile is 64 sequences x 2 steps (tile row j = sequence * 2 + step, fetched as one 3-D TMA box), and
 //   C = xg[sequence block][direction][t][gate][column group 16][unit 128][4 columns] fp32, feature = (direction,
@@ -71,6 +76,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     auto bar_acc_empty = [&](int b) { return bar_base + 144 + 8 * b; };
     const uint32_t bar_w = bar_base + 160;
     const uint32_t tmem_slot = bar_base + 168;
+    const uint32_t part_smem = bar_base + 192;                                // mode 4: [2][4 warps][32 rows] fp32 partial dots
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blk = blockIdx.x % p.n_blocks;
@@ -219,6 +225,41 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 if (c == SBM / 32 - 1) {
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(ab));                             // 128 arrivals release the accumulator
+                }
+                if (MODE == 4) {
+                    // v[j] <- wc[unit] * leaky_relu(z2[unit][row j]); then sum over the 128 units of every row
+                    const float w = __ldg(p.wc + out);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = v[j] + bias;
+                        v[j] = w * (x > 0.f ? x : 0.01f * x);
+                    }
+                    // transpose-reduction: after the step with offset o a lane keeps the rows whose bit o equals its own
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float keep = up ? v[i + o] : v[i];
+                            const float send = up ? v[i] : v[i + o];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    // v[0] = this warp's 32-unit partial for row c * 32 + lane; combine the 4 warps through smem
+                    const int pb = (it * (SBM / 32) + c) & 1;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(part_smem + 4 * ((pb * 4 + q) * 32 + lane)), "f"(v[0]) : "memory");
+                    named_bar_sync(1, 128);
+                    if (q == 0) {
+                        float s = __ldg(p.bc);
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            float pv;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pv) : "r"(part_smem + 4 * ((pb * 4 + w4) * 32 + lane)));
+                            s += pv;
+                        }
+                        if (c * 32 + lane < nrows) p.c[row0 + c * 32 + lane] = 1.f / (1.f + __expf(-s));
+                    }
+                    continue;
                 }
                 // lane = output feature, register j = row: every store instruction writes one contiguous run per warp
                 const int64_t base = (row0 + c * 32) * p.ldc + out;
@@ -372,14 +413,14 @@ static int gemm_ts_run(int mode, const CUtensorMap& tm_a_hi, const CUtensorMap& 
                        cudaStream_t st) {
     p.n_blocks = N / 128;
     p.stages = 6;
-    const int smem = 1024 + p.stages * 2 * S_TILE_BYTES + 256;
+    const int smem = 1024 + p.stages * 2 * S_TILE_BYTES + 192 + 1024 + 64;
     int grid = (num_sms / p.n_blocks) * p.n_blocks;
     if (grid < p.n_blocks) grid = p.n_blocks;
     const int64_t max_grid = (int64_t)p.num_m_tiles * p.n_blocks;
     if (grid > max_grid) grid = (int)max_grid;
     typedef void (*KernFn)(CUtensorMap, CUtensorMap, GemmTsParams);
-    static const KernFn kerns[4] = {gemm_ts_kernel<0>, gemm_ts_kernel<1>, gemm_ts_kernel<2>, gemm_ts_kernel<3>};
-    static bool attr[4] = {false, false, false, false};
+    static const KernFn kerns[5] = {gemm_ts_kernel<0>, gemm_ts_kernel<1>, gemm_ts_kernel<2>, gemm_ts_kernel<3>, gemm_ts_kernel<4>};
+    static bool attr[5] = {false, false, false, false, false};
     if (!attr[mode]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[mode] = true; }
     const int prof_kind = (mode == 0 || mode == 3) ? 1 : 2;
     prof_begin(prof_kind, st);
@@ -400,16 +441,20 @@ static int gemm_ts_check(int K, int Kp, int ldw, int N, int64_t lda, int nw) {
 // a_hi/a_lo: [M, K] fp16 (row pitch lda elements, lda % 8 == 0);  w_hi/w_lo: [N, ldw] fp16, columns [K, Kp) zero (Kp % 64 == 0);
 // N must be a multiple of 128 and planes * Kp <= 512 (weights resident in 256 TMEM columns).  w_lo may be null.
 // mode 0: c[M, ldc] fp32 = acc + bias (accumulate: c += acc);  mode 1: leaky_relu -> fp16 planes o_hi / o_lo [M, ldc];
-// mode 2: leaky_relu -> c fp32.
+// mode 2: leaky_relu -> c fp32;  mode 4 (N == 128): leaky_relu -> sigmoid(wc . z + bc) -> c = prob [M].
 int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
                    int Kp, int ldw, int N, const float* bias, int mode, int accumulate, float* c, __half* o_hi, __half* o_lo,
-                   int64_t ldc, int num_sms, cudaStream_t st) {
+                   int64_t ldc, int num_sms, cudaStream_t st, const float* wc, const float* bc) {
     if (M <= 0) return B200VAD_OK;
     const int nw = w_lo ? 2 : 1;
     int rc = gemm_ts_check(K, Kp, ldw, N, lda, nw);
     if (rc) return rc;
-    if (mode < 0 || mode > 2) { set_error("gemm_ts: bad mode %d", mode); return B200VAD_EINVAL; }
+    if (!(mode == 0 || mode == 1 || mode == 2 || (mode == 4 && N == 128 && wc && bc))) {
+        set_error("gemm_ts: bad mode %d (mode 4 needs N == 128 and the classifier weights)", mode);
+        return B200VAD_EINVAL;
+    }
     GemmTsParams p = {};
+    p.wc = wc; p.bc = bc;
     p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = c; p.o_hi = o_hi; p.o_lo = o_lo; p.ldc = ldc; p.M = M;
     p.num_m_tiles = (int)((M + SBM - 1) / SBM);
     p.kb = Kp / SBK; p.nw = nw; p.Kp = Kp; p.ldw = ldw; p.accumulate = accumulate;

@@ -29,7 +29,7 @@ int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, i
 int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
 int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
                    int Kp, int ldw, int N, const float* bias, int mode, int accumulate, float* c, __half* o_hi, __half* o_lo,
-                   int64_t ldc, int num_sms, cudaStream_t st);
+                   int64_t ldc, int num_sms, cudaStream_t st, const float* wc = nullptr, const float* bc = nullptr);
 int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
                       const __half* w_lo, int Kp, int ldw, const float* bias, int accumulate, float* xg, int num_sms,
                       cudaStream_t st);
