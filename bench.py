@@ -38,22 +38,22 @@ N_SAMPLES = int(SECONDS * 16000)
 T_FRAMES = (N_SAMPLES + 80) // 160
 # Per-kernel algorithmic work per FRAME (10 ms of one utterance; 3 276 800 frames per launch at 4096 x 8 s), DESIGN.md
 # section 4.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture
-# (profiles/r01_ncu_full_summary.md), null where no capture exists.  `executed_over_algorithmic`: the split-precision
+# (profiles/r01_ncu_full_summary.md; average over the launches of a kind), bytes per launch at 4096 x 8 s.  `executed_over_algorithmic`: the split-precision
 # products execute 3 (GEMM) / 2 (recurrence: h_hi, h_lo) fp16 MMAs per algorithmic one.
 KERNELS = {
     0: {"name": "lstm_tc_kernel (LSTM recurrence, 4 launches/step)", "bound": "hbm", "tensor": True,
         # per layer: xg read 2 x 512 x 4 B + y planes written 2 x 128 x (2 + 2) B
-        "bytes_per_frame": 4096 + 1024, "flop_per_frame": 2 * 2 * 512 * 128, "executed_over_algorithmic": 2.0, "traffic": None},
+        "bytes_per_frame": 4096 + 1024, "flop_per_frame": 2 * 2 * 512 * 128, "executed_over_algorithmic": 2.0, "traffic": 16.76e9},
     1: {"name": "gemm_ts_kernel<0> (input projections, 4 launches/step)", "bound": "tensor", "tensor": True,
         # per layer (1-3): x planes read 256 x 4 B + xg written 1024 x 4 B; layer 0 reads 80 x 4 B
         "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
-        "executed_over_algorithmic": 3.0, "traffic": None},
+        "executed_over_algorithmic": 3.0, "traffic": 18.1e9},
     2: {"name": "gemm_ts_kernel<1,4> (head linears + classifier, 2 launches/step)", "bound": "hbm", "tensor": True,
         # y planes 1024 B read -> z1 planes 512 B written, read again -> 4 B probability (classifier fused)
         "bytes_per_frame": (1024 + 512 + 512 + 4) / 2.0, "flop_per_frame": 2 * (256 * 128 + 128 * 128) / 2.0,
-        "executed_over_algorithmic": 3.0, "traffic": None},
+        "executed_over_algorithmic": 3.0, "traffic": 3.35e9},
     3: {"name": "fbank_kernel (frame/window/FFT/mel/log, 1 launch/step)", "bound": "hbm", "tensor": False,
-        "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": None},
+        "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": 3.12e9},
 }
 MODEL_FLOP_PER_FRAME = 2.884e6
 
