@@ -315,18 +315,18 @@ def main():
             ent["tflops"] = tfs
             ent["tensor_frac"] = tfs * spec["executed_over_algorithmic"] / peaks["tf_sustained"] if spec["tensor"] else None
             ent["bound"] = spec["bound"]
-            ent["traffic"] = spec["traffic"]
+            ent["traffic"] = spec["traffic"] if rows == ROWS else None      # captured at the named workload only
             kernels[spec["name"]] = ent
         dom = max(prof, key=lambda k: prof[k][0])
         dspec, (tms, n) = KERNELS[dom], prof[dom]
         dent = kernels[dspec["name"]]
         if dspec["bound"] == "hbm":
             roof = {"kernel": dspec["name"], "bound": "hbm", "achieved": dent["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": dent["hbm_frac"], "traffic": dspec["traffic"],
+                    "frac": dent["hbm_frac"], "traffic": dent["traffic"],
                     "peak_source": f"{peaks['src']} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"}
         else:
             roof = {"kernel": dspec["name"], "bound": "tensor", "achieved": dent["tflops"], "peak": peaks["tf_sustained"],
-                    "unit": "TFLOP/s", "frac": dent["tflops"] / peaks["tf_sustained"], "traffic": dspec["traffic"],
+                    "unit": "TFLOP/s", "frac": dent["tflops"] / peaks["tf_sustained"], "traffic": dent["traffic"],
                     "executed_frac": dent["tensor_frac"],
                     "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); `achieved` counts ALGORITHMIC "
                                    "FLOPs, the split-precision product executes 3 fp16 MMAs per algorithmic one (executed_frac)"}

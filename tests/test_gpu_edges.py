@@ -1,0 +1,117 @@
+"""GPU edge cases of the path: empty and ragged inputs, degenerate decisions, block boundaries, determinism."""
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import b200vad
+    b200vad._lib.init(0)
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def blob(dev):
+    import b200vad
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80})
+    return o, b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+
+
+def test_empty_inputs_are_no_ops(dev, blob):
+    _, b = blob
+    assert torch.ops.b200vad.fbank(torch.empty(0, 16000, device=dev), None).shape == (0, 100, 80)
+    assert torch.ops.b200vad.fbank(torch.empty(3, 0, device=dev), None).shape == (3, 0, 80)
+    assert torch.ops.b200vad.lstm_head(torch.empty(0, 50, 80, device=dev), b, 4).shape == (0, 50)
+    assert torch.ops.b200vad.threshold_median(torch.empty(0, 10, device=dev), 0.5, 49, False).shape == (0, 10)
+    seg, counts = torch.ops.b200vad.segments(torch.empty(0, 10, dtype=torch.uint8, device=dev), None, 2)
+    assert seg.shape == (0, 3) and counts.numel() == 0
+    p, d, s, c = torch.ops.b200vad.vad_pipeline(torch.empty(0, 16000, device=dev), None, b, 4, 0.5, 49)
+    assert p.shape == (0, 100) and s.shape == (0, 3)
+    assert torch.ops.b200vad.stat_scores(torch.empty(0, dtype=torch.uint8, device=dev), torch.empty(0, dtype=torch.uint8, device=dev)).tolist() == [0, 0, 0, 0]
+
+
+def test_degenerate_decisions(dev):
+    import oracle
+    T = 300
+    for fill, want in ((0.0, []), (1.0, [(0, 0, T - 1)])):
+        prob = torch.full((2, T), fill, device=dev)
+        dec = torch.ops.b200vad.threshold_median(prob, 0.5, 49, False)
+        assert torch.equal(dec.cpu().long(), oracle.median_filter(prob.cpu(), window=0.01))
+        seg, counts = torch.ops.b200vad.segments(dec, None, 2)
+        assert seg.cpu().tolist() == [[r, a, b] for r in range(2) for _, a, b in want]
+    # NaN probabilities count as speech (torch.where(x < 0.5, 0, 1), helper.py:89); p == 0.5 is speech
+    prob = torch.tensor([[float("nan")] * 60 + [0.5] * 60 + [0.49999] * 60], device=dev)
+    dec = torch.ops.b200vad.threshold_median(prob, 0.5, 1, False)
+    assert dec[0, :120].all() and not dec[0, 120:].any()
+    # alternating single frames: every run has length 1 -> no segments (predict.py:481 `end - start > 0`)
+    alt = (torch.arange(200, device=dev) % 2).to(torch.uint8).view(1, -1)
+    seg, _ = torch.ops.b200vad.segments(alt, None, 2)
+    assert seg.shape[0] == 0
+    seg1, _ = torch.ops.b200vad.segments(alt, None, 1)
+    assert seg1.shape[0] == 100
+
+
+@pytest.mark.parametrize("B", [1, 63, 64, 65, 70, 129])
+def test_sequence_block_boundaries(dev, blob, B):
+    """xg is laid out in blocks of 64 sequences: partial and multiple blocks give the same rows as one at a time."""
+    o, b = blob
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, 40, 80, generator=g) * 3 - 5
+    with torch.no_grad():
+        ref = o(x).squeeze(-1)
+    p = torch.ops.b200vad.lstm_head(x.to(dev), b, 4).cpu()
+    assert util.prob_err(p, ref) <= util.PROB_RTOL
+    rows = [0, B // 2, B - 1]
+    single = torch.cat([torch.ops.b200vad.lstm_head(x[r:r + 1].to(dev), b, 4).cpu() for r in rows])
+    assert torch.equal(single, p[rows])                      # batch composition does not change a row's result
+
+
+def test_ragged_rows_through_the_pipeline(dev, blob):
+    import oracle
+    o, b = blob
+    wav = util.synth_wave(4, 48000, seed=9)
+    lens = torch.tensor([48000, 30001, 16000, 401])
+    p, d, seg, counts = torch.ops.b200vad.vad_pipeline(wav.to(dev), lens.to(dev), b, 4, 0.5, 49)
+    for r in range(4):
+        n = int(lens[r])
+        f = oracle.lhotse_fbank(wav[r:r + 1, :n])[0]
+        f = torch.cat([f, torch.full((300 - f.shape[0], 80), -23.025850929940457)])      # lhotse pads features with LOG_EPSILON
+        with torch.no_grad():
+            ref = o(f.unsqueeze(0)).squeeze()
+        assert util.prob_err(p[r].cpu(), ref) <= util.PROB_RTOL, r
+
+
+def test_repeated_runs_are_bit_identical(dev, blob):
+    _, b = blob
+    wav = util.synth_wave(66, 32000, seed=1).to(dev)
+    a = torch.ops.b200vad.vad_pipeline(wav, None, b, 4, 0.5, 49)
+    for _ in range(3):
+        c = torch.ops.b200vad.vad_pipeline(wav, None, b, 4, 0.5, 49)
+        assert all(torch.equal(x, y) for x, y in zip(a, c))
+
+
+def test_small_workspace_chunks_the_batch(dev, blob):
+    """The C call chunks the batch in 64-sequence blocks when the caller's workspace is small; results are unchanged."""
+    import ctypes as C
+    import b200vad
+    o, b = blob
+    L = b200vad.lib()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(200, 30, 80, generator=g) * 3 - 5).to(dev)
+    full = torch.ops.b200vad.lstm_head(x, b, 4)
+    ws = torch.empty(L.b200vad_model_workspace_bytes(64, 30), dtype=torch.uint8, device=dev)
+    prob = torch.empty(200, 30, device=dev)
+    b200vad._lib.check(L.b200vad_model_forward_f32(b.data_ptr(), 80, 4, x.data_ptr(), 200, 30, prob.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), torch.cuda.current_stream().cuda_stream), "forward")
+    torch.cuda.synchronize()
+    assert torch.equal(prob, full)
+    tiny = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+    rc = L.b200vad_model_forward_f32(b.data_ptr(), 80, 4, x.data_ptr(), 200, 30, prob.data_ptr(), tiny.data_ptr(), tiny.numel(),
+                                     torch.cuda.current_stream().cuda_stream)
+    assert rc == -3 and b"workspace too small" in L.b200vad_last_error()
