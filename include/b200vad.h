@@ -66,6 +66,10 @@ B200VAD_API int64_t b200vad_fbank_num_frames(int64_t num_samples);
  * LOG_EPSILON; row_sum_ws: (B) f64 scratch. */
 B200VAD_API int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride,
                       float* feats, int64_t T, double* row_sum_ws, void* stream);
+/* the same from 16-bit PCM: samples are converted as an audio loader does (int16 / 32768 -> float32, exact), so the
+ * features are identical to b200vad_fbank_f32 on the converted waveform; halves the waveform bytes */
+B200VAD_API int b200vad_fbank_i16(const int16_t* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride,
+                      float* feats, int64_t T, double* row_sum_ws, void* stream);
 
 /* ---- a2: PyanNet2.forward (src/models/segmentation/PyanNet2.py:154-187): nn.LSTM stack
  * (4 x BiLSTM(128) by default) + Linear/LeakyReLU x2 + Linear(1) + Sigmoid.
@@ -148,6 +152,10 @@ B200VAD_API int b200vad_pipeline_fbank_f32(const void* packed, int num_layers, c
                                uint8_t* dec /* (B,T) */, int32_t* counts, int64_t* seg_off, int32_t* seg, int64_t cap,
                                void* workspace, size_t ws_bytes, void* stream);
 
+B200VAD_API int b200vad_pipeline_fbank_i16(const void* packed, int num_layers, const int16_t* wav, const int32_t* lens, int B,
+                               int64_t N, int64_t wav_stride, float thr, int kernel, float* prob, uint8_t* dec, int32_t* counts,
+                               int64_t* seg_off, int32_t* seg, int64_t cap, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- host-buffer session: the same path with HOST waveforms and HOST results -- what a caller holding
  * lhotse/DataLoader batches in host memory uses (src/engines/vad_engine.py:204-211 fed by
  * src/datasets/data_module.py:194-206).  The session owns device buffers for two batches in flight and three
@@ -167,6 +175,9 @@ B200VAD_API int b200vad_session_run_host(b200vad_session* s, const float* wav_ho
                              float* prob_host, int32_t* seg_host, int64_t cap, int64_t* nseg);
 B200VAD_API int b200vad_session_submit_host(b200vad_session* s, int slot, const float* wav_host, int B, float thr, int kernel,
                                 uint8_t* dec_host, float* prob_host);
+/* 16-bit PCM host waveforms (B, N) i16: half the PCIe bytes of the fp32 form, identical results */
+B200VAD_API int b200vad_session_submit_host_i16(b200vad_session* s, int slot, const int16_t* wav_host, int B, float thr, int kernel,
+                                    uint8_t* dec_host, float* prob_host);
 B200VAD_API int b200vad_session_wait(b200vad_session* s, int slot, int32_t* seg_host, int64_t cap, int64_t* nseg);
 /* Device timeline of the slot's most recent batch, in ms since the session was created:
  * ms[0..4] = H2D begin, H2D end, compute begin, compute end, D2H end (CUDA events on the three streams). */

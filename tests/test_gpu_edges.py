@@ -115,3 +115,29 @@ def test_small_workspace_chunks_the_batch(dev, blob):
     rc = L.b200vad_model_forward_f32(b.data_ptr(), 80, 4, x.data_ptr(), 200, 30, prob.data_ptr(), tiny.data_ptr(), tiny.numel(),
                                      torch.cuda.current_stream().cuda_stream)
     assert rc == -3 and b"workspace too small" in L.b200vad_last_error()
+
+
+def test_pcm16_input_equals_converted_float(dev, blob):
+    """16-bit PCM waveforms give bit-identical results to the float32 waveform an audio loader would produce from them."""
+    import b200vad
+    import oracle
+    o, b = blob
+    g = torch.Generator().manual_seed(11)
+    pcm = torch.randint(-20000, 20000, (6, 40000), generator=g, dtype=torch.int16)
+    pcm[2, 100:9000] = 0
+    pcm[3, :] = 32767
+    pcm[4, ::2] = -32768
+    f32 = pcm.float() / 32768.0
+    fa = torch.ops.b200vad.fbank(pcm.to(dev), None)
+    fb = torch.ops.b200vad.fbank(f32.to(dev), None)
+    assert torch.equal(fa, fb)
+    assert util.feat_err(fa.cpu(), oracle.lhotse_fbank(f32)) <= util.FEAT_RTOL
+    lens = torch.tensor([40000, 12345, 40000, 801, 40000, 16000], dtype=torch.int32, device=dev)
+    ra = torch.ops.b200vad.vad_pipeline(pcm.to(dev), lens, b, 4, 0.5, 49)
+    rb = torch.ops.b200vad.vad_pipeline(f32.to(dev), lens, b, 4, 0.5, 49)
+    assert all(torch.equal(x, y) for x, y in zip(ra, rb))
+    sess = b200vad.HostSession(b, 4, 40000, chunk_rows=6)
+    out = sess.wait(0, sess.submit(0, pcm.pin_memory(), 0.5, 49, want_dec=True, want_prob=True))
+    p0, d0, s0, _ = torch.ops.b200vad.vad_pipeline(pcm.to(dev), None, b, 4, 0.5, 49)
+    assert torch.equal(out["prob"], p0.cpu()) and torch.equal(out["dec"], d0.cpu()) and torch.equal(out["seg"], s0.cpu())
+    sess.close()

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "b200vad_init": (c_int, [c_int]),
     "b200vad_fbank_num_frames": (c_int64, [c_int64]),
     "b200vad_fbank_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200vad_fbank_i16": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200vad_model_packed_bytes": (c_size_t, [c_int, c_int]),
     "b200vad_model_pack_lstm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200vad_model_pack_head": (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 6 + [c_void_p]),
@@ -56,6 +57,9 @@ PROTOTYPES = {
     "b200vad_pipeline_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "b200vad_pipeline_fbank_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_float, c_int,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "b200vad_pipeline_fbank_i16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_float, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "b200vad_session_submit_host_i16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
     "b200vad_session_create": (c_int, [c_int, c_void_p, c_int, c_int, c_int64, C.POINTER(c_void_p)]),
     "b200vad_session_run_host": (c_int, [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                          C.POINTER(c_int64)]),

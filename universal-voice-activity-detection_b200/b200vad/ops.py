@@ -35,12 +35,12 @@ def _prep(t: torch.Tensor, dtype, what: str) -> torch.Tensor:
 
 
 def _prep_rows(t: torch.Tensor, what: str) -> torch.Tensor:
-    """(B, N) float32 CUDA rows with unit inner stride; the row stride may be anything >= 1 (overlapping
+    """(B, N) float32 (or int16 PCM) CUDA rows with unit inner stride; the row stride may be anything >= 1 (overlapping
     long-form windows are passed as an as_strided view, no copy)."""
     if not t.is_cuda:
         raise _lib.B200VadError(f"{what} must be a CUDA tensor (there is no CPU implementation of this path)")
-    if t.dtype != torch.float32:
-        raise _lib.B200VadError(f"{what} must be torch.float32, got {t.dtype}")
+    if t.dtype not in (torch.float32, torch.int16):
+        raise _lib.B200VadError(f"{what} must be torch.float32 or torch.int16 (16-bit PCM), got {t.dtype}")
     if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= 1:
         return t
     return t.contiguous()
@@ -77,7 +77,8 @@ def fbank(wav: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tenso
         sums = torch.empty(B, dtype=torch.float64, device=wav.device)
         for b0 in range(0, B, 32768):
             b1 = min(B, b0 + 32768)
-            _lib.check(L.b200vad_fbank_f32(wav.data_ptr() + 4 * b0 * wav.stride(0), None if lens_ptr is None else lens[b0:b1].data_ptr(),
+            fn = L.b200vad_fbank_i16 if wav.dtype == torch.int16 else L.b200vad_fbank_f32
+            _lib.check(fn(wav.data_ptr() + wav.element_size() * b0 * wav.stride(0), None if lens_ptr is None else lens[b0:b1].data_ptr(),
                                            b1 - b0, N, wav.stride(0), feats[b0:b1].data_ptr(), T,
                                            sums[b0:b1].data_ptr(), _stream_ptr(wav.device)), "b200vad_fbank_f32")
     return feats
@@ -86,7 +87,7 @@ def fbank(wav: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tenso
 @fbank.register_fake
 def _(wav, lens=None):
     B, N = wav.shape
-    return wav.new_empty((B, (N + 80) // 160, 80))
+    return wav.new_empty((B, (N + 80) // 160, 80), dtype=torch.float32)
 
 
 # ------------------------------------------------------------------ LSTM stack + head
@@ -247,7 +248,8 @@ def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.
         minimum = L.b200vad_pipeline_workspace_bytes(B, N) - L.b200vad_model_workspace_bytes(B, T) + \
             L.b200vad_model_workspace_bytes(1, T)
         ws = _ws(min(need, max(_MAX_WS_BYTES, minimum)), dev)
-        _lib.check(L.b200vad_pipeline_fbank_f32(packed.data_ptr(), num_layers, wav.data_ptr(), lens_ptr, B, N, wav.stride(0),
+        fn = L.b200vad_pipeline_fbank_i16 if wav.dtype == torch.int16 else L.b200vad_pipeline_fbank_f32
+        _lib.check(fn(packed.data_ptr(), num_layers, wav.data_ptr(), lens_ptr, B, N, wav.stride(0),
                                                 float(thr), int(kernel), prob.data_ptr(), dec.data_ptr(), counts.data_ptr(),
                                                 seg_off.data_ptr(), seg.data_ptr(), cap, ws.data_ptr(), ws.numel(),
                                                 _stream_ptr(dev)), "b200vad_pipeline_fbank_f32")
@@ -261,7 +263,7 @@ def _(wav, lens, packed, num_layers, thr, kernel):
     n = ctx.new_dynamic_size()
     B, N = wav.shape
     T = (N + 80) // 160
-    return (wav.new_empty((B, T)), wav.new_empty((B, T), dtype=torch.uint8), wav.new_empty((n, 3), dtype=torch.int32),
+    return (wav.new_empty((B, T), dtype=torch.float32), wav.new_empty((B, T), dtype=torch.uint8), wav.new_empty((n, 3), dtype=torch.int32),
             wav.new_empty((B,), dtype=torch.int32))
 
 

@@ -60,10 +60,11 @@ class HostSession:
     # ---- asynchronous form: two batches in flight (slot 0 / 1); PCIe copies overlap the other slot's compute
     def submit(self, slot: int, wav: torch.Tensor, thr: float = 0.5, kernel: int = 49, want_dec: bool = True,
                want_prob: bool = False, out: Optional[dict] = None) -> dict:
-        """Enqueue one batch (B <= chunk_rows rows) into ``slot`` and return at once.  ``out`` (reused across
+        """Enqueue one batch (B <= chunk_rows rows; float32 or int16 PCM samples) into ``slot`` and return at once.  ``out`` (reused across
         calls) receives pinned ``dec`` / ``prob`` buffers that are valid after ``wait(slot, out)``."""
-        if wav.is_cuda or wav.dtype != torch.float32 or wav.dim() != 2 or wav.shape[1] != self.N or not wav.is_contiguous():
-            raise _lib.B200VadError("wav must be a contiguous CPU float32 tensor of shape (B, N)")
+        if wav.is_cuda or wav.dtype not in (torch.float32, torch.int16) or wav.dim() != 2 or wav.shape[1] != self.N \
+                or not wav.is_contiguous():
+            raise _lib.B200VadError("wav must be a contiguous CPU float32 (or int16 PCM) tensor of shape (B, N)")
         B = wav.shape[0]
         out = out if out is not None else {}
         if want_dec and ("dec" not in out or out["dec"].shape[0] != B):
@@ -74,7 +75,8 @@ class HostSession:
         if "seg_buf" not in out or out["seg_buf"].shape[0] < cap:
             out["seg_buf"] = torch.empty((max(cap, 1), 3), dtype=torch.int32).pin_memory()
         out["_wav"] = wav          # keep the source alive until wait()
-        _lib.check(_lib.lib().b200vad_session_submit_host(
+        fn = _lib.lib().b200vad_session_submit_host_i16 if wav.dtype == torch.int16 else _lib.lib().b200vad_session_submit_host
+        _lib.check(fn(
             self._h, int(slot), wav.data_ptr(), B, float(thr), int(kernel),
             out["dec"].data_ptr() if want_dec else None, out["prob"].data_ptr() if want_prob else None),
             "b200vad_session_submit_host")

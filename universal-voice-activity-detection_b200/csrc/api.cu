@@ -330,8 +330,8 @@ int b200vad_init(int device) {
 
 int64_t b200vad_fbank_num_frames(int64_t n) { return n < 0 ? 0 : (n + kFrameShift / 2) / kFrameShift; }
 
-int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride, float* feats, int64_t T,
-                      double* row_sum_ws, void* stream) {
+static int fbank_entry(const void* wav, int wav_i16, const int32_t* lens, int B, int64_t N, int64_t wav_stride, float* feats,
+                       int64_t T, double* row_sum_ws, void* stream) {
     B200VAD_CHECK_ARG(B >= 0 && N >= 0 && T >= 0, "negative size");
     if (B == 0 || T == 0) return B200VAD_OK;
     B200VAD_CHECK_ARG(wav && feats && row_sum_ws, "null pointer");
@@ -339,7 +339,15 @@ int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, i
     B200VAD_CHECK_ARG(B <= 65535, "B must be <= 65535 per call");
     int dev = 0;
     B200VAD_CUDA(cudaGetDevice(&dev));
-    return fbank_launch(wav, lens, B, N, wav_stride, feats, nullptr, nullptr, T, row_sum_ws, dev, (cudaStream_t)stream);
+    return fbank_launch(wav, wav_i16, lens, B, N, wav_stride, feats, nullptr, nullptr, T, row_sum_ws, dev, (cudaStream_t)stream);
+}
+int b200vad_fbank_f32(const float* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride, float* feats, int64_t T,
+                      double* row_sum_ws, void* stream) {
+    return fbank_entry(wav, 0, lens, B, N, wav_stride, feats, T, row_sum_ws, stream);
+}
+int b200vad_fbank_i16(const int16_t* wav, const int32_t* lens, int B, int64_t N, int64_t wav_stride, float* feats, int64_t T,
+                      double* row_sum_ws, void* stream) {
+    return fbank_entry(wav, 1, lens, B, N, wav_stride, feats, T, row_sum_ws, stream);
 }
 
 size_t b200vad_model_packed_bytes(int D, int L) {
@@ -602,7 +610,7 @@ size_t b200vad_pipeline_workspace_bytes(int B, int64_t N) {
     return pipeline_ws_bytes(B, N);
 }
 
-static int pipeline_run(const void* packed, int L, const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride,
+static int pipeline_run(const void* packed, int L, const void* wav, int wav_i16, const int32_t* lens, int B, int64_t N, int64_t stride,
                         float thr, int kernel, int row_base, float* prob, uint8_t* dec, int32_t* counts, int64_t* seg_off,
                         int32_t* seg, int64_t cap, void* ws, size_t ws_bytes, cudaStream_t st) {
     B200VAD_CHECK_ARG(packed && wav && prob && dec && counts && seg_off && ws, "null pointer");
@@ -623,7 +631,7 @@ static int pipeline_run(const void* packed, int L, const float* wav, const int32
     __half* f_hi = reinterpret_cast<__half*>(feats);
     __half* f_lo = f_hi + (size_t)B * T * kNumMel;
     const bool planes = g_impl == 2;
-    int rc = fbank_launch(wav, lens, B, N, stride, planes ? nullptr : feats, planes ? f_hi : nullptr, planes ? f_lo : nullptr, T,
+    int rc = fbank_launch(wav, wav_i16, lens, B, N, stride, planes ? nullptr : feats, planes ? f_hi : nullptr, planes ? f_lo : nullptr, T,
                           sums, dev, st);
     if (rc) return rc;
     rc = model_forward(packed, kNumMel, L, planes ? nullptr : feats, f_hi, f_lo, B, T, prob, w, ws_bytes - used, st);
@@ -637,7 +645,15 @@ int b200vad_pipeline_fbank_f32(const void* packed, int L, const float* wav, cons
                                int64_t stride, float thr, int kernel, float* prob, uint8_t* dec, int32_t* counts,
                                int64_t* seg_off, int32_t* seg, int64_t cap, void* ws, size_t ws_bytes, void* stream) {
     B200VAD_CHECK_ARG(B >= 0 && B <= 65535 && N >= 1 && stride >= 1, "bad shape");
-    return pipeline_run(packed, L, wav, lens, B, N, stride, thr, kernel, 0, prob, dec, counts, seg_off, seg, cap, ws, ws_bytes,
+    return pipeline_run(packed, L, wav, 0, lens, B, N, stride, thr, kernel, 0, prob, dec, counts, seg_off, seg, cap, ws, ws_bytes,
+                        (cudaStream_t)stream);
+}
+
+int b200vad_pipeline_fbank_i16(const void* packed, int L, const int16_t* wav, const int32_t* lens, int B, int64_t N,
+                               int64_t stride, float thr, int kernel, float* prob, uint8_t* dec, int32_t* counts,
+                               int64_t* seg_off, int32_t* seg, int64_t cap, void* ws, size_t ws_bytes, void* stream) {
+    B200VAD_CHECK_ARG(B >= 0 && B <= 65535 && N >= 1 && stride >= 1, "bad shape");
+    return pipeline_run(packed, L, wav, 1, lens, B, N, stride, thr, kernel, 0, prob, dec, counts, seg_off, seg, cap, ws, ws_bytes,
                         (cudaStream_t)stream);
 }
 
@@ -714,16 +730,17 @@ int b200vad_session_create(int device, const void* packed_device, int num_layers
     return B200VAD_OK;
 }
 
-static int session_submit(b200vad_session* s, int slot, const float* wav_host, int B, int row_base, float thr, int kernel,
+static int session_submit(b200vad_session* s, int slot, const void* wav_host, int wav_i16, int B, int row_base, float thr, int kernel,
                           uint8_t* dec_host, float* prob_host) {
     SessionSlot& sl = s->slot[slot];
     const int64_t N = s->N, T = s->T;
     B200VAD_CUDA(cudaEventRecord(sl.copy_begin, s->copy_stream));
-    B200VAD_CUDA(cudaMemcpyAsync(sl.wav_dev, wav_host, sizeof(float) * (size_t)B * N, cudaMemcpyHostToDevice, s->copy_stream));
+    B200VAD_CUDA(cudaMemcpyAsync(sl.wav_dev, wav_host, (wav_i16 ? sizeof(int16_t) : sizeof(float)) * (size_t)B * N,
+                                 cudaMemcpyHostToDevice, s->copy_stream));
     B200VAD_CUDA(cudaEventRecord(sl.copied, s->copy_stream));
     B200VAD_CUDA(cudaStreamWaitEvent(s->compute_stream, sl.copied, 0));
     B200VAD_CUDA(cudaEventRecord(sl.compute_begin, s->compute_stream));
-    int rc = pipeline_run(s->packed, s->L, sl.wav_dev, nullptr, B, N, N, thr, kernel, row_base, sl.prob_dev, sl.dec_dev,
+    int rc = pipeline_run(s->packed, s->L, sl.wav_dev, wav_i16, nullptr, B, N, N, thr, kernel, row_base, sl.prob_dev, sl.dec_dev,
                           sl.counts_dev, sl.seg_off_dev, sl.seg_dev, (int64_t)B * s->max_seg_per_row, s->ws, s->ws_bytes,
                           s->compute_stream);
     if (rc) return rc;
@@ -755,8 +772,8 @@ static int session_wait(b200vad_session* s, int slot, int32_t* seg_host, int64_t
     return B200VAD_OK;
 }
 
-int b200vad_session_submit_host(b200vad_session* s, int slot, const float* wav_host, int B, float thr, int kernel,
-                                uint8_t* dec_host, float* prob_host) {
+static int submit_entry(b200vad_session* s, int slot, const void* wav_host, int wav_i16, int B, float thr, int kernel,
+                        uint8_t* dec_host, float* prob_host) {
     B200VAD_CHECK_ARG(s && wav_host, "null pointer");
     B200VAD_CHECK_ARG(slot == 0 || slot == 1, "slot must be 0 or 1");
     B200VAD_CHECK_ARG(B >= 1 && B <= s->chunk, "B must be in [1, max_chunk_rows]");
@@ -765,7 +782,15 @@ int b200vad_session_submit_host(b200vad_session* s, int slot, const float* wav_h
         return B200VAD_ESTATE;
     }
     B200VAD_CUDA(cudaSetDevice(s->device));
-    return session_submit(s, slot, wav_host, B, 0, thr, kernel, dec_host, prob_host);
+    return session_submit(s, slot, wav_host, wav_i16, B, 0, thr, kernel, dec_host, prob_host);
+}
+int b200vad_session_submit_host(b200vad_session* s, int slot, const float* wav_host, int B, float thr, int kernel,
+                                uint8_t* dec_host, float* prob_host) {
+    return submit_entry(s, slot, wav_host, 0, B, thr, kernel, dec_host, prob_host);
+}
+int b200vad_session_submit_host_i16(b200vad_session* s, int slot, const int16_t* wav_host, int B, float thr, int kernel,
+                                    uint8_t* dec_host, float* prob_host) {
+    return submit_entry(s, slot, wav_host, 1, B, thr, kernel, dec_host, prob_host);
 }
 
 int b200vad_session_wait(b200vad_session* s, int slot, int32_t* seg_host, int64_t cap, int64_t* nseg) {
@@ -813,7 +838,7 @@ int b200vad_session_run_host(b200vad_session* s, const float* wav_host, int B, f
         const int b0 = c * s->chunk, bc = std::min(s->chunk, B - b0);
         int rc;
         if (c >= 2 && (rc = drain(c - 2))) return rc;
-        rc = session_submit(s, c & 1, wav_host + (size_t)b0 * N, bc, b0, thr, kernel,
+        rc = session_submit(s, c & 1, wav_host + (size_t)b0 * N, 0, bc, b0, thr, kernel,
                             dec_host ? dec_host + (size_t)b0 * T : nullptr, prob_host ? prob_host + (size_t)b0 * T : nullptr);
         if (rc) return rc;
     }
@@ -881,7 +906,7 @@ struct b200vad_stream {
 static int stream_forward(b200vad_stream* s) {
     __half* f_hi = reinterpret_cast<__half*>(s->feats);
     __half* f_lo = f_hi + (size_t)s->S * s->T * kNumMel;
-    int rc = fbank_launch(s->lin, nullptr, s->S, s->W, s->W, nullptr, f_hi, f_lo, s->T, s->sums, s->device, s->st);
+    int rc = fbank_launch(s->lin, 0, nullptr, s->S, s->W, s->W, nullptr, f_hi, f_lo, s->T, s->sums, s->device, s->st);
     if (rc) return rc;
     rc = model_forward(s->packed, kNumMel, s->L, nullptr, f_hi, f_lo, s->S, s->T, s->prob, s->ws, s->ws_bytes, s->st);
     if (rc) return rc;

@@ -119,31 +119,46 @@ int zero_f64_launch(double* p, int64_t n, cudaStream_t stream) {
     return B200VAD_OK;
 }
 
+// ---------------------------------------------------------------- waveform loads: fp32 samples or 16-bit PCM
+// PCM input is converted exactly as an audio loader does (int16 / 32768 -> float32), so both forms give identical
+// features; 16-bit input halves the waveform bytes read (and the H2D copy of the host session).
+__device__ __forceinline__ float ld1(const float* p, int64_t i) { return __ldg(p + i); }
+__device__ __forceinline__ float ld1(const int16_t* p, int64_t i) { return (float)__ldg(p + i) * (1.f / 32768.f); }
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i) { return __ldg(reinterpret_cast<const float4*>(p + i)); }
+__device__ __forceinline__ float4 ld4(const int16_t* p, int64_t i) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + i));
+    const short2 a = *reinterpret_cast<const short2*>(&u.x), b = *reinterpret_cast<const short2*>(&u.y);
+    const float k = 1.f / 32768.f;
+    return make_float4(a.x * k, a.y * k, b.x * k, b.y * k);
+}
+template <typename WT> __device__ __forceinline__ bool vec_aligned(const WT* p) {
+    return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(WT) - 1)) == 0;
+}
+
 // ---------------------------------------------------------------- row sums (DC offset)
 // grid (chunks, B): fp32 lane partials over <= 32 elements, then double.
-__global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens,
+template <typename WT>
+__global__ void __launch_bounds__(256) row_sum_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens,
                                                       int64_t N, int64_t stride, double* __restrict__ sums) {
     const int b = blockIdx.y;
     const int64_t n = lens ? min((int64_t)lens[b], N) : N;
-    const float* row = wav + (int64_t)b * stride;
+    const WT* row = wav + (int64_t)b * stride;
     const int64_t chunk = 256 * 32;
     int64_t begin = (int64_t)blockIdx.x * chunk;
     if (begin >= n) return;
     int64_t end = min(begin + chunk, n);
     double acc = 0.0;
-    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-    if (vec && end - begin == chunk) {
-        const float4* p = reinterpret_cast<const float4*>(row + begin);
+    if (vec_aligned(row) && end - begin == chunk) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float4 v = __ldg(p + threadIdx.x + i * 256);
+            float4 v = ld4(row, begin + 4 * (threadIdx.x + i * 256));
             s += (v.x + v.y) + (v.z + v.w);
         }
         acc = (double)s;
     } else {
         float s = 0.f;
-        for (int64_t i = begin + threadIdx.x; i < end; i += 256) s += row[i];
+        for (int64_t i = begin + threadIdx.x; i < end; i += 256) s += ld1(row, i);
         acc = (double)s;
     }
 #pragma unroll
@@ -219,9 +234,9 @@ __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
 // PLANES = false: feats (B, T, 80) fp32 (the lhotse layout).  PLANES = true: the same values as fp16 (hi, lo) planes
 // feats_hi / feats_lo (B, T, 80) -- the operand format of the layer-0 projection GEMM, so the fused pipeline skips the
 // fp32 feature round trip and the split kernel.
-template <bool PLANES>
+template <bool PLANES, typename WT>
 __global__ void __launch_bounds__(kFbankThreads, 4)
-fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, int64_t N, int64_t stride,
+fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64_t N, int64_t stride,
              const double* __restrict__ sums, const FbankTables* __restrict__ tab,
              float* __restrict__ feats, __half* __restrict__ feats_hi, __half* __restrict__ feats_lo, int64_t T_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -251,7 +266,7 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
         return;
     }
     const int nframes = (int)min((int64_t)kTileFrames, T - f0);
-    const float* row = wav + (int64_t)b * stride;
+    const WT* row = wav + (int64_t)b * stride;
     const float mean = (float)(sums[b] / (double)n);
     const int g = tid >> 4;         // group = frame slot
     const int j = tid & 15;         // lane within the group
@@ -275,14 +290,13 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     // ---- stage the pre-emphasised span
     const int64_t start = f0 * kFrameShift - kPadLeft;               // original index of span[0]
     const int span = (nframes - 1) * kFrameShift + kFrameLen;
-    const bool interior = (start >= 4) && (start + span <= n) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const bool interior = (start >= 4) && (start + span <= n) && vec_aligned(row);
     if (interior) {
-        // start is a multiple of 8 samples -> 16-byte aligned float4 loads
-        const float4* p = reinterpret_cast<const float4*>(row + start);
+        // start is a multiple of 8 samples -> aligned 4-sample vector loads
 #pragma unroll 4
         for (int i = tid; i < span / 4; i += kFbankThreads) {
-            float4 v = __ldg(p + i);
-            float prev = __ldg(row + start + 4 * i - 1);
+            float4 v = ld4(row, start + 4 * i);
+            float prev = ld1(row, start + 4 * i - 1);
             float4 o;
             o.x = preemph(v.x, prev, mean);
             o.y = preemph(v.y, v.x, mean);
@@ -296,8 +310,8 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
             if (i < 0) i = -1 - i;                 // left mirror (edge sample repeated)
             if (i >= n) i = 2 * n - 1 - i;         // right mirror
             i = max((int64_t)0, min(i, n - 1));
-            float x = row[i];
-            float xp = row[i > 0 ? i - 1 : 0];     // replicate-padded predecessor
+            float x = ld1(row, i);
+            float xp = ld1(row, i > 0 ? i - 1 : 0);     // replicate-padded predecessor
             sm.y[s] = preemph(x, xp, mean);
         }
     }
@@ -381,8 +395,31 @@ fbank_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, in
     }
 }
 
-// exactly one of feats (fp32) / (feats_hi, feats_lo) (fp16 planes) is written
-int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
+// exactly one of feats (fp32) / (feats_hi, feats_lo) (fp16 planes) is written; wav is fp32 or (wav_i16) 16-bit PCM
+template <typename WT>
+static int fbank_launch_t(const WT* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
+                          __half* feats_lo, int64_t T_out, double* row_sums, const FbankTables* tab, cudaStream_t stream) {
+    static bool attr_set = false;          // one flag per waveform type
+    if (!attr_set) {
+        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<false, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
+        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<true, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
+        attr_set = true;
+    }
+    int rc = zero_f64_launch(row_sums, B, stream);
+    if (rc) return rc;
+    dim3 g1((unsigned)((N + 256 * 32 - 1) / (256 * 32)), B);
+    row_sum_kernel<WT><<<g1, 256, 0, stream>>>(wav, lens, N, stride, row_sums);
+    B200VAD_LAUNCH_CHECK();
+    dim3 g2((unsigned)((T_out + kTileFrames - 1) / kTileFrames), B);
+    prof_begin(3, stream);
+    if (feats_hi) fbank_kernel<true, WT><<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, nullptr, feats_hi, feats_lo, T_out);
+    else fbank_kernel<false, WT><<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, nullptr, nullptr, T_out);
+    prof_end(3, stream);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+int fbank_launch(const void* wav, int wav_i16, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
                  __half* feats_lo, int64_t T_out, double* row_sums, int device, cudaStream_t stream) {
     const FbankTables* tab = fbank_tables(device);
     if (!tab) {
@@ -390,24 +427,9 @@ int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_
         return B200VAD_ESTATE;
     }
     if (B == 0 || T_out == 0) return B200VAD_OK;
-    static bool attr_set[64] = {false};
-    if (!attr_set[device]) {
-        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
-        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
-        attr_set[device] = true;
-    }
-    int rc = zero_f64_launch(row_sums, B, stream);
-    if (rc) return rc;
-    dim3 g1((unsigned)((N + 256 * 32 - 1) / (256 * 32)), B);
-    row_sum_kernel<<<g1, 256, 0, stream>>>(wav, lens, N, stride, row_sums);
-    B200VAD_LAUNCH_CHECK();
-    dim3 g2((unsigned)((T_out + kTileFrames - 1) / kTileFrames), B);
-    prof_begin(3, stream);
-    if (feats_hi) fbank_kernel<true><<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, nullptr, feats_hi, feats_lo, T_out);
-    else fbank_kernel<false><<<g2, kFbankThreads, sizeof(FbankSmem), stream>>>(wav, lens, N, stride, row_sums, tab, feats, nullptr, nullptr, T_out);
-    prof_end(3, stream);
-    B200VAD_LAUNCH_CHECK();
-    return B200VAD_OK;
+    if (wav_i16)
+        return fbank_launch_t(static_cast<const int16_t*>(wav), lens, B, N, stride, feats, feats_hi, feats_lo, T_out, row_sums, tab, stream);
+    return fbank_launch_t(static_cast<const float*>(wav), lens, B, N, stride, feats, feats_hi, feats_lo, T_out, row_sums, tab, stream);
 }
 
 }  // namespace b200vad

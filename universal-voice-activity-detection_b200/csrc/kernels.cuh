@@ -23,7 +23,7 @@ int gemm_launch(const GemmArgs& a, int a_half, int terms, cudaStream_t stream);
 int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, cudaStream_t stream, int gate_scale = 0);
 int fbank_tables_init(int device);
 int zero_f64_launch(double* p, int64_t n, cudaStream_t stream);
-int fbank_launch(const float* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
+int fbank_launch(const void* wav, int wav_i16, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
                  __half* feats_lo, int64_t T_out, double* row_sums, int device, cudaStream_t stream);
 int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, int T, cudaStream_t stream);
 int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
