@@ -198,6 +198,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the b200 path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = b200vad.bind_to_gpu_numa(local)      # pinned host buffers land on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
@@ -356,7 +357,7 @@ def main():
                        "frames_per_row": T_FRAMES, "parallelism": f"utterance-sharded x{world}",
                        "l2": f"inputs ({rows * N_SAMPLES * 4 / 1e9:.2f} GB waveforms + GBs of intermediates per step) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms,
+                    "ms_per_step": e2e_ms, "host_numa_node": numa,
                     "pcm16_input": {"value": hours_step_global / (pcm_ms / 1e3), "ms_per_step": pcm_ms, "h2d_bytes_per_step": h2d // 2,
                                     "note": "same API fed int16 PCM host waveforms (b200vad_session_submit_host_i16); informational"},
                     "api": "b200vad_session_submit_host / b200vad_session_wait, 2 steps in flight (pinned host waveforms -> host decisions + segments)"},

@@ -12,6 +12,32 @@ from . import _lib
 from .host import shard_range  # noqa: F401  (re-export)
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards: first touch) to the NUMA node
+    the GPU hangs off.  With one process per GPU on a multi-socket host this keeps every rank's H2D copies off the
+    inter-socket link.  Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001  (no sysfs / no permission: leave the affinity alone)
+        return None
+
+
 class HostSession:
     """waveforms on the HOST -> decisions / probabilities / segments on the HOST.
 
