@@ -30,12 +30,14 @@ constexpr int kGroups = kFbankThreads / 16;                           // 16 thre
 constexpr int kZStride = 17 * 16;                                     // padded 16x16 complex tile (float2 units)
 constexpr int kPowStride = 264;
 constexpr int kMaxMelWidth = 32;
+static const int kSlotTapsHost[kNumMel / 16] = {3, 4, 6, 10, 16};      // widest triangle per slot of 16 mel bins
 constexpr int kMelRows = 18;                                          // widest Kaldi triangle at 512/16 kHz spans 17 FFT bins
 
 struct FbankTables {
     float window[kFrameLen];
     float2 tw256[256];          // exp(-2*pi*i*m/256)
     float2 tw512[257];          // exp(-2*pi*i*k/512), k = 0..256
+    float2 tw16[16][16];        // stage twiddles W256^(j*k1) as [k1][j] (coalesced per half-warp)
     int mel_start[kNumMel];
     int mel_len[kNumMel];
     float mel_w[kNumMel][kMaxMelWidth];
@@ -55,6 +57,9 @@ static void build_tables(FbankTables& t) {
         t.window[n] = (float)pow(hann, 0.85);
     }
     for (int m = 0; m < 256; ++m) t.tw256[m] = make_float2((float)cos(2 * pi * m / 256), (float)-sin(2 * pi * m / 256));
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int jj = 0; jj < 16; ++jj)
+            t.tw16[k1][jj] = make_float2((float)cos(2 * pi * (jj * k1) / 256), (float)-sin(2 * pi * (jj * k1) / 256));
     for (int k = 0; k <= 256; ++k) t.tw512[k] = make_float2((float)cos(2 * pi * k / 512), (float)-sin(2 * pi * k / 512));
     // Kaldi mel triangles (torchaudio.compliance.kaldi.get_mel_banks, vtln off):
     // 80 bins, 20 Hz .. 7600 Hz, triangles in the mel domain, FFT bin width 31.25 Hz.
@@ -79,6 +84,7 @@ static void build_tables(FbankTables& t) {
         t.mel_len[b] = len;
         for (int j = len; j < kMaxMelWidth; ++j) t.mel_w[b][j] = 0.f;
         for (int j = 0; j < kMelRows; ++j) t.mel_wt[j][b] = (j < len) ? t.mel_w[b][j] : 0.f;
+        if (len > kSlotTapsHost[b / 16]) fprintf(stderr, "b200vad: mel triangle %d has %d taps, slot allows %d\n", b, len, kSlotTapsHost[b / 16]);
         if (len > kMelRows) fprintf(stderr, "b200vad: mel triangle %d wider than kMelRows (%d)\n", b, len);
     }
 }
@@ -216,14 +222,21 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 // CTA = 128 threads = 8 groups of 16 threads; a group owns one frame at a time and walks frames g, g+8, g+16, g+24 of
 // the 32-frame tile.  After the span is staged there is no CTA barrier: every hand-off (FFT transpose, conjugate
 // partners, power spectrum -> mel) stays inside the group's half-warp and needs only __syncwarp.
-// Per-thread constants (stage twiddles W256^(j k1), untangle twiddles W512^(j+16i), mel bin ranges) live in registers.
+// Registers are the occupancy limit (5 CTAs = 20 warps per SM at <= 102 registers): the per-thread constants (stage
+// twiddles W256^(j k1), untangle twiddles W512^(j+16i), window) are re-read through L1 from 2 KB tables laid out so
+// that a half-warp reads one contiguous run, the power spectrum aliases the transpose scratch, and the mel triangles
+// use fixed per-slot tap counts (no data-dependent branches).
 struct FbankSmem {
     float y[kSpan];                                  // pre-emphasised samples of the tile
-    float2 z[kGroups * kZStride];                    // per-group FFT transpose / partner scratch
-    float pw[kGroups * kPowStride];                  // per-group power spectrum (x4) of the frame in flight
-    float window[kFrameLen];
+    float2 z[kGroups * kZStride];                    // per-group FFT transpose / partner scratch; the power spectrum (x4) of
+                                                     // the frame in flight aliases its upper half (float2 slots 136..267)
     float mel_wt[kMelRows][kNumMel];
 };
+constexpr int kPwOff = 136;                          // first float2 slot of the aliased power spectrum (partners use 0..128)
+static_assert(kPwOff * 2 + kPowStride <= kZStride * 2, "power spectrum must fit behind the partner slots");
+// widest mel triangle per slot of 16 bins (bins 16 i .. 16 i + 15): fixed, branch-free trip counts; narrower triangles
+// read zero weights (the table is zero padded).  Checked against the table at init.
+__device__ constexpr int kSlotTaps[kNumMel / 16] = {3, 4, 6, 10, 16};
 
 __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
     // (x - mu) - 0.97 * (xprev - mu), with the reference's separate roundings
@@ -235,7 +248,7 @@ __device__ __forceinline__ float preemph(float x, float xprev, float mean) {
 // feats_hi / feats_lo (B, T, 80) -- the operand format of the layer-0 projection GEMM, so the fused pipeline skips the
 // fp32 feature round trip and the split kernel.
 template <bool PLANES, typename WT>
-__global__ void __launch_bounds__(kFbankThreads, 4)
+__global__ void __launch_bounds__(kFbankThreads, 5)
 fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64_t N, int64_t stride,
              const double* __restrict__ sums, const FbankTables* __restrict__ tab,
              float* __restrict__ feats, __half* __restrict__ feats_hi, __half* __restrict__ feats_lo, int64_t T_out) {
@@ -272,20 +285,15 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
     const int j = tid & 15;         // lane within the group
 
     // ---- per-thread constants (registers) and per-CTA tables (smem)
-    float2 tw[16];                  // W256^(j*k1), k1 = 1..15
+    const float2* const tw = &tab->tw16[0][0] + j;   // W256^(j*k1) at tw[16 * k1], through L1
+    const float2* const tq = tab->tw512 + j;      // W512^(j + 16 i): read through L1 (2 KB table, hot)
+    const float* const win = tab->window + 2 * j; // povey window, likewise
+    int mstart[kNumMel / 16];
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) tw[k1] = __ldg(&tab->tw256[(j * k1) & 255]);
-    float2 tq[8];                   // W512^(j + 16 i)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tq[i] = __ldg(&tab->tw512[j + 16 * i]);
-    int mstart[kNumMel / 16], mlen[kNumMel / 16];
-#pragma unroll
-    for (int i = 0; i < kNumMel / 16; ++i) {
-        mstart[i] = __ldg(&tab->mel_start[j + 16 * i]);
-        mlen[i] = __ldg(&tab->mel_len[j + 16 * i]);
-    }
-    for (int i = tid; i < kFrameLen; i += kFbankThreads) sm.window[i] = tab->window[i];
+    for (int i = 0; i < kNumMel / 16; ++i) mstart[i] = __ldg(&tab->mel_start[j + 16 * i]);
     for (int i = tid; i < kMelRows * kNumMel; i += kFbankThreads) (&sm.mel_wt[0][0])[i] = (&tab->mel_wt[0][0])[i];
+    // zero the padding behind every group's power spectrum once (fixed-length mel taps may read it with zero weights)
+    if (tid < kGroups * 8) reinterpret_cast<float*>(sm.z + (tid >> 3) * kZStride + kPwOff)[257 + (tid & 7)] = 0.f;
 
     // ---- stage the pre-emphasised span
     const int64_t start = f0 * kFrameShift - kPadLeft;               // original index of span[0]
@@ -318,7 +326,7 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
     __syncthreads();
 
     float2* zf = sm.z + g * kZStride;
-    float* pw = sm.pw + g * kPowStride;
+    float* pw = reinterpret_cast<float*>(zf + kPwOff);
     for (int pass = 0; pass < kTileFrames / kGroups; ++pass) {
         const int f = pass * kGroups + g;
         const bool active = f < nframes;
@@ -332,7 +340,7 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
                 const int s = 32 * n1 + 2 * j;
                 if (n1 < 12 || (n1 == 12 && j < 8)) {
                     float2 yy = *reinterpret_cast<const float2*>(ys + s);
-                    float2 ww = *reinterpret_cast<const float2*>(sm.window + s);
+                    float2 ww = __ldg(reinterpret_cast<const float2*>(win + 32 * n1));
                     v[n1] = make_float2(yy.x * ww.x, yy.y * ww.y);
                 } else {
                     v[n1] = make_float2(0.f, 0.f);
@@ -341,7 +349,7 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
             fft16(v);                                                  // over n1 -> k1
             zf[j] = v[0];
 #pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) zf[k1 * 17 + j] = cmul(v[k1], tw[k1]);
+            for (int k1 = 1; k1 < 16; ++k1) zf[k1 * 17 + j] = cmul(v[k1], __ldg(tw + 16 * k1));
         }
         __syncwarp();
         {
@@ -367,8 +375,9 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
                 const float2 c = zf[(8 - i) * 16 - j];
                 const float sr = a.x + c.x, si = a.y - c.y;
                 const float dr = a.x - c.x, di = a.y + c.y;
-                const float tr = tq[i].x * di + tq[i].y * dr;
-                const float ti = tq[i].y * di - tq[i].x * dr;
+                const float2 w = __ldg(tq + 16 * i);
+                const float tr = w.x * di + w.y * dr;
+                const float ti = w.y * di - w.x * dr;
                 const float pr = sr + tr, pi = si + ti, qr = sr - tr, qi = si - ti;
                 pw[j + 16 * i] = pr * pr + pi * pi;
                 pw[256 - j - 16 * i] = qr * qr + qi * qi;
@@ -384,7 +393,8 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
                 const int m = j + 16 * i;
                 const float* p = pw + mstart[i];
                 float acc = 0.f;
-                for (int k = 0; k < mlen[i]; ++k) acc = fmaf(p[k], sm.mel_wt[k][m], acc);
+#pragma unroll
+                for (int k = 0; k < kSlotTaps[i]; ++k) acc = fmaf(p[k], sm.mel_wt[k][m], acc);
                 put(fr * kNumMel + m, __logf(fmaxf(0.25f * acc, kEpsilon)));
             }
         } else if (fr < T_out) {
