@@ -228,8 +228,10 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
 // ---------------------------------------------------------------- SincNet packed layout
 struct SincLayout {
     size_t filt, sinc_hi, sinc_lo, c1_f32, c1_hi, c1_lo, c1_b, c2_f32, c2_hi, c2_lo, c2_b, wn_w, wn_b, n0_w, n0_b, n1_w, n1_b,
-        n2_w, n2_b, total;
+        n2_w, n2_b, tmp_f32, sinc_t_hi, sinc_t_lo, c1_t_hi, c1_t_lo, c2_t_hi, c2_t_lo, total;
 };
+// tcgen05 path: weights zero padded to 128 output rows; conv2's 60 input channels are padded to 64 (16-byte rows)
+constexpr int kSincTLd = 256, kC1TLd = 448, kC2Cp = 64, kC2TLd = 5 * kC2Cp;
 constexpr int kSincK = 251, kSincKp = 256, kC1K = 400, kC1Kp = 416, kC2K = 300, kC2Kp = 320;
 static SincLayout sinc_layout() {
     SincLayout s;
@@ -250,6 +252,10 @@ static SincLayout sinc_layout() {
     s.n0_w = take(sizeof(float) * 80); s.n0_b = take(sizeof(float) * 80);
     s.n1_w = take(sizeof(float) * 60); s.n1_b = take(sizeof(float) * 60);
     s.n2_w = take(sizeof(float) * 60); s.n2_b = take(sizeof(float) * 60);
+    s.tmp_f32 = take(sizeof(float) * 128 * kC1TLd);
+    s.sinc_t_hi = take(sizeof(__half) * 128 * kSincTLd); s.sinc_t_lo = take(sizeof(__half) * 128 * kSincTLd);
+    s.c1_t_hi = take(sizeof(__half) * 128 * kC1TLd); s.c1_t_lo = take(sizeof(__half) * 128 * kC1TLd);
+    s.c2_t_hi = take(sizeof(__half) * 128 * kC2TLd); s.c2_t_lo = take(sizeof(__half) * 128 * kC2TLd);
     s.total = off;
     return s;
 }
@@ -266,12 +272,14 @@ static SincDims sinc_dims(int64_t N) {
     d.P3 = d.L3 / 3;
     return d;
 }
+static inline int64_t sinc_np(int64_t N) { return (N + 16 + 7) / 8 * 8; }     // padded length of a shifted waveform copy
 static size_t sinc_ws_per_row(int64_t N) {
     SincDims d = sinc_dims(N);
-    // normalised wave + conv1 out + pooled1 + conv2 out + pooled2 + conv3 out, stats
-    return align_up(sizeof(float) * N) + align_up(sizeof(float) * d.L1 * 80) + align_up(sizeof(float) * d.P1 * 80) +
-           align_up(sizeof(float) * d.L2 * 60) + align_up(sizeof(float) * d.P2 * 60) + align_up(sizeof(float) * d.L3 * 60) +
-           align_up(sizeof(double) * 2 * 80) + 2048;
+    // normalised wave (fp32, or 4 shifted fp16 hi/lo copies) + conv1 out + pooled1 (+ planes) + conv2 out + pooled2 (+ planes)
+    // + conv3 out, stats
+    return align_up(std::max<size_t>(sizeof(float) * N, 16 * (size_t)sinc_np(N))) + align_up(sizeof(float) * d.L1 * 80) +
+           2 * align_up(sizeof(float) * d.P1 * 80) + align_up(sizeof(float) * d.L2 * 60) + align_up(sizeof(float) * d.P2 * 60) +
+           align_up(sizeof(float) * d.P2 * kC2Cp) + align_up(sizeof(float) * d.L3 * 60) + align_up(sizeof(double) * 2 * 80) + 4096;
 }
 
 }  // namespace b200vad
@@ -456,6 +464,17 @@ int b200vad_sincnet_pack(void* packed, const float* wav_norm_w, const float* wav
     rc = split_weights(reinterpret_cast<float*>(pk + s.c2_f32), 60, kC2K, kC2Kp, reinterpret_cast<__half*>(pk + s.c2_hi),
                        reinterpret_cast<__half*>(pk + s.c2_lo), st);
     if (rc) return rc;
+    // tcgen05 path: (128, ld) zero-padded copies
+    float* tmp = reinterpret_cast<float*>(pk + s.tmp_f32);
+    if ((rc = pad_rows_launch(reinterpret_cast<float*>(pk + s.filt), 80, kSincK, kSincTLd, tmp, st))) return rc;
+    if ((rc = split_weights(tmp, 128, kSincTLd, kSincTLd, reinterpret_cast<__half*>(pk + s.sinc_t_hi),
+                            reinterpret_cast<__half*>(pk + s.sinc_t_lo), st))) return rc;
+    if ((rc = repack_conv_pad_launch(conv1_w, 60, 80, 5, 80, kC1TLd, tmp, st))) return rc;
+    if ((rc = split_weights(tmp, 128, kC1TLd, kC1TLd, reinterpret_cast<__half*>(pk + s.c1_t_hi),
+                            reinterpret_cast<__half*>(pk + s.c1_t_lo), st))) return rc;
+    if ((rc = repack_conv_pad_launch(conv2_w, 60, 60, 5, kC2Cp, kC2TLd, tmp, st))) return rc;
+    if ((rc = split_weights(tmp, 128, kC2TLd, kC2TLd, reinterpret_cast<__half*>(pk + s.c2_t_hi),
+                            reinterpret_cast<__half*>(pk + s.c2_t_lo), st))) return rc;
     struct { size_t off; const float* src; size_t n; } cp[] = {
         {s.c1_b, conv1_b, 60}, {s.c2_b, conv2_b, 60}, {s.wn_w, wav_norm_w, 1}, {s.wn_b, wav_norm_b, 1},
         {s.n0_w, norm0_w, 80}, {s.n0_b, norm0_b, 80}, {s.n1_w, norm1_w, 60}, {s.n1_b, norm1_b, 60},
@@ -492,15 +511,64 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
         const int bc = (int)std::min<int64_t>(Bc, B - b0);
         char* w = reinterpret_cast<char*>(workspace);
         auto take = [&](size_t bytes) { char* p = w; w += align_up(bytes); return p; };
-        float* wn = reinterpret_cast<float*>(take(sizeof(float) * N * bc));
+        const int64_t Np = sinc_np(N);
+        char* wn_raw = take(std::max<size_t>(sizeof(float) * N, 16 * (size_t)Np) * bc);
+        float* wn = reinterpret_cast<float*>(wn_raw);
         float* c1 = reinterpret_cast<float*>(take(sizeof(float) * d.L1 * 80 * bc));
         float* p1 = reinterpret_cast<float*>(take(sizeof(float) * d.P1 * 80 * bc));
+        __half* p1_hi = reinterpret_cast<__half*>(take(sizeof(float) * d.P1 * 80 * bc));
+        __half* p1_lo = p1_hi + d.P1 * 80 * bc;
         float* c2 = reinterpret_cast<float*>(take(sizeof(float) * d.L2 * 60 * bc));
         float* p2 = reinterpret_cast<float*>(take(sizeof(float) * d.P2 * 60 * bc));
+        __half* p2_hi = reinterpret_cast<__half*>(take(sizeof(float) * d.P2 * kC2Cp * bc));
+        __half* p2_lo = p2_hi + d.P2 * kC2Cp * bc;
         float* c3 = reinterpret_cast<float*>(take(sizeof(float) * d.L3 * 60 * bc));
         double* stats = reinterpret_cast<double*>(take(sizeof(double) * 2 * 80 * bc));
-        int rc = wave_instnorm_launch(wav + b0 * wav_stride, bc, N, wav_stride, reinterpret_cast<const float*>(pk + s.wn_w),
-                                      reinterpret_cast<const float*>(pk + s.wn_b), stats, wn, st);
+        int rc;
+        if (g_impl == 2) {
+            // ---- tcgen05 path: every convolution is an overlapping-row GEMM on gemm_ts (weights resident in TMEM)
+            const int sms = num_sms_cached();
+            __half* wn_hi = reinterpret_cast<__half*>(wn_raw);
+            __half* wn_lo = wn_hi + 4 * (int64_t)bc * Np;
+            if ((rc = wave_norm_planes_launch(wav + b0 * wav_stride, bc, N, wav_stride, Np, reinterpret_cast<const float*>(pk + s.wn_w),
+                                              reinterpret_cast<const float*>(pk + s.wn_b), stats, wn_hi, wn_lo, st))) return rc;
+            // sinc conv, stride 10: rows t = 4 m + r start at 40 m + 10 r -> copy shifted by (10 r) % 8, offset 8 * ((10 r) / 8)
+            for (int r = 0; r < 4; ++r) {
+                const int64_t rows_r = (d.L1 - r + 3) / 4;
+                if (rows_r <= 0) continue;
+                const int e = ((10 * r) % 8) / 2, q = ((10 * r) / 8) * 8;
+                if ((rc = gemm_ts_rows_launch(wn_hi + (int64_t)e * bc * Np + q, wn_lo + (int64_t)e * bc * Np + q, 40, Np, bc, (int)rows_r,
+                                              kSincTLd, reinterpret_cast<const __half*>(pk + s.sinc_t_hi),
+                                              reinterpret_cast<const __half*>(pk + s.sinc_t_lo), kSincTLd, kSincTLd, 80, nullptr, 0, 1,
+                                              c1, 80, d.L1, 4, r, sms, st))) return rc;
+            }
+            if ((rc = pool_norm_lrelu_launch(c1, bc, d.L1, 80, p1, stats, reinterpret_cast<const float*>(pk + s.n0_w),
+                                             reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80))) return rc;
+            // Conv1d(80, 60, 5): row t = p1[b, t : t + 5, :] = 400 contiguous values, K split 256 + 144
+            const __half* w1h = reinterpret_cast<const __half*>(pk + s.c1_t_hi);
+            const __half* w1l = reinterpret_cast<const __half*>(pk + s.c1_t_lo);
+            const float* b1 = reinterpret_cast<const float*>(pk + s.c1_b);
+            if ((rc = gemm_ts_rows_launch(p1_hi, p1_lo, 80, d.P1 * 80, bc, (int)d.L2, 256, w1h, w1l, 256, kC1TLd, 60, b1, 0, 0, c2, 60,
+                                          d.L2, 1, 0, sms, st))) return rc;
+            if ((rc = gemm_ts_rows_launch(p1_hi + 256, p1_lo + 256, 80, d.P1 * 80, bc, (int)d.L2, 144, w1h + 256, w1l + 256, 192, kC1TLd,
+                                          60, nullptr, 1, 0, c2, 60, d.L2, 1, 0, sms, st))) return rc;
+            if ((rc = pool_norm_lrelu_launch(c2, bc, d.L2, 60, p2, stats, reinterpret_cast<const float*>(pk + s.n1_w),
+                                             reinterpret_cast<const float*>(pk + s.n1_b), st, p2_hi, p2_lo, kC2Cp))) return rc;
+            // Conv1d(60, 60, 5) on channels padded to 64: row t = 320 contiguous values, K split 256 + 64
+            const __half* w2h = reinterpret_cast<const __half*>(pk + s.c2_t_hi);
+            const __half* w2l = reinterpret_cast<const __half*>(pk + s.c2_t_lo);
+            const float* b2 = reinterpret_cast<const float*>(pk + s.c2_b);
+            if ((rc = gemm_ts_rows_launch(p2_hi, p2_lo, kC2Cp, d.P2 * kC2Cp, bc, (int)d.L3, 256, w2h, w2l, 256, kC2TLd, 60, b2, 0, 0, c3,
+                                          60, d.L3, 1, 0, sms, st))) return rc;
+            if ((rc = gemm_ts_rows_launch(p2_hi + 256, p2_lo + 256, kC2Cp, d.P2 * kC2Cp, bc, (int)d.L3, 64, w2h + 256, w2l + 256, 64,
+                                          kC2TLd, 60, nullptr, 1, 0, c3, 60, d.L3, 1, 0, sms, st))) return rc;
+            if ((rc = pool_norm_lrelu_launch(c3, bc, d.L3, 60, out + b0 * d.P3 * 60, stats, reinterpret_cast<const float*>(pk + s.n2_w),
+                                             reinterpret_cast<const float*>(pk + s.n2_b), st))) return rc;
+            continue;
+        }
+        // ---- warp-MMA validation path
+        rc = wave_instnorm_launch(wav + b0 * wav_stride, bc, N, wav_stride, reinterpret_cast<const float*>(pk + s.wn_w),
+                                  reinterpret_cast<const float*>(pk + s.wn_b), stats, wn, st);
         if (rc) return rc;
         GemmArgs g;
         // sinc conv: rows (b, t) = wn[b, 10 t : 10 t + 251]

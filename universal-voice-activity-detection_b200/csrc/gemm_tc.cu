@@ -47,6 +47,13 @@ struct GemmTsParams {
     int T, tiles_per_blk;    // mode 3: rows are (sequence, step) pairs; a tile = 64 sequences x 2 steps
     const float* wc;         // mode 4: classifier weight [128] and bias [1]; c = prob [M]
     const float* bc;
+    // batched overlapping-row activations (the SincNet convolutions): a tile = 128 rows of one batch item, fetched as a
+    // 3-D box; tile row j of tile (b, rt) is output row  b * out_batch_rows + (rt * 128 + j) * out_row_step + out_row_off
+    int rows3d, rows_per_batch, tiles_per_batch;
+    int64_t out_batch_rows;
+    int out_row_step, out_row_off;
+    int n_valid;             // features >= n_valid are padding (weights zero) and are not stored
+    int act_abs;             // mode 0: store |x| (after the last K pass)
     int n_blocks;            // N / 128
     int kb;                  // k-blocks of 64
     int nw;                  // weight planes: 1 (hi) or 2 (hi, lo)
@@ -111,6 +118,10 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
                         tma_load_3d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, tp * 2, bblk * 64, bar_a_full(s));
                         tma_load_3d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, tp * 2, bblk * 64, bar_a_full(s));
+                    } else if (p.rows3d) {
+                        const int bi = t / p.tiles_per_batch, rt = t - bi * p.tiles_per_batch;
+                        tma_load_3d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, rt * SBM, bi, bar_a_full(s));
+                        tma_load_3d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, rt * SBM, bi, bar_a_full(s));
                     } else {
                         tma_load_2d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, t * SBM, bar_a_full(s));
                         tma_load_2d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, t * SBM, bar_a_full(s));
@@ -172,7 +183,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_w);
-        const float bias = (p.bias && !p.accumulate) ? __ldg(p.bias + out) : 0.f;
+        const float bias = (p.bias && !p.accumulate && out < p.n_valid) ? __ldg(p.bias + out) : 0.f;
         int it = 0;
         for (int t = tile0; t < p.num_m_tiles; t += tile_step, ++it) {
             const int ab = it & 1;
@@ -215,8 +226,16 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 }
                 continue;
             }
-            const int64_t row0 = (int64_t)t * SBM;
-            const int nrows = (int)min((int64_t)SBM, p.M - row0);
+            int64_t row0 = (int64_t)t * SBM;
+            int nrows = (int)min((int64_t)SBM, p.M - row0);
+            int64_t row_step = 1;
+            if (p.rows3d) {
+                const int bi = t / p.tiles_per_batch, rt = t - bi * p.tiles_per_batch;
+                nrows = min(SBM, p.rows_per_batch - rt * SBM);
+                row_step = p.out_row_step;
+                row0 = (int64_t)bi * p.out_batch_rows + (int64_t)rt * SBM * row_step + p.out_row_off;
+            }
+            const bool out_ok = out < p.n_valid;
 #pragma unroll 1
             for (int c = 0; c < SBM / 32; ++c) {
                 float v[32];
@@ -261,23 +280,47 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     }
                     continue;
                 }
-                // lane = output feature, register j = row: every store instruction writes one contiguous run per warp
-                const int64_t base = (row0 + c * 32) * p.ldc + out;
-                const int lim = nrows - c * 32;
+                // lane = output feature, register j = row: every store instruction writes one contiguous run per warp.
+                // Running pointers and a full-chunk fast path keep this at ~3 instructions per element: with one epilogue
+                // warp per scheduler the instruction stream itself is the tile's critical path (profiles/r01_gemm.md).
+                const int64_t base = (row0 + (int64_t)c * 32 * row_step) * p.ldc + out;
+                const int64_t jstride = row_step * p.ldc;
+                const int lim = out_ok ? nrows - c * 32 : 0;
+                if (lim <= 0) continue;
+                if (MODE == 0 && p.accumulate) {
+                    // K split over two launches: fetch the 32 partial sums first (independent loads), then add
+                    const float* src = p.c + base;
+                    float old[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { old[j] = (j < lim) ? __ldcg(src) : 0.f; src += jstride; }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += old[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (j < lim) {
-                        float x = v[j] + bias;
-                        if (MODE == 0 && p.accumulate) x += p.c[base + j * p.ldc];
-                        if (MODE != 0) x = x > 0.f ? x : 0.01f * x;
-                        if (MODE == 1) {
-                            __half hh, hl;
-                            split_f16(x, hh, hl);
-                            p.o_hi[base + j * p.ldc] = hh;
-                            p.o_lo[base + j * p.ldc] = hl;
-                        } else {
-                            p.c[base + j * p.ldc] = x;
-                        }
+                    float x = v[j] + bias;
+                    if (MODE == 0 && p.act_abs) x = fabsf(x);
+                    if (MODE != 0) x = x > 0.f ? x : 0.01f * x;
+                    v[j] = x;
+                }
+                if (MODE == 1) {
+                    __half* dh = p.o_hi + base;
+                    __half* dl = p.o_lo + base;
+                    if (lim >= 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { split_f16(v[j], *dh, *dl); dh += jstride; dl += jstride; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (j < lim) split_f16(v[j], *dh, *dl); dh += jstride; dl += jstride; }
+                    }
+                } else {
+                    float* dst = p.c + base;
+                    if (lim >= 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { *dst = v[j]; dst += jstride; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (j < lim) *dst = v[j]; dst += jstride; }
                     }
                 }
             }
@@ -454,7 +497,7 @@ int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t 
         return B200VAD_EINVAL;
     }
     GemmTsParams p = {};
-    p.wc = wc; p.bc = bc;
+    p.wc = wc; p.bc = bc; p.n_valid = N;
     p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = c; p.o_hi = o_hi; p.o_lo = o_lo; p.ldc = ldc; p.M = M;
     p.num_m_tiles = (int)((M + SBM - 1) / SBM);
     p.kb = Kp / SBK; p.nw = nw; p.Kp = Kp; p.ldw = ldw; p.accumulate = accumulate;
@@ -462,6 +505,41 @@ int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t 
     if ((rc = make_tmap_2d(&tm_a_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_tmap_2d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, M, lda * 2, SBK, SBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     return gemm_ts_run(mode, tm_a_hi, tm_a_lo, p, N, num_sms, st);
+}
+
+// Batched overlapping-row GEMM (the SincNet convolutions as GEMMs over sliding windows of a channel-last signal):
+// planes a_hi / a_lo hold, per batch item (batch_stride elements apart), a signal whose row r is the K consecutive
+// elements starting at r * row_stride (rows overlap; row_stride * 2 bytes must be a multiple of 16).  C row
+// b * out_batch_rows + r * out_row_step + out_row_off, feature f < n_valid  (+)=  sum_k a[b][r][k] * w[f][k] (+ bias),
+// optionally |.| on the way out.  Weights: [128][ldw] fp16 hi / lo, rows >= n_valid and columns >= K zero.
+int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int rows_per_batch,
+                        int K, const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias,
+                        int accumulate, int act_abs, float* c, int64_t ldc, int64_t out_batch_rows, int out_row_step,
+                        int out_row_off, int num_sms, cudaStream_t st) {
+    if (B <= 0 || rows_per_batch <= 0) return B200VAD_OK;
+    int rc = gemm_ts_check(K, Kp, ldw, 128, 8, w_lo ? 2 : 1);
+    if (rc) return rc;
+    if ((row_stride * 2) % 16 != 0 || (batch_stride * 2) % 16 != 0 || n_valid < 1 || n_valid > 128 ||
+        (reinterpret_cast<uintptr_t>(a_hi) & 15) || (reinterpret_cast<uintptr_t>(a_lo) & 15)) {
+        set_error("gemm_ts_rows: row / batch strides and base pointers must be 16-byte aligned, 1 <= n_valid <= 128");
+        return B200VAD_EINVAL;
+    }
+    GemmTsParams p = {};
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = c; p.ldc = ldc;
+    p.rows3d = 1; p.rows_per_batch = rows_per_batch; p.tiles_per_batch = (rows_per_batch + SBM - 1) / SBM;
+    p.out_batch_rows = out_batch_rows; p.out_row_step = out_row_step; p.out_row_off = out_row_off;
+    p.n_valid = n_valid; p.act_abs = act_abs; p.accumulate = accumulate;
+    p.M = (int64_t)B * rows_per_batch;
+    const int64_t tiles = (int64_t)B * p.tiles_per_batch;
+    if (tiles >= (1LL << 31)) { set_error("gemm_ts_rows: too many tiles"); return B200VAD_EINVAL; }
+    p.num_m_tiles = (int)tiles;
+    p.kb = Kp / SBK; p.nw = w_lo ? 2 : 1; p.Kp = Kp; p.ldw = ldw;
+    CUtensorMap tm_a_hi, tm_a_lo;
+    if ((rc = make_tmap_3d(&tm_a_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, rows_per_batch, B, row_stride * 2, batch_stride * 2,
+                           SBK, SBM, 1, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_3d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, rows_per_batch, B, row_stride * 2, batch_stride * 2,
+                           SBK, SBM, 1, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    return gemm_ts_run(0, tm_a_hi, tm_a_lo, p, 128, num_sms, st);
 }
 
 // LSTM input projection (mode 3): x planes (B, T, K) with row pitch lda -> xg in the step-blocked layout described at
@@ -474,6 +552,7 @@ int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B
     int rc = gemm_ts_check(K, Kp, ldw, 2 * kGates, lda, nw);
     if (rc) return rc;
     GemmTsParams p = {};
+    p.n_valid = 2 * kGates;
     p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.c = xg; p.M = (int64_t)B * T;
     p.T = T; p.tiles_per_blk = (T + 1) / 2;
     p.num_m_tiles = ((B + 63) / 64) * p.tiles_per_blk;

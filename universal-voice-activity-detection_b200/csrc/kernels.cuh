@@ -30,6 +30,10 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
 int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
                    int Kp, int ldw, int N, const float* bias, int mode, int accumulate, float* c, __half* o_hi, __half* o_lo,
                    int64_t ldc, int num_sms, cudaStream_t st, const float* wc = nullptr, const float* bc = nullptr);
+int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int rows_per_batch,
+                        int K, const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias,
+                        int accumulate, int act_abs, float* c, int64_t ldc, int64_t out_batch_rows, int out_row_step,
+                        int out_row_off, int num_sms, cudaStream_t st);
 int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
                       const __half* w_lo, int Kp, int ldw, const float* bias, int accumulate, float* xg, int num_sms,
                       cudaStream_t st);
@@ -48,7 +52,11 @@ int repack_conv_launch(const float* w, int Cout, int Cin, int k, float* out, cud
 int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, const float* gamma, const float* beta,
                          double* stats, float* out, cudaStream_t s);
 int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
-                           const float* beta, cudaStream_t s);
+                           const float* beta, cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0);
+int wave_norm_planes_launch(const float* wav, int B, int64_t N, int64_t stride, int64_t Np, const float* gamma, const float* beta,
+                            double* stats, __half* hi, __half* lo, cudaStream_t s);
+int pad_rows_launch(const float* w, int Cout, int K, int ld, float* out, cudaStream_t s);
+int repack_conv_pad_launch(const float* w, int Cout, int Cin, int k, int Cp, int ld, float* out, cudaStream_t s);
 
 int stat_scores_launch(const uint8_t* dec, const uint8_t* lab, int64_t n, int64_t* out4, cudaStream_t st);
 int score_intervals_launch(const int32_t* gt_iv, int64_t n_gt, const int32_t* pred_iv, int64_t n_pred, const int64_t* word_off,

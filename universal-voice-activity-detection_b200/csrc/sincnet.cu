@@ -119,6 +119,71 @@ int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, con
     return B200VAD_OK;
 }
 
+// normalised waveform as fp16 (hi, lo) planes in FOUR shifted copies (shift 0, 2, 4, 6 samples), each (B, Np):
+// copy e holds wn[i + 2 e].  The sinc convolution has stride 10 samples = 20 bytes, which is not a legal TMA row
+// stride; but rows t = 4 m + r of one residue class r start at 40 m + 10 r = (40 m + 8 floor(10 r / 8)) + (10 r mod 8),
+// i.e. at a 16-byte aligned offset of the copy shifted by 10 r mod 8 in {0, 2, 4, 6}, 80 bytes apart: four
+// overlapping-row tensor maps, one per residue class, feed the tcgen05 GEMM without an im2col pass.
+__global__ void __launch_bounds__(256) wave_norm_planes_kernel(const float* __restrict__ wav, int64_t N, int64_t stride, int64_t Np,
+                                                               int B, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, __half* __restrict__ hi,
+                                                               __half* __restrict__ lo) {
+    const int b = blockIdx.y;
+    double mean = stats[2 * b] / (double)N;
+    double var = stats[2 * b + 1] / (double)N - mean * mean;
+    float rstd = (float)(1.0 / sqrt(fmax(var, 0.0) + 1e-5));
+    float m = (float)mean, g = gamma[0], be = beta[0];
+    const float* row = wav + (int64_t)b * stride;
+    for (int64_t i = (int64_t)blockIdx.x * 256 * 16 + threadIdx.x; i < min(Np + 8, ((int64_t)blockIdx.x + 1) * 256 * 16); i += 256) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (i < N) split_f16((row[i] - m) * rstd * g + be, h, l);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t d = i - 2 * e;                      // copy e: element d holds sample d + 2 e
+            if (d >= 0 && d < Np) {
+                hi[((int64_t)e * B + b) * Np + d] = h;
+                lo[((int64_t)e * B + b) * Np + d] = l;
+            }
+        }
+    }
+}
+int wave_norm_planes_launch(const float* wav, int B, int64_t N, int64_t stride, int64_t Np, const float* gamma, const float* beta,
+                            double* stats, __half* hi, __half* lo, cudaStream_t s) {
+    { int rc = zero_f64_launch(stats, (int64_t)2 * B, s); if (rc) return rc; }
+    dim3 g1((unsigned)((N + 8191) / 8192), B);
+    wave_stats_kernel<<<g1, 256, 0, s>>>(wav, N, stride, stats);
+    B200VAD_LAUNCH_CHECK();
+    dim3 g2((unsigned)((Np + 8 + 4095) / 4096), B);
+    wave_norm_planes_kernel<<<g2, 256, 0, s>>>(wav, N, stride, Np, B, stats, gamma, beta, hi, lo);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// GEMM weights for the tcgen05 path, zero padded to 128 output rows: (Cout, K) -> (128, ld)
+__global__ void pad_rows_kernel(const float* __restrict__ w, int Cout, int K, int ld, float* __restrict__ out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128 * ld) return;
+    int r = idx / ld, k = idx % ld;
+    out[idx] = (r < Cout && k < K) ? w[(size_t)r * K + k] : 0.f;
+}
+int pad_rows_launch(const float* w, int Cout, int K, int ld, float* out, cudaStream_t s) {
+    pad_rows_kernel<<<(128 * ld + 255) / 256, 256, 0, s>>>(w, Cout, K, ld, out);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+// Conv1d weight (Cout, Cin, k) -> (128, ld) with element [co][kk * Cp + ci] (channel-last rows whose channels are padded to Cp)
+__global__ void repack_conv_pad_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cp, int ld, float* __restrict__ out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128 * ld) return;
+    int co = idx / ld, col = idx % ld, kk = col / Cp, ci = col % Cp;
+    out[idx] = (co < Cout && kk < k && ci < Cin) ? w[((size_t)co * Cin + ci) * k + kk] : 0.f;
+}
+int repack_conv_pad_launch(const float* w, int Cout, int Cin, int k, int Cp, int ld, float* out, cudaStream_t s) {
+    repack_conv_pad_kernel<<<(128 * ld + 255) / 256, 256, 0, s>>>(w, Cout, Cin, k, Cp, ld, out);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
 // ---------------------------------------------------------------- MaxPool1d(3,3) + InstanceNorm stats
 // in: (B, L, C) -> pooled (B, P, C), P = L / 3 (floor).  stats[(b*C + c)*2 + {0,1}] += sum, sumsq.
 constexpr int kPoolRows = 64;   // pooled rows per CTA
@@ -149,9 +214,11 @@ __global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict
         atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2 + 1, d);
     }
 }
-// in place: x = leaky_relu((x - mean) * rstd * gamma + beta)
+// in place: x = leaky_relu((x - mean) * rstd * gamma + beta); optionally also as fp16 (hi, lo) planes (B, P, Cp) with the
+// channels zero padded to Cp (the operand of the next convolution on the tcgen05 path)
 __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, int64_t P, int C, const double* __restrict__ stats,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         __half* __restrict__ p_hi, __half* __restrict__ p_lo, int Cp) {
     const int b = blockIdx.y;
     __shared__ float sc[128], sh[128];
     if (threadIdx.x < C) {
@@ -168,11 +235,18 @@ __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, 
     for (int64_t i = (int64_t)blockIdx.x * 256 * 16 + threadIdx.x; i < min(tot, ((int64_t)blockIdx.x + 1) * 256 * 16); i += 256) {
         int c = (int)(i % C);
         float v = fmaf(base[i], sc[c], sh[c]);
-        base[i] = v > 0.f ? v : 0.01f * v;
+        v = v > 0.f ? v : 0.01f * v;
+        base[i] = v;
+        if (p_hi) {
+            const int64_t o = ((int64_t)b * P + i / C) * Cp + c;
+            split_f16(v, p_hi[o], p_lo[o]);
+            if (c == C - 1)
+                for (int cc = C; cc < Cp; ++cc) { p_hi[o + cc - c] = __float2half_rn(0.f); p_lo[o + cc - c] = __float2half_rn(0.f); }
+        }
     }
 }
 int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
-                           const float* beta, cudaStream_t s) {
+                           const float* beta, cudaStream_t s, __half* p_hi, __half* p_lo, int Cp) {
     if (C > 128 || C < 1) {
         set_error("pool_norm: C must be in [1,128]");
         return B200VAD_EINVAL;
@@ -184,7 +258,7 @@ int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pool
     pool_stats_kernel<<<g1, 256, 0, s>>>(in, L, C, P, pooled, stats);
     B200VAD_LAUNCH_CHECK();
     dim3 g2((unsigned)((P * C + 4095) / 4096), B);
-    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta);
+    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta, p_hi, p_lo, Cp);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }
