@@ -71,3 +71,27 @@ def test_tc_model_matches_warp_mma_and_oracle(dev, B, T):
     print(f"B={B} T={T}: warp-MMA rel err {e1:.2e}, tcgen05 rel err {e2:.2e}")
     assert e2 <= util.PROB_RTOL, e2
     assert e1 <= util.PROB_RTOL, e1
+
+
+@pytest.mark.parametrize("B,T", [(5, 60), (70, 90), (200, 41)])
+def test_recurrence_tile_variants_agree(dev, B, T):
+    """16 and 64 sequences per CTA (latency / throughput schedules of the recurrence) give the same probabilities to
+    fp32 rounding of the accumulation order, and both match the oracle."""
+    import b200vad
+    g = torch.Generator().manual_seed(B * T)
+    x = torch.randn(B, T, 80, generator=g) * 3 - 5
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=x)
+    with torch.no_grad():
+        ref = o(x).squeeze(-1)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    L = b200vad.lib()
+    out = {}
+    try:
+        for nb in (16, 64):
+            b200vad._lib.check(L.b200vad_set_lstm_tile(nb), "set_lstm_tile")
+            out[nb] = torch.ops.b200vad.lstm_head(x.to(dev), blob, 4).cpu()
+    finally:
+        L.b200vad_set_lstm_tile(0)
+    assert util.prob_err(out[16], ref) <= util.PROB_RTOL and util.prob_err(out[64], ref) <= util.PROB_RTOL
+    assert util.prob_err(out[16], out[64]) <= 1e-5
+    assert L.b200vad_set_lstm_tile(32) != 0

@@ -322,6 +322,12 @@ int b200vad_set_impl(int impl) {
     return B200VAD_OK;
 }
 
+int b200vad_set_lstm_tile(int sequences_per_cta) {
+    int rc = lstm_tc_set_tile(sequences_per_cta);
+    if (rc) set_error("b200vad_set_lstm_tile: must be 0 (automatic), 16 or 64");
+    return rc;
+}
+
 int b200vad_init(int device) {
     int n = 0;
     B200VAD_CUDA(cudaGetDeviceCount(&n));

@@ -38,20 +38,33 @@ namespace b200vad {
 
 using namespace tc;
 
-constexpr int LNB = 64;                    // sequences per CTA
+constexpr int XBLK = 64;                   // sequences per xg record block (gemm_ts mode 3 layout)
 // The 64 columns are split into PARTS (2 or 4) independently pipelined groups of 64 / PARTS columns: while the
 // pointwise warpgroups of one part update their cells, the tensor core runs another part's MMAs.
 constexpr int LPARTS_DEFAULT = 4;          // pipelined column groups (B200VAD_LSTM_PARTS=2 selects the two-half schedule)
 constexpr int LWG = 4;                     // pointwise warpgroups
-constexpr int LWCOLS = LNB / LWG;          // 16 columns per warpgroup
 constexpr int LCH = 4;                     // columns per ring stage / inner chunk
-constexpr int LNCH = LWCOLS / LCH;         // chunks per step and warpgroup
 constexpr int LSTAGES = 4;                 // xg ring depth per warpgroup
 constexpr int LTC_THREADS = (LWG * 4 + 1 + LWG) * 32;   // 16 pointwise warps + MMA warp + one xg producer warp per warpgroup = 672
-constexpr int H_TILE = LNB * 64 * 2;       // 8 KB
-constexpr int C_BYTES = LNB * kHidden * 4; // 32 KB cell state
 constexpr int X_STAGE = 4 * kHidden * LCH * 4;   // one TMA box: 4 gates x 128 units x 4 columns (fp32) = 8 KB
-constexpr int TMEM_W = 4 * LNB;            // first TMEM column of W_hh (gate q at TMEM_W + 64 q)
+// Sequences per CTA (NB): 64 for throughput (4096-row batches fill 128 SMs), 16 for latency (small batches such as the
+// 256 streams of the streaming mode spread over 4x as many SMs and a step shrinks to one MMA group + one 4-column chunk
+// per warpgroup).  Derived sizes:
+template <int NB> struct LstmGeom {
+    static constexpr int LWCOLS = NB / LWG;             // columns per warpgroup (16 / 4)
+    static constexpr int LNCH = LWCOLS / LCH;           // chunks per step and warpgroup (4 / 1)
+    static constexpr int H_TILE = NB * 64 * 2;          // one [NB x 64] fp16 operand tile (8 KB / 2 KB)
+    static constexpr int C_BYTES = NB * kHidden * 4;    // cell state (32 KB / 8 KB)
+    static constexpr int TMEM_W = 4 * NB;               // first TMEM column of W_hh (after the 4 x NB accumulator columns)
+    static constexpr int SMEM = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
+};
+
+static int g_lstm_tile = 0;               // 0 = automatic, 16 / 64 = forced (b200vad_set_lstm_tile)
+int lstm_tc_set_tile(int nb) {
+    if (nb != 0 && nb != 16 && nb != 64) return B200VAD_EINVAL;
+    g_lstm_tile = nb;
+    return B200VAD_OK;
+}
 
 struct LstmTcParams {
     const __half* whh;     // [2][512][128]
@@ -59,10 +72,14 @@ struct LstmTcParams {
     int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
 };
 
-template <int PARTS>
+template <int PARTS, int NB>
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant__ CUtensorMap tm_yhi,
                const __grid_constant__ CUtensorMap tm_ylo, LstmTcParams p) {
+    constexpr int LNB = NB;
+    constexpr int LWCOLS = LstmGeom<NB>::LWCOLS, LNCH = LstmGeom<NB>::LNCH, H_TILE = LstmGeom<NB>::H_TILE;
+    constexpr int C_BYTES = LstmGeom<NB>::C_BYTES, TMEM_W = LstmGeom<NB>::TMEM_W;
+    static_assert(NB % (16 * PARTS) == 0 && LWCOLS % LCH == 0, "MMA N = NB / PARTS must be a multiple of 16");
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* const smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -112,7 +129,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     const uint32_t dst = smem_base + x_off + (wg * LSTAGES + st) * X_STAGE;
                     mbar_expect_tx(bar_x_full(wg, st), X_STAGE);
                     // one box = 4 gates x (128 units x 4 columns) of this step's 128 KB record
-                    tma_load_4d(dst, &tm_xg, 0, wg * LNCH + ch, 0, (blockIdx.x * 2 + dir) * T + t, bar_x_full(wg, st));
+                    tma_load_4d(dst, &tm_xg, 0, (b0 % XBLK) / LCH + wg * LNCH + ch, 0, ((b0 / XBLK) * 2 + dir) * T + t, bar_x_full(wg, st));
                     if (++st == LSTAGES) { st = 0; ph ^= 1; }
                 }
             }
@@ -284,11 +301,11 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     CUtensorMap tm_x, tm_yh, tm_yl;
     // xg is step-blocked (gemm_ts mode 3): [sequence block][dir][t][gate 4][column group 16][unit 128][4] fp32.  Viewed as
     // 8-byte elements: 256 per (gate, column group) run of 2 KB; one box = the 4 gates of one column group of one step.
-    const uint64_t nblk = (uint64_t)((B + LNB - 1) / LNB);
+    const uint64_t nblk = (uint64_t)((B + XBLK - 1) / XBLK);
     const uint64_t xdims[4] = {256, 16, 4, nblk * 2 * (uint64_t)T};
     const uint64_t xpitch[3] = {2048, 32768, 131072};
     const uint32_t xbox[4] = {256, 1, 4, 1};
-    static_assert(LCH == 4 && LNB == 64, "xg layout assumes 4-column groups and 64-sequence blocks");
+    static_assert(LCH == 4 && XBLK == 64, "xg layout assumes 4-column groups and 64-sequence blocks");
     int rc = make_tmap_4d(&tm_x, xg, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, xdims, xpitch, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     const void* yh = y_hi;
@@ -300,7 +317,12 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     }
     static int parts = -1;
     if (parts < 0) { const char* e = getenv("B200VAD_LSTM_PARTS"); parts = (e && atoi(e) == 2) ? 2 : LPARTS_DEFAULT; }
-    const uint32_t lpn = LNB / parts;
+    const int nb_env = g_lstm_tile;
+    // 16 sequences per CTA while that still fits one wave of CTAs (latency mode), else 64 (throughput mode)
+    const int sms = 148;
+    int nb = ((B + 15) / 16) * 2 <= sms ? 16 : 64;
+    if (nb_env == 16 || nb_env == 64) nb = nb_env;
+    const uint32_t lpn = nb == 16 ? 16 : XBLK / parts;
     rc = make_tmap_3d(&tm_yh, yh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * kHidden, yT, yB, (uint64_t)2 * kHidden * 2,
                       yT * 2 * kHidden * 2, 64, 1, lpn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -310,13 +332,14 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
     LstmTcParams p{whh, B, T, dbg};
-    const int smem = 8 * H_TILE + C_BYTES + LWG * LSTAGES * X_STAGE + 1024 + 512;
-    dim3 grid((B + LNB - 1) / LNB, 2);
-    prof_begin(0, st);
     typedef void (*KernFn)(CUtensorMap, CUtensorMap, CUtensorMap, LstmTcParams);
-    static const KernFn kerns[2] = {lstm_tc_kernel<2>, lstm_tc_kernel<4>};
-    static bool attr[2] = {false, false};
-    const int ki = parts == 4 ? 1 : 0;
+    static const KernFn kerns[3] = {lstm_tc_kernel<2, 64>, lstm_tc_kernel<4, 64>, lstm_tc_kernel<1, 16>};
+    static const int smems[3] = {LstmGeom<64>::SMEM, LstmGeom<64>::SMEM, LstmGeom<16>::SMEM};
+    static bool attr[3] = {false, false, false};
+    const int ki = nb == 16 ? 2 : (parts == 4 ? 1 : 0);
+    const int smem = smems[ki];
+    dim3 grid((B + nb - 1) / nb, 2);
+    prof_begin(0, st);
     if (!attr[ki]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[ki] = true; }
     kerns[ki]<<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
     prof_end(0, st);
