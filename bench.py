@@ -68,7 +68,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms while the timed regions (device arm and e2e arm) run."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -78,7 +78,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -250,7 +250,6 @@ def main():
         _lib.check(L.b200vad_profile_collect(kind, C.byref(tot_ms), C.byref(nl)), "profile_collect")
         prof[kind] = (tot_ms.value, nl.value)
     L.b200vad_profile_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +293,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item() / steps
     e2e_value = hours_step_global / (e2e_ms / 1e3)
+    clocks = sampler.stop() if rank == 0 else None
     # informational: the same loop fed 16-bit PCM (half the PCIe bytes, identical results -- tests/test_gpu_edges.py); the
     # headline e2e above keeps the reference's float32 waveforms
     pcm_host = (wav_host * 32768.0).clamp_(-32768, 32767).to(torch.int16).pin_memory()
