@@ -48,6 +48,16 @@ B200VAD_API void b200vad_profile_enable(int on);
 B200VAD_API int b200vad_profile_collect(int kind /* 0 = LSTM recurrence, 1 = input-projection GEMM, 2 = head / warp-MMA GEMMs, 3 = fbank */, double* total_ms, int* launches);
 /* 2 = tcgen05 kernels (default); 1 = the warp-MMA kernels kept for cross-validation of the tcgen05 path */
 B200VAD_API int b200vad_set_impl(int impl);
+/* fp16 tensor-core products per k-step of the input projections of LSTM layers >= 1: 2 (default: the layer outputs
+ * travel as planes y1 = fp16((1 - 2^-6) y), y2 = fp16(y - y1) and xg = y1.W_hi + y2.W' with W' = fp16(W_hi + 2^6 W_lo),
+ * one accumulator) or 3 (hi / lo planes and the plain split product x_lo.W_hi + x_hi.W_lo + x_hi.W_hi; validation).
+ * Layer 0 and the head always use 3. */
+B200VAD_API int b200vad_set_projection_terms(int terms);
+/* Kernel of the input projections with K <= 256: 2 (default) = CTA pairs (tcgen05.mma.cta_group::2: two feature blocks
+ * share an activation tile, each CTA loading half of it), both weight planes in tensor memory, 2 or 3 products per
+ * k-step (see above); 1 = the same on single CTAs with an 8-warp epilogue; 0 = the general K-split kernel (always 3
+ * products; validation, and the path of inputs wider than 256). */
+B200VAD_API int b200vad_set_projection_kernel(int which);
 /* Sequences per CTA of the tcgen05 recurrence: 0 = automatic (16 while the batch fits one wave of CTAs -- low latency
  * for small batches / streaming --, else 64), or 16 / 64 to force one (validation, tuning). */
 B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);

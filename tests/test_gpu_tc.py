@@ -95,3 +95,36 @@ def test_recurrence_tile_variants_agree(dev, B, T):
     assert util.prob_err(out[16], ref) <= util.PROB_RTOL and util.prob_err(out[64], ref) <= util.PROB_RTOL
     assert util.prob_err(out[16], out[64]) <= 1e-5
     assert L.b200vad_set_lstm_tile(32) != 0
+
+
+@pytest.mark.parametrize("B,T", [(70, 64), (7, 333), (129, 41)])
+def test_projection_kernels_agree(dev, B, T):
+    """Input projections: the general kernel (0), the single-CTA resident-weight kernel (1) and the CTA-pair kernel (2,
+    default) give bit-identical results with three fp16 products per k-step; with two products (layers >= 1: scaled
+    (y1, y2) planes and W' = fp16(W_hi + 2^6 W_lo), the default) the probabilities move by ~2e-5 relative, far inside the
+    tolerance, and every variant matches the oracle."""
+    import b200vad
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, 80, generator=g) * 3 - 5
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=x)
+    with torch.no_grad():
+        ref = o(x).squeeze(-1)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    L = b200vad.lib()
+    out = {}
+    try:
+        for kern, terms in ((0, 3), (1, 3), (2, 3), (1, 2), (2, 2)):
+            b200vad._lib.check(L.b200vad_set_projection_kernel(kern), "set_projection_kernel")
+            b200vad._lib.check(L.b200vad_set_projection_terms(terms), "set_projection_terms")
+            out[(kern, terms)] = torch.ops.b200vad.lstm_head(x.to(dev), blob, 4).cpu()
+    finally:
+        L.b200vad_set_projection_kernel(2)
+        L.b200vad_set_projection_terms(2)
+    for k, v in out.items():
+        e = util.prob_err(v, ref)
+        print(f"B={B} T={T}: kernel {k[0]} terms {k[1]}: err vs oracle {e:.2e}")
+        assert e <= util.PROB_RTOL
+    assert torch.equal(out[(1, 3)], out[(0, 3)]) and torch.equal(out[(2, 3)], out[(0, 3)])
+    assert torch.equal(out[(2, 2)], out[(1, 2)])
+    assert util.prob_err(out[(2, 2)], out[(0, 3)]) <= 1e-4
+    assert L.b200vad_set_projection_kernel(3) != 0 and L.b200vad_set_projection_terms(4) != 0

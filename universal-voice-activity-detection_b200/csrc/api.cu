@@ -49,6 +49,8 @@ void prof_end(int kind, cudaStream_t st) {
 }
 
 static int g_impl = 2;        // 2 = tcgen05 kernels (default), 1 = warp-MMA kernels (validation only)
+static int g_proj_terms = 2;  // fp16 products per k-step of the layer >= 1 input projections: 2 (default) or 3 (validation)
+static int g_proj_kernel = 2;  // input projections with K <= 256: 0 = gemm_ts_kernel<3>, 1 = gemm_xg2_kernel, 2 = gemm_xg_pair_kernel (default)
 static int num_sms_cached() {
     static int n = 0;
     if (!n) {
@@ -198,6 +200,19 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
             const float* bias = reinterpret_cast<const float*>(pk + lo.bias);
             // hi + lo weight planes stay resident in tensor memory: 256 k-values per launch; wider inputs (768-dim SSL
             // features on layer 0) are split along K and accumulated into xg
+            int* const sync = reinterpret_cast<int*>(x_hi);
+            const size_t sync_bytes = 2 * align_up(sizeof(__half) * D8 * rows);
+            const int terms = (l > 0 && g_proj_terms == 2) ? 2 : 3;
+            if (g_proj_kernel != 0 && lo.D <= 256) {
+                // one launch, both weight planes resident in TMEM; the lockstep counters live in the layer-0 input planes'
+                // workspace, which is free when the planes come from the fused fbank and dead after layer 0
+                int* const sy = (l == 0 && xin) ? nullptr : sync;
+                if (g_proj_kernel == 2)      // CTA pairs share every activation tile (cta_group::2 MMAs)
+                    rc = gemm_xg_pair_launch(a_hi, a_lo, lda, bc, (int)T, lo.D, w_hi, w_lo, lo.Kp, lo.Kp, bias, terms, xg, sy, sync_bytes, sms, st);
+                else
+                    rc = gemm_xg2_launch(a_hi, a_lo, lda, bc, (int)T, lo.D, w_hi, w_lo, lo.Kp, lo.Kp, bias, terms, xg, sy, sync_bytes, sms, st);
+                if (rc) return rc;
+            } else
             for (int k0 = 0; k0 < lo.D; k0 += 256) {
                 const int kc = std::min(256, lo.D - k0);
                 if ((rc = gemm_ts_xg_launch(a_hi + k0, a_lo + k0, lda, bc, (int)T, kc, w_hi + k0, w_lo + k0, round64(kc), lo.Kp, bias,
@@ -205,7 +220,10 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
             }
             __half* yh = reinterpret_cast<__half*>(outbuf);
             __half* yl = yh + rows * 2 * kHidden;
-            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), yh, yl, bc, (int)T, st))) return rc;
+            // the output planes of a layer that feeds a 2-MMA projection use that kernel's scaled split; the last layer
+            // (into the head's 3-term product) keeps hi / lo
+            const int scaled = (g_proj_terms == 2 && g_proj_kernel != 0 && l + 1 < L) ? 1 : 0;
+            if ((rc = lstm_tc_launch(xg, reinterpret_cast<const __half*>(pk + lo.whh), yh, yl, bc, (int)T, scaled, st))) return rc;
             a_hi = yh; a_lo = yl; lda = 2 * kHidden;
             outbuf = (outbuf == buf0) ? buf1 : buf0;
         }
@@ -319,6 +337,18 @@ int b200vad_profile_collect(int kind, double* total_ms, int* launches) {
 int b200vad_set_impl(int impl) {
     B200VAD_CHECK_ARG(impl == 1 || impl == 2, "impl must be 1 (warp-MMA) or 2 (tcgen05)");
     g_impl = impl;
+    return B200VAD_OK;
+}
+
+int b200vad_set_projection_terms(int terms) {
+    B200VAD_CHECK_ARG(terms == 2 || terms == 3, "terms must be 2 or 3");
+    g_proj_terms = terms;
+    return B200VAD_OK;
+}
+
+int b200vad_set_projection_kernel(int which) {
+    B200VAD_CHECK_ARG(which >= 0 && which <= 2, "which must be 0, 1 or 2");
+    g_proj_kernel = which;
     return B200VAD_OK;
 }
 

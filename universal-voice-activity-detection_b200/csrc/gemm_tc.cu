@@ -331,6 +331,422 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------- 2-MMA input projection (layers >= 1)
+// xg = x . W^T with x and W as fp16 (hi, lo) planes needs three fp16 products for ~2^-21 accuracy (x_lo.W_hi + x_hi.W_lo
+// + x_hi.W_hi) and that makes the K = 256 projections tensor bound.  Two products into ONE accumulator are enough when
+// the activation planes are split with a scale s = 2^-6 instead of at the fp16 rounding point (lstm_tc_kernel writes
+// them that way when asked):
+//     x1 = fp16((1 - s) x),  x2 = fp16(x - x1) = s x + r      (r = rounding residual of x1, 2^-12 |x|; x1 + x2 = x to 2^-18)
+//     W' = fp16(W_hi + W_lo / s)                              (once per CTA, on the way into TMEM)
+//     x1.W_hi + x2.W' = x.((1 - s) W_hi + s W') + r.(W' - W_hi)
+// (1 - s) W_hi + s W' equals W up to s * rounding(W') = 2^-18 |W|, and |W' - W_hi| = |W_lo| / s <= 2^-6 |W| multiplies
+// r: every term is accurate to ~2^-18 relative (3-term: 2^-22; dropping W_lo: 2^-12).  The recurrence (W_hh single fp16)
+// and the head's 3-term product consume the same (x1, x2) planes unchanged.  End to end the probabilities move by
+// ~2.6e-5 relative (tools/two_mma_precision.py), 10x below the W_hh rounding that dominates.  Layer 0 (un-normalised
+// log-mel input in hi / lo planes, HBM-write bound anyway) stays 3-term.
+//
+// Structure as gemm_ts_kernel<3> (tile = 64 sequences x 2 steps, weights in TMEM, double-buffered accumulator).  With
+// 2/3 of the tensor work the kernel is bound by the 4 KB / frame xg write, and the 8 CTAs of a group (the 8 feature
+// blocks) that read the same activation tiles drift apart unless they are kept in lockstep (see the producer).
+// (A first version converted hi / lo planes to (x1, x2)-like operands in shared memory with a transform warpgroup: the
+// extra 48 KB of shared-memory traffic per stage made it slower than the 3-term kernel -- profiles/r01_gemm.md.)
+constexpr int X2_THREADS = 320;                       // TMA, MMA, 8 epilogue warps
+constexpr int X2_STAGES = 6;
+constexpr float X2_S = kPlaneScale;
+
+struct GemmX2Params {
+    const __half* w_hi;      // [1024][ldw]
+    const __half* w_lo;
+    const float* bias;       // [1024]
+    float* xg;
+    int T, tiles_per_blk, num_tiles, kb, ldw, terms;
+    int* sync;               // [groups][sync_stride] window arrival counters (zeroed per launch) or null
+    int sync_stride;
+};
+constexpr int X2_WINDOW = 2;                          // tiles per lockstep window
+
+// Epilogue store of one 32-column accumulator chunk c of a (64 sequences x 2 steps) tile: accumulator column j =
+// sequence * 2 + step; 8 columns = 4 sequences (one column group) x 2 steps; one 16-byte store = 4 sequences of a unit.
+__device__ __forceinline__ void xg_store_chunk(float* base, int c, const float (&v)[32], float bias, bool t1_ok) {
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+            if (tl == 1 && !t1_ok) continue;
+            float4* dst = reinterpret_cast<float4*>(base + (int64_t)tl * 4 * 8192 + ((c * 4 + g4) * 128) * 4);
+            *dst = make_float4(v[8 * g4 + tl] + bias, v[8 * g4 + 2 + tl] + bias, v[8 * g4 + 4 + tl] + bias, v[8 * g4 + 6 + tl] + bias);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(X2_THREADS, 1)
+gemm_xg2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo, GemmX2Params p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;                                        // [stages][x1, x2] tiles of 128 x 64
+    const uint32_t bar_base = a_base + X2_STAGES * 2 * S_TILE_BYTES;
+    auto bar_a_full = [&](int s) { return bar_base + 8 * s; };                // TMA landed        (count 1 + tx)
+    auto bar_a_empty = [&](int s) { return bar_base + 128 + 8 * s; };         // MMAs retired      (count 1)
+    auto bar_acc_full = [&](int b) { return bar_base + 192 + 8 * b; };
+    auto bar_acc_empty = [&](int b) { return bar_base + 208 + 8 * b; };
+    const uint32_t bar_w = bar_base + 224;
+    const uint32_t tmem_slot = bar_base + 232;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x & 7;                                           // feature block = dir * 4 + gate
+    const int tile0 = blockIdx.x >> 3;
+    const int tile_step = gridDim.x >> 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < X2_STAGES; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 256); }
+        mbar_init(bar_w, 256);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int wcols = p.kb * 32;                                              // TMEM columns per weight plane (K / 2)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+            int s = 0;
+            uint32_t ph = 0;
+            // The 8 CTAs of a group read the same activation tiles; only if they stay within a few tiles of each other does
+            // L2 serve 7 of the 8 reads.  The kernel is memory bound, so free-running CTAs drift (measured: 15.5 GB of DRAM
+            // reads for 3.4 GB of activations).  Lockstep: a producer announces every window of X2_WINDOW tiles it starts
+            // and does not start window w + 1 before all 8 have started window w.  The wait is bounded (a late CTA only
+            // costs bandwidth, never correctness), so co-residency of the group is not a requirement.
+            int* const sync = p.sync ? p.sync + (size_t)tile0 * p.sync_stride : nullptr;
+            int ti = 0;
+            for (int t = tile0; t < p.num_tiles; t += tile_step, ++ti) {
+                if (sync && (ti % X2_WINDOW) == 0) {
+                    const int w = ti / X2_WINDOW;
+                    if (w < p.sync_stride) {
+                        atomicAdd(sync + w, 1);
+                        if (w > 0) {
+                            const long long t0c = clock64();
+                            while (*reinterpret_cast<volatile int*>(sync + w - 1) < 8 && clock64() - t0c < 2000000LL) { }
+                        }
+                    }
+                }
+                const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_a_full(s), 2 * S_TILE_BYTES);
+                    tma_load_3d(a_base + (2 * s) * S_TILE_BYTES, &tm_a_hi, kb * SBK, tp * 2, bblk * 64, bar_a_full(s));
+                    tma_load_3d(a_base + (2 * s + 1) * S_TILE_BYTES, &tm_a_lo, kb * SBK, tp * 2, bblk * 64, bar_a_full(s));
+                    if (++s == X2_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_f16(128, SBM);
+            mbar_wait(bar_w, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
+                const int ab = it & 1;
+                const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(bar_acc_empty(ab), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ACC_COL + ab * SBM;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t x_1 = a_base + (2 * s) * S_TILE_BYTES, x_2 = x_1 + S_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_p = w_hi + wcols;
+                        const uint64_t dx_1 = smem_desc_sw128(x_1 + k * 32), dx_2 = smem_desc_sw128(x_2 + k * 32);
+                        if (p.terms == 3) {
+                            mma_f16_ts(d_tmem, w_hi, dx_2, idesc, (kb | k) != 0);              // x_lo.W_hi: small terms first
+                            mma_f16_ts(d_tmem, w_p, dx_1, idesc, 1);                           // x_hi.W_lo
+                        } else {
+                            mma_f16_ts(d_tmem, w_p, dx_2, idesc, (kb | k) != 0);               // x2.W'
+                        }
+                        mma_f16_ts(d_tmem, w_hi, dx_1, idesc, 1);                              // x_hi.W_hi / x1.W_hi
+                    }
+                    mma_commit(bar_a_empty(s));
+                    if (++s == X2_STAGES) { s = 0; ph ^= 1; }
+                }
+                mma_commit(bar_acc_full(ab));
+            }
+        }
+    } else {
+        // ===================== weights -> TMEM, then epilogue =====================
+        // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of every accumulator
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int unit = q * 32 + lane;
+        const int out = blk * 128 + unit;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        {
+            const uint4* whi = reinterpret_cast<const uint4*>(p.w_hi + (size_t)out * p.ldw);
+            const uint4* wlo = reinterpret_cast<const uint4*>(p.w_lo + (size_t)out * p.ldw);
+            for (int part = half; part < p.kb * 2; part += 2) {                 // 32 fp16 = 16 packed columns
+                uint32_t ra[16], rb[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 vh = __ldg(whi + part * 4 + i), vl = __ldg(wlo + part * 4 + i);
+                    const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        ra[4 * i + e] = hw[e];
+                        if (p.terms == 3) {
+                            rb[4 * i + e] = lw[e];
+                        } else {
+                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                            const __half2 wp = __floats2half2_rn(fmaf(fl.x, 1.f / X2_S, fh.x), fmaf(fl.y, 1.f / X2_S, fh.y));
+                            rb[4 * i + e] = *reinterpret_cast<const uint32_t*>(&wp);
+                        }
+                    }
+                }
+                tmem_st16(lane_addr + part * 16, ra);
+                tmem_st16(lane_addr + wcols + part * 16, rb);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_w);
+        const float bias = p.bias ? __ldg(p.bias + out) : 0.f;
+        const int dir = blk >> 2, gate = blk & 3;
+        int it = 0;
+        for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
+            const int ab = it & 1;
+            const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(bar_acc_full(ab), acc_ph);
+            tc_fence_after();
+            const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
+            const int t0 = tp * 2;
+            float* base = p.xg + ((((int64_t)bblk * 2 + dir) * p.T + t0) * 4 + gate) * 8192 + unit * 4;
+            const bool t1_ok = t0 + 1 < p.T;
+            // both 32-column chunks of this warp's half are fetched before the first store is issued
+            float v0[32], v1[32];
+            tmem_ld32(lane_addr + ACC_COL + ab * SBM + half * 64, v0);
+            tmem_ld32(lane_addr + ACC_COL + ab * SBM + half * 64 + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty(ab));
+            xg_store_chunk(base, half * 2, v0, bias, t1_ok);
+            xg_store_chunk(base, half * 2 + 1, v1, bias, t1_ok);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------- CTA-pair input projection (cta_group::2)
+// Every activation tile is consumed by the 8 feature-block CTAs of a group, so 8x the activation bytes cross the L2
+// fabric (26.8 GB per K = 256 launch next to 13.4 GB of xg writes); the single-CTA kernels above run at the fabric's
+// ~6300 B/clk whatever their tensor work (3-term and 2-MMA variants measured the same 4.05 ms -- profiles/r01_gemm.md).
+// Here two feature blocks form a CTA pair on one TPC: each CTA keeps its own 128 features' weights in its own TMEM and
+// loads HALF of the activation tile (32 sequences x 2 steps); one tcgen05.mma.cta_group::2 (M = 256, N = 128) issued
+// by the even CTA multiplies both CTAs' weights with both halves.  Activation bytes through L2 and per-CTA shared-memory
+// fill are halved; accumulators, epilogue and xg layout are those of gemm_ts_kernel<3>.
+// terms = 3: planes are (hi, lo), weights (W_hi, W_lo);  terms = 2: planes are the scaled (x1, x2) split, weights
+// (W_hi, W') -- see gemm_xg2_kernel.
+constexpr int XP_THREADS = 192;                       // TMA, MMA, 4 epilogue warps
+constexpr int XP_STAGES = 10;
+constexpr int XP_HALF_BYTES = 64 * SBK * 2;           // 8 KB: 32 sequences x 2 steps x 64 k
+
+struct GemmXpParams {
+    const __half* w_hi;      // [1024][ldw]
+    const __half* w_lo;
+    const float* bias;       // [1024]
+    float* xg;
+    int T, tiles_per_blk, num_tiles, kb, ldw, terms;
+    int* sync;               // [groups][sync_stride] window arrival counters (zeroed per launch) or null
+    int sync_stride;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XP_THREADS, 1)
+gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmXpParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;                                        // [stages][plane a, plane b] half tiles of 64 x 64
+    const uint32_t bar_base = a_base + XP_STAGES * 2 * XP_HALF_BYTES;
+    auto bar_a_full = [&](int s) { return bar_base + 8 * s; };                // even CTA's: both CTAs' TMA bytes (tx) + 1
+    auto bar_a_empty = [&](int s) { return bar_base + 128 + 8 * s; };         // both CTAs': MMAs retired (multicast commit)
+    auto bar_acc_full = [&](int b) { return bar_base + 256 + 8 * b; };        // both CTAs' (multicast commit)
+    auto bar_acc_empty = [&](int b) { return bar_base + 272 + 8 * b; };       // even CTA's: 256 epilogue threads of the pair
+    const uint32_t bar_w = bar_base + 288;                                    // even CTA's: 256 weight loaders
+    const uint32_t tmem_slot = bar_base + 296;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                                  // == blockIdx.x & 1
+    const int blk = blockIdx.x & 7;                                           // feature block = dir * 4 + gate
+    const int tile0 = blockIdx.x >> 3;
+    const int tile_step = gridDim.x >> 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < XP_STAGES; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 256); }
+        mbar_init(bar_w, 256);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                                                       // barriers of both CTAs exist before any remote use
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int wcols = p.kb * 32;                                              // TMEM columns per weight plane (K / 2)
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; bytes are credited to the even CTA's barrier) =====================
+        if (elect_one()) {
+            tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+            int s = 0;
+            uint32_t ph = 0;
+            // lockstep of the 8 CTAs of a group, as in gemm_xg2_kernel: bounded waits, bandwidth only
+            int* const sync = p.sync ? p.sync + (size_t)tile0 * p.sync_stride : nullptr;
+            int ti = 0;
+            for (int t = tile0; t < p.num_tiles; t += tile_step, ++ti) {
+                if (sync && (ti % X2_WINDOW) == 0) {
+                    const int w = ti / X2_WINDOW;
+                    if (w < p.sync_stride) {
+                        atomicAdd(sync + w, 1);
+                        if (w > 0) {
+                            const long long t0c = clock64();
+                            while (*reinterpret_cast<volatile int*>(sync + w - 1) < 8 && clock64() - t0c < 2000000LL) { }
+                        }
+                    }
+                }
+                const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
+                const int seq0 = bblk * 64 + (int)rank * 32;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_empty(s), ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(bar_a_full(s), 4 * XP_HALF_BYTES);
+                    tma_load_3d_pair(a_base + (2 * s) * XP_HALF_BYTES, &tm_a, kb * SBK, tp * 2, seq0, bar_a_full(s));
+                    tma_load_3d_pair(a_base + (2 * s + 1) * XP_HALF_BYTES, &tm_b, kb * SBK, tp * 2, seq0, bar_a_full(s));
+                    if (++s == XP_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (even CTA only, for the pair) =====================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = idesc_f16(256, SBM);
+            mbar_wait(bar_w, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
+                const int ab = it & 1;
+                const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(bar_acc_empty(ab), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ACC_COL + ab * SBM;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t x_a = a_base + (2 * s) * XP_HALF_BYTES, x_b = x_a + XP_HALF_BYTES;
+#pragma unroll
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_a = tmem_base + (kb * 4 + k) * 8, w_b = w_a + wcols;
+                        const uint64_t dx_a = smem_desc_sw128(x_a + k * 32), dx_b = smem_desc_sw128(x_b + k * 32);
+                        if (p.terms == 3) {
+                            mma_f16_ts_pair(d_tmem, w_a, dx_b, idesc, (kb | k) != 0);          // x_lo.W_hi: small terms first
+                            mma_f16_ts_pair(d_tmem, w_b, dx_a, idesc, 1);                      // x_hi.W_lo
+                        } else {
+                            mma_f16_ts_pair(d_tmem, w_b, dx_b, idesc, (kb | k) != 0);          // x2.W'
+                        }
+                        mma_f16_ts_pair(d_tmem, w_a, dx_a, idesc, 1);                          // x_hi.W_hi / x1.W_hi
+                    }
+                    mma_commit_pair(bar_a_empty(s));
+                    if (++s == XP_STAGES) { s = 0; ph ^= 1; }
+                }
+                mma_commit_pair(bar_acc_full(ab));
+            }
+        }
+    } else {
+        // ===================== weights -> own TMEM, then epilogue (warps 2..5 -> lane quarters 2,3,0,1) =====================
+        const int q = warp & 3;
+        const int unit = q * 32 + lane;
+        const int out = blk * 128 + unit;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        {
+            const uint4* whi = reinterpret_cast<const uint4*>(p.w_hi + (size_t)out * p.ldw);
+            const uint4* wlo = reinterpret_cast<const uint4*>(p.w_lo + (size_t)out * p.ldw);
+            for (int part = 0; part < p.kb * 2; ++part) {                       // 32 fp16 = 16 packed columns
+                uint32_t ra[16], rb[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 vh = __ldg(whi + part * 4 + i), vl = __ldg(wlo + part * 4 + i);
+                    const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        ra[4 * i + e] = hw[e];
+                        if (p.terms == 3) {
+                            rb[4 * i + e] = lw[e];
+                        } else {
+                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                            const __half2 wp = __floats2half2_rn(fmaf(fl.x, 1.f / X2_S, fh.x), fmaf(fl.y, 1.f / X2_S, fh.y));
+                            rb[4 * i + e] = *reinterpret_cast<const uint32_t*>(&wp);
+                        }
+                    }
+                }
+                tmem_st16(lane_addr + part * 16, ra);
+                tmem_st16(lane_addr + wcols + part * 16, rb);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(mapa_shared(bar_w, 0));
+        const float bias = p.bias ? __ldg(p.bias + out) : 0.f;
+        const int dir = blk >> 2, gate = blk & 3;
+        const uint32_t acc_empty0 = mapa_shared(bar_acc_empty(0), 0), acc_empty1 = mapa_shared(bar_acc_empty(1), 0);
+        int it = 0;
+        for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
+            const int ab = it & 1;
+            const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(bar_acc_full(ab), acc_ph);
+            tc_fence_after();
+            const int bblk = t / p.tiles_per_blk, tp = t - bblk * p.tiles_per_blk;
+            const int t0 = tp * 2;
+            float* base = p.xg + ((((int64_t)bblk * 2 + dir) * p.T + t0) * 4 + gate) * 8192 + unit * 4;
+            const bool t1_ok = t0 + 1 < p.T;
+#pragma unroll 1
+            for (int c = 0; c < SBM / 32; ++c) {
+                float v[32];
+                tmem_ld32(lane_addr + ACC_COL + ab * SBM + c * 32, v);
+                tmem_ld_wait();
+                if (c == SBM / 32 - 1) {
+                    tc_fence_before();
+                    mbar_arrive_cluster(ab ? acc_empty1 : acc_empty0);
+                }
+                // accumulator column j = sequence * 2 + step (columns [0, 64) come from the even CTA's half tile)
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+#pragma unroll
+                    for (int tl = 0; tl < 2; ++tl) {
+                        if (tl == 1 && !t1_ok) continue;
+                        float4* dst = reinterpret_cast<float4*>(base + (int64_t)tl * 4 * 8192 + ((c * 4 + g4) * 128) * 4);
+                        *dst = make_float4(v[8 * g4 + tl] + bias, v[8 * g4 + 2 + tl] + bias, v[8 * g4 + 4 + tl] + bias,
+                                           v[8 * g4 + 6 + tl] + bias);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                                       // the peer's TMEM / barriers stay alive until both are done
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+}
+
 // ---------------------------------------------------------------- fp32 -> fp16 (hi, lo) planes
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t n, __half* __restrict__ hi,
                                                            __half* __restrict__ lo) {
@@ -540,6 +956,87 @@ int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stri
     if ((rc = make_tmap_3d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, rows_per_batch, B, row_stride * 2, batch_stride * 2,
                            SBK, SBM, 1, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     return gemm_ts_run(0, tm_a_hi, tm_a_lo, p, 128, num_sms, st);
+}
+
+// 2-MMA input projection (K <= 256, both weight planes given): same contract as gemm_ts_xg_launch without `accumulate`;
+// sync / sync_bytes: optional 4-byte aligned device scratch for the lockstep counters (skipped when too small)
+int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
+                    const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
+                    size_t sync_bytes, int num_sms, cudaStream_t st) {
+    if (B <= 0 || T <= 0) return B200VAD_OK;
+    int rc = gemm_ts_check(K, Kp, ldw, 2 * kGates, lda, 2);
+    if (rc) return rc;
+    if (!w_lo || (terms != 2 && terms != 3)) { set_error("gemm_xg2: needs both weight planes and terms 2 or 3"); return B200VAD_EINVAL; }
+    GemmX2Params p;
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.xg = xg; p.T = T; p.kb = Kp / SBK; p.ldw = ldw; p.terms = terms;
+    p.tiles_per_blk = (T + 1) / 2;
+    const int64_t tiles = (int64_t)((B + 63) / 64) * p.tiles_per_blk;
+    if (tiles >= (1LL << 31)) { set_error("gemm_xg2: too many tiles"); return B200VAD_EINVAL; }
+    p.num_tiles = (int)tiles;
+    CUtensorMap tm_a_hi, tm_a_lo;
+    if ((rc = make_tmap_3d(&tm_a_hi, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, T, B, lda * 2, (uint64_t)T * lda * 2, SBK, 2, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_3d(&tm_a_lo, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, T, B, lda * 2, (uint64_t)T * lda * 2, SBK, 2, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const int smem = 1024 + X2_STAGES * 2 * S_TILE_BYTES + 512;
+    int grid = (num_sms / 8) * 8;
+    if (grid < 8) grid = 8;
+    if ((int64_t)grid > tiles * 8) grid = (int)(tiles * 8);
+    // lockstep counters: one int per (group, window) in caller-provided scratch, zeroed on the launch stream
+    const int groups = grid / 8;
+    const int64_t stride = ((tiles + groups - 1) / groups + X2_WINDOW - 1) / X2_WINDOW + 1;
+    p.sync = nullptr; p.sync_stride = (int)std::min<int64_t>(stride, 1 << 30);
+    if (sync && stride < (1 << 30) && sizeof(int) * (size_t)groups * stride <= sync_bytes) {
+        p.sync = sync;
+        B200VAD_CUDA(cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)groups * stride, st));
+    }
+    static bool attr = false;
+    if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_xg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    prof_begin(1, st);
+    gemm_xg2_kernel<<<grid, X2_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
+    prof_end(1, st);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// CTA-pair input projection (K <= 256, both weight planes): terms = 3 (hi / lo planes) or 2 (scaled planes, see
+// gemm_xg2_kernel); same contract as gemm_xg2_launch.  The grid is a multiple of 8 CTAs = 4 pairs per activation tile.
+int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int K, const __half* w_hi,
+                        const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
+                        size_t sync_bytes, int num_sms, cudaStream_t st) {
+    if (B <= 0 || T <= 0) return B200VAD_OK;
+    int rc = gemm_ts_check(K, Kp, ldw, 2 * kGates, lda, 2);
+    if (rc) return rc;
+    if (!w_lo || (terms != 2 && terms != 3)) { set_error("gemm_xg_pair: needs both weight planes and terms 2 or 3"); return B200VAD_EINVAL; }
+    GemmXpParams p;
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.xg = xg; p.T = T; p.kb = Kp / SBK; p.ldw = ldw; p.terms = terms;
+    p.tiles_per_blk = (T + 1) / 2;
+    const int64_t tiles = (int64_t)((B + 63) / 64) * p.tiles_per_blk;
+    if (tiles >= (1LL << 31)) { set_error("gemm_xg_pair: too many tiles"); return B200VAD_EINVAL; }
+    p.num_tiles = (int)tiles;
+    CUtensorMap tm_a, tm_b;
+    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, T, B, lda * 2, (uint64_t)T * lda * 2, SBK, 2, 32,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, T, B, lda * 2, (uint64_t)T * lda * 2, SBK, 2, 32,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const int smem = 1024 + XP_STAGES * 2 * XP_HALF_BYTES + 512;
+    int grid = (num_sms / 8) * 8;
+    if (grid < 8) grid = 8;
+    if ((int64_t)grid > tiles * 8) grid = (int)(tiles * 8);
+    const int groups = grid / 8;
+    const int64_t stride = ((tiles + groups - 1) / groups + X2_WINDOW - 1) / X2_WINDOW + 1;
+    p.sync = nullptr; p.sync_stride = (int)std::min<int64_t>(stride, 1 << 30);
+    if (sync && stride < (1 << 30) && sizeof(int) * (size_t)groups * stride <= sync_bytes) {
+        p.sync = sync;
+        B200VAD_CUDA(cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)groups * stride, st));
+    }
+    static bool attr = false;
+    if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_xg_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    prof_begin(1, st);
+    gemm_xg_pair_kernel<<<grid, XP_THREADS, smem, st>>>(tm_a, tm_b, p);
+    prof_end(1, st);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
 }
 
 // LSTM input projection (mode 3): x planes (B, T, K) with row pitch lda -> xg in the step-blocked layout described at

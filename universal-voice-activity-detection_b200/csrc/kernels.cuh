@@ -27,7 +27,9 @@ int fbank_launch(const void* wav, int wav_i16, const int32_t* lens, int B, int64
                  __half* feats_lo, int64_t T_out, double* row_sums, int device, cudaStream_t stream);
 int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, int T, cudaStream_t stream);
 int lstm_tc_set_tile(int nb);
-int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st);
+// Scale s of the (x1, x2) activation planes of the 2-MMA projection: x1 = fp16((1 - s) x), x2 = fp16(x - x1) (gemm_tc.cu)
+constexpr float kPlaneScale = 0.015625f;   // 2^-6
+int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, int scaled_planes, cudaStream_t st);
 int gemm_ts_launch(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, int K, const __half* w_hi, const __half* w_lo,
                    int Kp, int ldw, int N, const float* bias, int mode, int accumulate, float* c, __half* o_hi, __half* o_lo,
                    int64_t ldc, int num_sms, cudaStream_t st, const float* wc = nullptr, const float* bc = nullptr);
@@ -35,6 +37,12 @@ int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stri
                         int K, const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias,
                         int accumulate, int act_abs, float* c, int64_t ldc, int64_t out_batch_rows, int out_row_step,
                         int out_row_off, int num_sms, cudaStream_t st);
+int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
+                    const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
+                    size_t sync_bytes, int num_sms, cudaStream_t st);
+int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int K, const __half* w_hi,
+                        const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
+                        size_t sync_bytes, int num_sms, cudaStream_t st);
 int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
                       const __half* w_lo, int Kp, int ldw, const float* bias, int accumulate, float* xg, int num_sms,
                       cudaStream_t st);

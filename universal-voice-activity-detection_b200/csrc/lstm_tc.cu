@@ -70,6 +70,7 @@ struct LstmTcParams {
     const __half* whh;     // [2][512][128]
     int B, T;
     int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
+    float h1_scale;        // first plane of h = fp16(h1_scale * h), second = fp16(h - first): 1 (hi / lo) or 1 - kPlaneScale
 };
 
 template <int PARTS, int NB>
@@ -269,7 +270,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     const f32x2 hv2 = mul2(add2(ec, mone), rcp2(mul2(add2(eo, one), add2(ec, one))));
                     float hv0, hv1;
                     unpack2(hv2, hv0, hv1);
-                    const __half hh0 = __float2half_rn(hv0), hh1 = __float2half_rn(hv1);
+                    // planes: fp16(h1_scale * h) and the remainder (h1_scale = 1: hi / lo; 1 - 2^-6: the 2-MMA projection's split)
+                    const __half hh0 = __float2half_rn(hv0 * p.h1_scale), hh1 = __float2half_rn(hv1 * p.h1_scale);
                     const __half hl0 = __float2half_rn(hv0 - __half2float(hh0)), hl1 = __float2half_rn(hv1 - __half2float(hh1));
                     unsigned char* dst0 = h_hi + n * 128 + ((uc ^ (n & 7)) << 4);
                     unsigned char* dst1 = h_hi + (n + 1) * 128 + ((uc ^ ((n + 1) & 7)) << 4);
@@ -295,8 +297,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
 }
 
 // xg: step-blocked [ceil(B/64)][2][T][4][16][128][4] fp32 as gemm_ts_xg_launch writes it; whh: [2][512][128] fp16 (gate-major rows, as nn.LSTM stores weight_hh).
-// Output: the layer output as fp16 planes y_hi / y_lo [B][T][256].
-int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, cudaStream_t st) {
+// Output: the layer output as fp16 planes y_hi / y_lo [B][T][256] (hi / lo split, or the scaled (x1, x2) split of the
+// 2-MMA projection when scaled_planes is set; either way the planes sum to the fp32 value).
+int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_lo, int B, int T, int scaled_planes, cudaStream_t st) {
     if (B <= 0 || T <= 0) return B200VAD_OK;
     CUtensorMap tm_x, tm_yh, tm_yl;
     // xg is step-blocked (gemm_ts mode 3): [sequence block][dir][t][gate 4][column group 16][unit 128][4] fp32.  Viewed as
@@ -331,7 +334,7 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     if (rc) return rc;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200VAD_LSTM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    LstmTcParams p{whh, B, T, dbg};
+    LstmTcParams p{whh, B, T, dbg, scaled_planes ? 1.f - kPlaneScale : 1.f};
     typedef void (*KernFn)(CUtensorMap, CUtensorMap, CUtensorMap, LstmTcParams);
     static const KernFn kerns[3] = {lstm_tc_kernel<2, 64>, lstm_tc_kernel<4, 64>, lstm_tc_kernel<1, 16>};
     static const int smems[3] = {LstmGeom<64>::SMEM, LstmGeom<64>::SMEM, LstmGeom<16>::SMEM};
