@@ -38,16 +38,17 @@ N_SAMPLES = int(SECONDS * 16000)
 T_FRAMES = (N_SAMPLES + 80) // 160
 # Per-kernel algorithmic work per FRAME (10 ms of one utterance; 3 276 800 frames per launch at 4096 x 8 s), DESIGN.md
 # section 4.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture
-# (profiles/r01_ncu_full_summary.md; average over the launches of a kind), bytes per launch at 4096 x 8 s.  `executed_over_algorithmic`: the split-precision
-# products execute 3 (GEMM) / 2 (recurrence: h_hi, h_lo) fp16 MMAs per algorithmic one.
+# (profiles/r01_ncu_full_summary_v8.md; average over the launches of a kind), bytes per launch at 4096 x 8 s.  `executed_over_algorithmic`: the split-precision
+# products execute 3 (layer-0 projection, head) / 2 (layer 1-3 projections; recurrence: two h planes) fp16 MMAs per algorithmic one.
 KERNELS = {
     0: {"name": "lstm_tc_kernel (LSTM recurrence, 4 launches/step)", "bound": "hbm", "tensor": True,
         # per layer: xg read 2 x 512 x 4 B + y planes written 2 x 128 x (2 + 2) B
         "bytes_per_frame": 4096 + 1024, "flop_per_frame": 2 * 2 * 512 * 128, "executed_over_algorithmic": 2.0, "traffic": 16.76e9},
-    1: {"name": "gemm_ts_kernel<0> (input projections, 4 launches/step)", "bound": "tensor", "tensor": True,
-        # per layer (1-3): x planes read 256 x 4 B + xg written 1024 x 4 B; layer 0 reads 80 x 4 B
+    1: {"name": "gemm_xg_pair_kernel (input projections, 4 launches/step)", "bound": "hbm", "tensor": True,
+        # per layer (1-3): x planes read 256 x 4 B + xg written 1024 x 4 B; layer 0 reads 80 x 4 B.  Bound by the xg write
+        # stream (and, at 1.3 GHz under the power cap, 81 % of the sustained tensor peak: profiles/r01_ncu_full_summary_v8.md)
         "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
-        "executed_over_algorithmic": 3.0, "traffic": 18.1e9},
+        "executed_over_algorithmic": (3 * 80 + 2 * 3 * 256) / (80 + 3 * 256.0), "traffic": (14.76e9 + 3 * 16.76e9) / 4},
     2: {"name": "gemm_ts_kernel<1,4> (head linears + classifier, 2 launches/step)", "bound": "hbm", "tensor": True,
         # y planes 1024 B read -> z1 planes 512 B written, read again -> 4 B probability (classifier fused)
         "bytes_per_frame": (1024 + 512 + 512 + 4) / 2.0, "flop_per_frame": 2 * (256 * 128 + 128 * 128) / 2.0,
@@ -344,7 +345,7 @@ def main():
                     "unit": "TFLOP/s", "frac": dent["tflops"] / peaks["tf_sustained"], "traffic": dent["traffic"],
                     "executed_frac": dent["tensor_frac"],
                     "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); `achieved` counts ALGORITHMIC "
-                                   "FLOPs, the split-precision product executes 3 fp16 MMAs per algorithmic one (executed_frac)"}
+                                   "FLOPs, the split-precision products execute 2-3 fp16 MMAs per algorithmic one (executed_frac)"}
         roof.update({"launches": int(n), "avg_launch_ms": tms / max(n, 1), "share_of_step": dent["share_of_step"],
                      "algorithmic_per_launch": "bytes (or FLOPs) per frame below x 3 276 800 frames per launch (DESIGN.md section 4)",
                      "kernels": kernels})

@@ -556,7 +556,7 @@ gemm_xg2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // fill are halved; accumulators, epilogue and xg layout are those of gemm_ts_kernel<3>.
 // terms = 3: planes are (hi, lo), weights (W_hi, W_lo);  terms = 2: planes are the scaled (x1, x2) split, weights
 // (W_hi, W') -- see gemm_xg2_kernel.
-constexpr int XP_THREADS = 192;                       // TMA, MMA, 4 epilogue warps
+constexpr int XP_THREADS = 320;                       // TMA, MMA, 8 epilogue warps
 constexpr int XP_STAGES = 10;
 constexpr int XP_HALF_BYTES = 64 * SBK * 2;           // 8 KB: 32 sequences x 2 steps x 64 k
 
@@ -579,8 +579,8 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     auto bar_a_full = [&](int s) { return bar_base + 8 * s; };                // even CTA's: both CTAs' TMA bytes (tx) + 1
     auto bar_a_empty = [&](int s) { return bar_base + 128 + 8 * s; };         // both CTAs': MMAs retired (multicast commit)
     auto bar_acc_full = [&](int b) { return bar_base + 256 + 8 * b; };        // both CTAs' (multicast commit)
-    auto bar_acc_empty = [&](int b) { return bar_base + 272 + 8 * b; };       // even CTA's: 256 epilogue threads of the pair
-    const uint32_t bar_w = bar_base + 288;                                    // even CTA's: 256 weight loaders
+    auto bar_acc_empty = [&](int b) { return bar_base + 272 + 8 * b; };       // even CTA's: 512 epilogue threads of the pair
+    const uint32_t bar_w = bar_base + 288;                                    // even CTA's: 512 weight loaders
     const uint32_t tmem_slot = bar_base + 296;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -591,8 +591,8 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < XP_STAGES; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 256); }
-        mbar_init(bar_w, 256);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 512); }
+        mbar_init(bar_w, 512);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
@@ -672,15 +672,16 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
         }
     } else {
-        // ===================== weights -> own TMEM, then epilogue (warps 2..5 -> lane quarters 2,3,0,1) =====================
-        const int q = warp & 3;
+        // ===================== weights -> own TMEM, then epilogue =====================
+        // 8 warps: warp w owns TMEM lane quarter w & 3 (hardware rule) and column half (w - 2) >> 2 of every accumulator
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int unit = q * 32 + lane;
         const int out = blk * 128 + unit;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         {
             const uint4* whi = reinterpret_cast<const uint4*>(p.w_hi + (size_t)out * p.ldw);
             const uint4* wlo = reinterpret_cast<const uint4*>(p.w_lo + (size_t)out * p.ldw);
-            for (int part = 0; part < p.kb * 2; ++part) {                       // 32 fp16 = 16 packed columns
+            for (int part = half; part < p.kb * 2; part += 2) {                 // 32 fp16 = 16 packed columns
                 uint32_t ra[16], rb[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -719,27 +720,16 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int t0 = tp * 2;
             float* base = p.xg + ((((int64_t)bblk * 2 + dir) * p.T + t0) * 4 + gate) * 8192 + unit * 4;
             const bool t1_ok = t0 + 1 < p.T;
-#pragma unroll 1
-            for (int c = 0; c < SBM / 32; ++c) {
-                float v[32];
-                tmem_ld32(lane_addr + ACC_COL + ab * SBM + c * 32, v);
-                tmem_ld_wait();
-                if (c == SBM / 32 - 1) {
-                    tc_fence_before();
-                    mbar_arrive_cluster(ab ? acc_empty1 : acc_empty0);
-                }
-                // accumulator column j = sequence * 2 + step (columns [0, 64) come from the even CTA's half tile)
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-#pragma unroll
-                    for (int tl = 0; tl < 2; ++tl) {
-                        if (tl == 1 && !t1_ok) continue;
-                        float4* dst = reinterpret_cast<float4*>(base + (int64_t)tl * 4 * 8192 + ((c * 4 + g4) * 128) * 4);
-                        *dst = make_float4(v[8 * g4 + tl] + bias, v[8 * g4 + 2 + tl] + bias, v[8 * g4 + 4 + tl] + bias,
-                                           v[8 * g4 + 6 + tl] + bias);
-                    }
-                }
-            }
+            // both 32-column chunks of this warp's half are fetched before the first store is issued
+            // (accumulator columns [0, 64) come from the even CTA's half tile)
+            float v0[32], v1[32];
+            tmem_ld32(lane_addr + ACC_COL + ab * SBM + half * 64, v0);
+            tmem_ld32(lane_addr + ACC_COL + ab * SBM + half * 64 + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_cluster(ab ? acc_empty1 : acc_empty0);
+            xg_store_chunk(base, half * 2, v0, bias, t1_ok);
+            xg_store_chunk(base, half * 2 + 1, v1, bias, t1_ok);
         }
     }
     tc_fence_before();
