@@ -10,18 +10,22 @@ Who may import it: ``tests/``, ``__graft_entry__.smoke()`` and the
 as the timed CPU baseline, never as part of the product path.  Nothing under
 ``universal-voice-activity-detection_b200/`` imports it.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- and its own modules cannot be imported in this image
-(pytorch_lightning, lhotse, asteroid_filterbanks, torchmetrics, ml_collections
-are absent, no network).  The oracle is therefore pinned only by (a) being built
-from the very same torch / scipy primitives the reference calls (nn.LSTM,
-nn.Linear, nn.Conv1d, nn.InstanceNorm1d, nn.MaxPool1d, torch.fft.rfft,
-scipy.signal.medfilt), (b) the structural constants the reference states
-(293 SincNet frames / 5 s, receptive field 991 / step 270, 500 fbank frames
-/ 5 s), and (c) cross-checks against torchaudio's Kaldi mel banks.  Third-party
-arithmetic restated from upstream knowledge: lhotse ``Fbank`` (un-pinned editable
-checkout, requirements.txt:13) and asteroid-filterbanks==0.4 ``ParamSincFB``
-(requirements.txt:1).
+PINNING.  The reference ships no tests, golden vectors or fixtures and its modules do not
+import as they are in this image (pytorch_lightning, lhotse, asteroid_filterbanks, torchmetrics, ml_collections are
+absent, no network).  What pins the oracle:
+  * PINNED against outputs of the reference's OWN code run in this container (tests/golden/make_reference_golden.py:
+    the reference modules are imported from /root/reference with inert stubs for the absent packages, which carry no
+    arithmetic on these paths; fixtures tests/golden/reference_golden.{npz,json}; checked by
+    tests/test_reference_golden.py): PyanNet2 construction + forward and VadModel.forward / predict_step (models.py),
+    median_filter, the RLE + seconds arithmetic of both time bases, merge / split, the DER helpers (postproc.py), the
+    frame arithmetic (receptive_field.py).  Under manual_seed(42) the oracle's weights equal the reference's bit for bit.
+  * PARITY UNPINNED for the two pieces whose arithmetic lives in third-party code that is not under /root/reference:
+    lhotse ``Fbank`` (un-pinned editable checkout, requirements.txt:13; fbank.py) and asteroid-filterbanks==0.4
+    ``ParamSincFB`` (requirements.txt:1; the filter synthesis inside models.SincNet -- the rest of SincNet is
+    torch modules).  Those are restated from upstream knowledge and held by (a) being built from the same torch
+    primitives (torch.fft.rfft, nn.Conv1d, nn.InstanceNorm1d, nn.MaxPool1d), (b) the structural constants the reference
+    states (293 SincNet frames / 5 s, receptive field 991 / step 270, 500 fbank frames / 5 s) and (c) a bit-for-bit
+    check of the Kaldi mel banks against torchaudio.
 """
 
 from .fbank import lhotse_fbank, kaldi_mel_banks, povey_window, num_fbank_frames  # noqa: F401

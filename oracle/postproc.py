@@ -7,6 +7,8 @@ TEST INFRASTRUCTURE ONLY.  Follows
   src/scripts/predict_sincnet.py:348-370,492-504 run-length encoding, SincNet time base
   src/scripts/predict.py:614-647                 merge_intervals_with_buffer, split_into_windows
   src/scripts/predict.py:654-673                 get_binary_tensor / false alarm / missed detection
+PINNED: every function here is checked against the output of the reference's own code on seeded inputs
+(tests/golden/make_reference_golden.py -> tests/golden/reference_golden.npz, tests/test_reference_golden.py).
 """
 
 from __future__ import annotations

@@ -1,0 +1,328 @@
+"""Generates tests/golden/reference_*.npz / .json by running the REFERENCE'S OWN CODE, unmodified, from where it lies
+under /root/reference (read-only), in this container.  Run:  python tests/golden/make_reference_golden.py
+
+The reference's modules import third-party packages that are not installed here (pytorch_lightning, lhotse,
+torchmetrics, ml_collections, asteroid_filterbanks, wandb ...).  None of them contributes arithmetic to
+the functions pinned below -- they provide a base class, metric objects, a config container and manifest types -- so
+they are replaced by inert stub modules installed in sys.modules before the import:
+  * pytorch_lightning.LightningModule -> nn.Module + `save_hyperparameters(*names)` (captures the named locals of the
+    calling __init__ into `self.hparams`, as Lightning does) + no-op `log` / `log_dict`;
+  * ml_collections.ConfigDict -> a dict with attribute access;
+  * everything else (lhotse.*, torchmetrics.*, asteroid_filterbanks.*, wandb, s3prl ...) -> modules whose every attribute
+    is a dummy class.
+Two more shims, both outside the arithmetic:
+  * `median_filter` ends with a hard-coded `.to("cuda")` (src/utils/helper.py:95); there is no GPU here, so while the
+    reference runs `torch.Tensor.to` maps the device "cuda" to "cpu";
+  * the run-length extraction of `get_new_cuts` (src/scripts/predict.py:472-490) is a loop inside a 200-line function
+    that needs lhotse cut objects; its `for k, value in enumerate(obj["tensor"])` statement and the trailing-run block
+    are lifted from the file's syntax tree and executed verbatim on a seeded stream.  `merge_intervals_with_buffer`,
+    `split_into_windows`, `get_binary_tensor`, `get_false_alarm`, `get_missed_detection` (predict.py:614-673) and
+    `get_timestamp_from_sample_boundary` (predict_sincnet.py:492-504) are function definitions compiled from the
+    reference files' syntax trees the same way (importing those scripts would pull in the data modules).
+What is pinned: PyanNet2 construction order / forward (a2), VadModel.forward / predict_step (a6), median_filter (a7),
+the RLE and its seconds arithmetic (a8, a8'), merge / split (a10), the frame arithmetic (a5), load_config (a12) and the
+DER helpers (f1).  What is NOT (arithmetic lives in absent third-party code): lhotse Fbank (a1) and asteroid's
+ParamSincFB filters inside SincNet (a3 / a4).
+
+The fixtures cannot be regenerated on the GPU box (/root/reference does not exist there); tests only read them.
+"""
+import ast
+import hashlib
+import importlib.abc
+import importlib.machinery
+import inspect
+import json
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+STUB_ROOTS = ("pytorch_lightning", "lhotse", "torchmetrics", "ml_collections", "asteroid_filterbanks", "wandb", "s3prl",
+              "lightning", "jiwer", "whisper", "pyannote", "speechbrain", "torchaudio_stub")
+
+
+class _HParams(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class LightningModule(nn.Module):
+    """nn.Module + the two Lightning services the reference models use."""
+
+    def save_hyperparameters(self, *names):
+        frame = inspect.currentframe().f_back
+        if not hasattr(self, "_hp"):
+            object.__setattr__(self, "_hp", _HParams())
+        for n in names:
+            self._hp[n] = frame.f_locals[n]
+
+    @property
+    def hparams(self):
+        return self._hp
+
+    def log(self, *a, **k):
+        pass
+
+    def log_dict(self, *a, **k):
+        pass
+
+
+class ConfigDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    __setattr__ = dict.__setitem__
+
+
+class _Dummy:
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return None
+
+
+class _StubModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        if self.__name__ == "pytorch_lightning" and name == "LightningModule":
+            return LightningModule
+        if self.__name__ == "ml_collections" and name == "ConfigDict":
+            return ConfigDict
+        cls = type(name, (_Dummy,), {})
+        setattr(self, name, cls)
+        return cls
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StubModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def _lift(path, names):
+    """Compile the named top-level function definitions of a reference file, unmodified, into a namespace."""
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "math": math, "np": np}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in body} == set(names), (path, names)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def _lift_rle(path):
+    """The RLE statements of get_new_cuts (predict.py:471-490): `start = None`, the frame loop, the trailing-run block."""
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "get_new_cuts")
+    for node in ast.walk(fn):
+        if not isinstance(node, ast.For):
+            continue
+        for i, st in enumerate(node.body):
+            if (isinstance(st, ast.For) and isinstance(st.iter, ast.Call) and getattr(st.iter.func, "id", "") == "enumerate"
+                    and "obj" in ast.unparse(st.iter) and "tensor" in ast.unparse(st.iter)):
+                stmts = [node.body[i - 1], st, node.body[i + 1]]
+                assert ast.unparse(stmts[0]).strip() == "start = None" and isinstance(stmts[2], ast.If)
+                return compile(ast.Module(body=stmts, type_ignores=[]), path, "exec"), (stmts[0].lineno, stmts[2].end_lineno)
+    raise RuntimeError("RLE loop not found")
+
+
+def state_hash(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def spread(vm, x):
+    """Rescale the classifier so that the logits on x have zero mean and unit spread."""
+    p = vm(x).double()
+    z = torch.log(p / (1 - p))
+    scale = (1.0 / z.std().clamp_min(1e-9)).float()
+    cls = vm.model.classifier
+    cls.bias.copy_((cls.bias - z.mean().float()) * scale)
+    cls.weight.mul_(scale)
+
+
+def main():
+    assert os.path.isdir(REF), "the reference tree is needed to regenerate these fixtures"
+    torch.set_num_threads(1)
+    sys.meta_path.insert(0, _StubFinder())
+    sys.path.insert(0, REF)
+    orig_to = torch.Tensor.to
+
+    def to_cpu_for_cuda(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        return orig_to(self, *a, **k)
+
+    from src.engines.vad_engine import VadModel                      # the reference's own modules
+    from src.models.segmentation.PyanNet2 import PyanNet2
+    from src.utils.helper import median_filter
+    from src.utils import receptive_field as rf
+    from config.config import load_config
+
+    out, meta = {}, {"reference_files": {}}
+
+    # ---- a2 / a6: PyanNet2 through VadModel, seed 42 (config/config.py:11), fbank-dim input
+    g = torch.Generator().manual_seed(123)
+    feats = torch.randn(3, 120, 80, generator=g) * 3 - 5
+    labels = (torch.rand(3, 120, generator=g) > 0.5).float()
+    torch.manual_seed(42)
+    vm = VadModel("PyanNet2", {"encoding_dim": 80}).eval()
+    meta["pyannet2_d80_seed42_state_sha256"] = state_hash(vm.state_dict())
+    meta["pyannet2_d80_state_keys"] = {k: list(v.shape) for k, v in vm.state_dict().items()}
+    with torch.no_grad():
+        out["d80_feats"] = feats.numpy()
+        out["d80_labels"] = labels.numpy()
+        out["d80_prob"] = vm(feats).numpy()
+        torch.Tensor.to = to_cpu_for_cuda
+        try:
+            out["d80_predict"] = vm.predict_step({"inputs": feats, "is_voice": labels}, 0).numpy()
+        finally:
+            torch.Tensor.to = orig_to
+    # the same with a classifier rescaled (a parameter change, not a code change) so that the logits are ~N(0, 1): the
+    # decisions of a random-init model are otherwise constant
+    with torch.no_grad():
+        spread(vm, feats)
+        out["d80_spread_cls_w"] = vm.model.classifier.weight.numpy().copy()
+        out["d80_spread_cls_b"] = vm.model.classifier.bias.numpy().copy()
+        out["d80_spread_prob"] = vm(feats).numpy()
+        torch.Tensor.to = to_cpu_for_cuda
+        try:
+            out["d80_spread_predict"] = vm.predict_step({"inputs": feats, "is_voice": labels}, 0).numpy()
+        finally:
+            torch.Tensor.to = orig_to
+
+    # ---- a2: a small PyanNet2 with every weight stored (independent of the RNG stream): monolithic and layer-wise LSTMs
+    for tag, mono in (("tiny_mono", True), ("tiny_split", False)):
+        torch.manual_seed(7)
+        m = PyanNet2(lstm={"hidden_size": 8, "num_layers": 2, "monolithic": mono}, linear={"hidden_size": 6, "num_layers": 2},
+                     encoding_dim=5)
+        m.build()
+        m.eval()
+        x = torch.randn(2, 17, 5, generator=g)
+        with torch.no_grad():
+            out[f"{tag}_x"] = x.numpy()
+            out[f"{tag}_prob"] = m(x).numpy()
+        for k, v in m.state_dict().items():
+            out[f"{tag}_w_{k}"] = v.numpy()
+
+    # ---- a6: SSL-dim model -> median window 25 (vad_engine.py:207)
+    torch.manual_seed(42)
+    vm768 = VadModel("PyanNet2", {"encoding_dim": 768}).eval()
+    meta["pyannet2_d768_seed42_state_sha256"] = state_hash(vm768.state_dict())
+    x768 = torch.randn(2, 60, 768, generator=g)
+    with torch.no_grad():
+        spread(vm768, x768)
+        out["d768_cls_w"] = vm768.model.classifier.weight.numpy().copy()
+        out["d768_cls_b"] = vm768.model.classifier.bias.numpy().copy()
+        out["d768_x"] = x768.numpy()
+        out["d768_prob"] = vm768(x768).numpy()
+        torch.Tensor.to = to_cpu_for_cuda
+        try:
+            out["d768_predict"] = vm768.predict_step({"inputs": x768, "is_voice": torch.zeros(2, 60)}, 0).numpy()
+        finally:
+            torch.Tensor.to = orig_to
+
+    # ---- a7: median_filter on its own (helper.py:66-97), both windows, ties / NaN / short rows
+    prob = torch.sigmoid(torch.cumsum(torch.randn(5, 400, generator=g), 1) * 0.3)
+    prob[0, 100] = 0.5
+    prob[1, 7] = float("nan")
+    short = torch.rand(3, 10, generator=g)
+    torch.Tensor.to = to_cpu_for_cuda
+    try:
+        out["mf_prob"] = prob.numpy()
+        out["mf_49"] = median_filter(prob.clone(), window=0.01).numpy()
+        out["mf_25"] = median_filter(prob.clone(), window=0.02).numpy()
+        out["mf_default"] = median_filter(prob.clone()).numpy()
+        out["mf_short_prob"] = short.numpy()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out["mf_short_49"] = median_filter(short.clone(), window=0.01).numpy()
+    finally:
+        torch.Tensor.to = orig_to
+
+    # ---- a5: frame arithmetic (receptive_field.py)
+    ns = [0, 250, 251, 260, 991, 1261, 16000, 80000, 128000, 960000, 57600000] + [int(v) for v in torch.randint(251, 200000, (20,), generator=g)]
+    out["rf_num_samples"] = np.array(ns, dtype=np.int64)
+    out["rf_num_frames"] = np.array([rf.get_num_frames(n) if n >= 251 else -1 for n in ns], dtype=np.int64)
+    out["rf_field_size"] = np.array([rf.receptive_field_size(k) for k in (1, 2, 3, 10, 293)], dtype=np.int64)
+    out["rf_conv1d"] = np.array([rf.conv1d_num_frames(n, 5, 1) for n in (5, 6, 100)] + [rf.conv1d_num_frames(n, 251, 10) for n in (251, 1000)],
+                                dtype=np.int64)
+
+    # ---- a8 / a8' / a10 / f1: predict.py and predict_sincnet.py pieces
+    pred_py = os.path.join(REF, "src/scripts/predict.py")
+    psinc_py = os.path.join(REF, "src/scripts/predict_sincnet.py")
+    fns = _lift(pred_py, ["merge_intervals_with_buffer", "split_into_windows", "get_binary_tensor", "get_false_alarm", "get_missed_detection"])
+    ts = _lift(psinc_py, ["get_timestamp_from_sample_boundary"])["get_timestamp_from_sample_boundary"]
+    rle_code, rle_lines = _lift_rle(pred_py)
+    meta["reference_files"]["rle_lines_predict_py"] = list(rle_lines)
+    streams = []
+    for i in range(6):
+        s = (torch.cumsum(torch.randn(700, generator=g), 0) > 0).long()
+        if i == 1:
+            s[-5:] = 1          # trailing run
+        if i == 2:
+            s[:] = 0
+        if i == 3:
+            s[:] = 1
+        if i == 4:
+            s = torch.tensor([0, 1, 0, 1, 1, 0, 1, 1, 1, 0, 0, 1], dtype=torch.long)   # runs of 1, 2, 3 and a trailing single
+        streams.append(s)
+    for i, s in enumerate(streams):
+        for fs_tag, fs in (("10ms", 0.01), ("20ms", 0.02)):
+            loc = {"obj": {"tensor": s}, "frame_shift": fs, "pred_intervals": [], "round": round, "len": len, "enumerate": enumerate}
+            exec(rle_code, loc)
+            out[f"rle{i}_{fs_tag}_stream"] = s.numpy().astype(np.uint8)
+            out[f"rle{i}_{fs_tag}_intervals"] = np.array(loc["pred_intervals"], dtype=np.float64).reshape(-1, 2)
+    iv = [(5.2, 7.9), (0.3, 1.1), (1.05, 2.0), (30.0, 55.5), (7.9, 8.0), (59.5, 60.0)]
+    for b in (0, 0.25, 1.0):
+        out[f"merge_b{b}"] = np.array(fns["merge_intervals_with_buffer"](list(iv), 60.0, b), dtype=np.float64).reshape(-1, 2)
+    out["merge_in"] = np.array(iv, dtype=np.float64)
+    out["split10"] = np.array(fns["split_into_windows"]([[0.0, 35.05], [40.0, 40.05], [50.0, 60.1], [70.0, 80.0]], window=10), dtype=np.float64)
+    gt = fns["get_binary_tensor"]([(0.3, 1.1), (5.2, 7.9)], 10.0, 0.01)
+    pr = fns["get_binary_tensor"]([(0.5, 1.5), (5.0, 7.0), (9.0, 9.5)], 10.0, 0.01)
+    out["der_gt"], out["der_pred"] = gt.numpy(), pr.numpy()
+    out["der_fa_md"] = np.array([float(fns["get_false_alarm"](gt, pr)), float(fns["get_missed_detection"](gt, pr))], dtype=np.float64)
+    out["sinc_ts_in"] = np.array([(0, 10, 5), (3, 293, 5), (100, 3551, 60), (0, 0, 1), (59, 118, 2)], dtype=np.int64)
+    out["sinc_ts_out"] = np.array([ts(a, b, d) for a, b, d in out["sinc_ts_in"].tolist()], dtype=np.int64)
+
+    # ---- a12: load_config
+    cfg = load_config()
+    meta["config"] = {k: cfg[k] for k in ("seed", "device", "feature_extractor", "frame_shift", "model_name", "supported_models",
+                                          "max_epochs", "learning_rate") if k in cfg}
+    meta["config"]["model_dict"] = dict(cfg["model_dict"])
+    for k in ("max_duration", "batch_size"):
+        if k in cfg:
+            meta["config"][k] = cfg[k]
+    meta["torch_version"] = torch.__version__
+
+    np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
+    with open(os.path.join(HERE, "reference_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True, default=str)
+    print("reference fixtures written:", len(out), "arrays;", os.path.getsize(os.path.join(HERE, "reference_golden.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,8 @@ def load_config(feature_extractor: str = "fbank"):
         cfg.model_dict.encoding_dim = 80
     else:
         cfg.model_dict.encoding_dim = 768
+    cfg.max_epochs = 20                                 # training keys kept for completeness of the drop-in (config.py:36-40)
+    cfg.check_val_every_n_epoch = 3
     cfg.learning_rate = 1e-3
     cfg.batch_size = 80
     cfg.max_duration = 400
