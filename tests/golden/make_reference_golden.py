@@ -308,6 +308,71 @@ def main():
     out["sinc_ts_in"] = np.array([(0, 10, 5), (3, 293, 5), (100, 3551, 60), (0, 0, 1), (59, 118, 2)], dtype=np.int64)
     out["sinc_ts_out"] = np.array([ts(a, b, d) for a, b, d in out["sinc_ts_in"].tolist()], dtype=np.int64)
 
+    # ---- a8-a10 + f1 end to end: the reference's get_new_cuts (predict.py:412-612) on a synthetic manifest pair.
+    # lhotse's load_manifest_lazy is I/O glue (one JSON object per line): a 10-line reader stands in; per-recording values are
+    # captured by wrapping (not changing) the reference's helpers.
+    import contextlib
+    import gzip
+    import io
+    import src.scripts.predict as P
+
+    class _Obj(dict):
+        def __getattr__(self, k):
+            v = self[k]
+            return [_Obj(x) for x in v] if k == "supervisions" else v
+
+        def to_dict(self):
+            return dict(self)
+
+    def _load(path):
+        with gzip.open(path, "rt") as f:
+            return [_Obj(json.loads(line)) for line in f if line.strip()]
+
+    P.load_manifest_lazy = _load
+    mdir = os.path.join(HERE, "manifests")
+    os.makedirs(mdir, exist_ok=True)
+    durs = [4.99, 13.0, 0.5, 20.2, 7.77, 31.4]
+    recs, cuts = [], []
+    for i, d in enumerate(durs):
+        rec = {"id": f"rec{i}", "sources": [{"type": "file", "channels": [0], "source": f"rec{i}.wav"}], "sampling_rate": 16000,
+               "num_samples": int(round(d * 16000)), "duration": d, "channel_ids": [0]}
+        sups, t = [], 0.0
+        while True:
+            t += float(torch.rand(1, generator=g)) * 2.0
+            du = 0.2 + float(torch.rand(1, generator=g)) * 3.0
+            if t + du > d:
+                break
+            sups.append({"id": f"rec{i}-sup{len(sups)}", "recording_id": f"rec{i}", "start": round(t, 3), "duration": round(du, 3),
+                         "channel": 0, "text": f"utt {len(sups)}"})
+            t += du
+        recs.append(rec)
+        cuts.append({"id": f"rec{i}-0", "start": 0, "duration": d, "channel": 0, "supervisions": sups, "recording": rec, "type": "MonoCut"})
+    for name, items in (("recordings.jsonl.gz", recs), ("cuts.jsonl.gz", cuts)):
+        with gzip.open(os.path.join(mdir, name), "wt") as f:
+            for it in items:
+                f.write(json.dumps(it) + "\n")
+    nfr = sum(math.ceil(d / 0.01) + 1 for d in durs)
+    rows = (nfr + 499) // 500
+    preds = (torch.cumsum(torch.randn(rows * 500, generator=g), 0).reshape(rows, 500, 1) > 0).long()
+    out["gnc_preds"] = preds.numpy().astype(np.uint8)
+    orig = {k: getattr(P, k) for k in ("get_false_alarm", "get_missed_detection", "merge_intervals_with_buffer", "split_into_windows")}
+    meta["get_new_cuts"] = {}
+    for tag, buffer, split in (("b0", 0, False), ("b025_split", 0.25, True)):
+        log = {"fa": [], "md": [], "merged": [], "split": []}
+        P.get_false_alarm = lambda a, b, log=log: (log["fa"].append(float(orig["get_false_alarm"](a, b))), orig["get_false_alarm"](a, b))[1]
+        P.get_missed_detection = lambda a, b, log=log: (log["md"].append(float(orig["get_missed_detection"](a, b))), orig["get_missed_detection"](a, b))[1]
+        P.merge_intervals_with_buffer = lambda iv, d, b, log=log: (lambda r: (log["merged"].append([list(x) for x in r]), r)[1])(orig["merge_intervals_with_buffer"](iv, d, b))
+        P.split_into_windows = lambda iv, window=10, log=log: (lambda r: (log["split"].append([list(x) for x in r]), r)[1])(orig["split_into_windows"](iv, window=window))
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            P.get_new_cuts("synthetic", "test", preds, os.path.join(mdir, "recordings.jsonl.gz"), os.path.join(mdir, "cuts.jsonl.gz"),
+                           mdir, "unused.jsonl.gz", buffer=buffer, split=split, frame_shift=0.01)
+        for k, v in orig.items():
+            setattr(P, k, v)
+        meta["get_new_cuts"][tag] = {"buffer": buffer, "split": split, "fa": log["fa"], "md": log["md"],
+                                     "intervals": log["split"] if split else log["merged"], "report": buf.getvalue()}
+    meta["get_new_cuts"]["durations"] = durs
+
     # ---- a12: load_config
     cfg = load_config()
     meta["config"] = {k: cfg[k] for k in ("seed", "device", "feature_extractor", "frame_shift", "model_name", "supported_models",

@@ -124,3 +124,32 @@ def test_segments_match_reference(dev, ref):
     got = get_segments(d, None, 0.01)
     want = host.merge_intervals_with_buffer([tuple(r) for r in z["rle4_10ms_intervals"].tolist()], 0.12, 0)
     assert [list(x) for x in got[0]] == [list(x) for x in want]
+
+
+def test_get_new_cuts_matches_reference(dev, ref, golden_dir, tmp_path):
+    """The drop-in get_new_cuts (manifests in, GPU RLE + bit-mask scoring, report out) against the reference's own run of
+    predict.py:412-612 on the same manifests and prediction stream."""
+    from src.scripts.predict import get_new_cuts
+    from b200vad import manifests
+    z, meta = ref
+    g = meta["get_new_cuts"]
+    preds = torch.from_numpy(z["gnc_preds"].astype(np.int64)).to(dev)
+    rp, cp = os.path.join(golden_dir, "manifests", "recordings.jsonl.gz"), os.path.join(golden_dir, "manifests", "cuts.jsonl.gz")
+
+    def report_value(report, name):
+        line = next(l for l in report.splitlines() if l.startswith(name))
+        return float(line.split(":")[1].strip())
+
+    for tag in ("b0", "b025_split"):
+        want = g[tag]
+        out = get_new_cuts("synthetic", "test", preds, rp, cp, str(tmp_path), f"pred_{tag}.jsonl.gz", buffer=want["buffer"],
+                           split=want["split"], frame_shift=0.01, verbose=False)
+        assert [[list(x) for x in iv] for iv in out["intervals"]] == want["intervals"], tag
+        fa = [float(out["fa_frames"][i] / out["nframes"][i]) for i in range(len(want["fa"]))]
+        md = [float(out["md_frames"][i] / out["nframes"][i]) for i in range(len(want["md"]))]
+        assert fa == want["fa"] and md == want["md"], tag
+        for key, name in (("detection_error", "Detection Error Rate"), ("false_alarm", "False Alarm Rate"), ("missed_detection", "Missed Detection Rate")):
+            assert float(out[key]) == report_value(want["report"], name), (tag, key)
+        sups = manifests.load_manifest(out["output_path"])
+        assert len(sups) == sum(len(iv) for iv in want["intervals"])
+        assert all(s.recording_id.startswith("rec") and s.duration > 0 for s in sups)

@@ -171,3 +171,64 @@ def test_config_keys(ref):
         assert got == v, (k, got, v)
     assert load_config("fbank").frame_shift == 0.01 and load_config("fbank").model_dict.encoding_dim == 80
     assert load_config("sincnet").model_name == "PyanNet" and load_config("sincnet").model_dict.encoding_dim == 60
+
+
+def _report_value(report, name):
+    line = next(l for l in report.splitlines() if l.startswith(name))
+    return float(line.split(":")[1].strip().replace("tensor(", "").rstrip(")"))
+
+
+def test_get_new_cuts_chain(ref, golden_dir):
+    """The reference's whole get_new_cuts (predict.py:412-612) ran on tests/golden/manifests/*.jsonl.gz; the oracle's
+    slice -> RLE -> merge -> split -> binary tensors -> FA / MD chain and the manifest reader reproduce it."""
+    from b200vad import manifests
+    z, meta = ref
+    g = meta["get_new_cuts"]
+    recs = manifests.load_manifest(os.path.join(golden_dir, "manifests", "recordings.jsonl.gz"))
+    cuts = manifests.load_manifest(os.path.join(golden_dir, "manifests", "cuts.jsonl.gz"))
+    durs = [r.to_dict()["duration"] for r in recs]
+    assert durs == g["durations"] and [c.recording.id for c in cuts] == [r.id for r in recs]
+    preds = torch.from_numpy(z["gnc_preds"].astype(np.int64))
+    streams = oracle.slice_recordings(preds.reshape(-1), durs, 0.01)
+    for tag in ("b0", "b025_split"):
+        want = g[tag]
+        fa_avg = md_avg = 0
+        for i, s in enumerate(streams):
+            iv = oracle.merge_intervals_with_buffer(oracle.rle_segments(s.tolist(), 0.01), durs[i], want["buffer"])
+            if want["split"]:
+                iv = oracle.split_into_windows(iv, window=10)
+            assert [list(x) for x in iv] == want["intervals"][i], (tag, i)
+            gt = oracle.get_binary_tensor([(sup.start, sup.start + sup.duration) for sup in cuts[i].supervisions], durs[i], 0.01)
+            pr = oracle.get_binary_tensor(iv, durs[i], 0.01)
+            fa, md = oracle.get_false_alarm(gt, pr), oracle.get_missed_detection(gt, pr)
+            assert float(fa) == want["fa"][i] and float(md) == want["md"][i], (tag, i)
+            fa_avg, md_avg = fa_avg + fa, md_avg + md
+        assert abs(float(fa_avg / len(durs)) - _report_value(want["report"], "False Alarm Rate")) < 1e-7
+        assert abs(float(md_avg / len(durs)) - _report_value(want["report"], "Missed Detection Rate")) < 1e-7
+
+
+def test_manifest_round_trip(tmp_path, golden_dir):
+    from b200vad import manifests
+    recs = manifests.load_manifest(os.path.join(golden_dir, "manifests", "recordings.jsonl.gz"))
+    cuts = manifests.load_manifest(os.path.join(golden_dir, "manifests", "cuts.jsonl.gz"))
+    for name, items in (("r.jsonl.gz", recs), ("c.jsonl", cuts)):
+        p = str(tmp_path / name)
+        assert manifests.save_manifest(items, p) == len(items)
+        assert [x.to_dict() for x in manifests.load_manifest_lazy(p)] == [x.to_dict() for x in items]
+    c = cuts[1]
+    assert c.type == "MonoCut" and c.supervisions[0].recording_id == c.recording.id and c.supervisions[0].end > c.supervisions[0].start
+    # builders produce the same line layout the reference's manifests have
+    r = manifests.recording("rec0", 79840)
+    assert r.to_dict() == recs[0].to_dict()
+    sups = manifests.intervals_to_supervisions(["a", "b"], [[(0.5, 1.25)], [(0.0, 2.0), (3.0, 3.5)]])
+    assert [s.id for s in sups] == ["a-vad-0", "b-vad-0", "b-vad-1"] and sups[0].duration == 0.75 and sups[2].recording_id == "b"
+    cut = manifests.mono_cut("rec0-0", r, sups[:1])
+    assert cut.duration == r.duration and cut.supervisions[0].id == "a-vad-0"
+    # PCM WAV sources
+    x = (np.sin(np.arange(16000) * 0.05) * 12000).astype(np.int16)
+    wav = str(tmp_path / "audio" / "rec9.wav")
+    manifests.write_wav_pcm16(wav, x)
+    rec = manifests.recording("rec9", len(x), source="audio/rec9.wav")
+    assert np.array_equal(manifests.load_recording_pcm16(rec, root=str(tmp_path)), x)
+    with pytest.raises(ValueError):
+        manifests.load_recording_pcm16(dict(rec, sources=[{"type": "url", "source": "x"}]))

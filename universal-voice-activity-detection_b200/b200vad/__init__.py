@@ -13,6 +13,7 @@ from .runtime import HostSession, bind_to_gpu_numa, gather_segments, shard_range
 from . import synth  # noqa: F401
 from . import score  # noqa: F401
 from . import corpus  # noqa: F401
+from . import manifests  # noqa: F401
 from .longform import LongFormVad  # noqa: F401
 from .streaming import StreamingVad  # noqa: F401
 

@@ -1,9 +1,10 @@
 """Hot-path part of src/scripts/predict.py: per-recording slicing of the flat prediction stream
 (:447-458), run-length segment extraction (:472-490, on the GPU here), merge_intervals_with_buffer
-(:614-634), split_into_windows (:638-647), and a manifest-free ``predict_vad``.  The reference's
-``predict_vad(**config)`` reads lhotse manifests and checkpoints from hard-coded paths
-(:55-409, out of scope); this one takes in-memory waveforms."""
+(:614-634), split_into_windows (:638-647), ``get_new_cuts`` (:412-612: manifests in, detection-error report out) and a
+manifest-free ``predict_vad``.  The reference's ``predict_vad(**config)`` reads lhotse manifests and checkpoints from
+hard-coded paths (:55-409, out of scope); this one takes in-memory waveforms."""
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -67,6 +68,42 @@ def score_predictions(gt_intervals, pred_intervals, durations, frame_shift=0.01,
     Returns (detection_error_rate, false_alarm_rate, missed_detection_rate) averaged over recordings."""
     r = b200vad.score.detection_error(gt_intervals, pred_intervals, durations, frame_shift, device)
     return r["detection_error"], r["false_alarm"], r["missed_detection"]
+
+
+def get_new_cuts(dataset_name, phase, test_preds, recordings_path, cuts_path, predict_output_dir=None, output_filename=None,
+                 buffer=0, split=False, alignment_path=None, frame_shift=0.02, verbose=True):
+    """predict.py:412-612 with the reference's signature: the flat prediction stream is sliced per recording of the
+    recordings manifest (:447-458), turned into intervals (RLE :472-490 on the GPU, merge :492-494, optional 10 s split
+    :496-498) and scored against the supervisions of the i-th cut (:468-470, 500-509) with the bit-mask kernels; the
+    report of :590-610 is printed and returned.  Manifests are lhotse ``.jsonl(.gz)`` files (b200vad.manifests).  The
+    reference's writer of the new cut set is commented out (:511-588); here the predicted intervals are written as
+    SupervisionSegment lines to ``predict_output_dir / output_filename`` when both are given.  ``alignment_path`` (word
+    alignments for the commented-out writer) is accepted and ignored."""
+    from b200vad import manifests
+
+    recordings = [obj.to_dict() for obj in manifests.load_manifest_lazy(recordings_path)]
+    all_cuts = list(manifests.load_manifest_lazy(cuts_path))
+    assert len(all_cuts) >= len(recordings), "one cut per recording, in manifest order (predict.py:462-463)"
+    durations = [obj["duration"] for obj in recordings]
+    gt_intervals = [[(sup.start, sup.start + sup.duration) for sup in all_cuts[i].supervisions] for i in range(len(recordings))]
+    pred_intervals = get_segments(test_preds, durations, frame_shift, buffer=buffer, split=split)
+    r = b200vad.score.detection_error(gt_intervals, pred_intervals, durations, frame_shift, test_preds.device)
+    out = {"detection_error": r["detection_error"], "false_alarm": r["false_alarm"], "missed_detection": r["missed_detection"],
+           "fa_frames": r["fa_frames"], "md_frames": r["md_frames"], "nframes": r["nframes"], "intervals": pred_intervals,
+           "total_supervisions": sum(len(c.supervisions) for c in all_cuts)}
+    if predict_output_dir is not None and output_filename is not None:
+        sups = manifests.intervals_to_supervisions([obj["id"] for obj in recordings], pred_intervals)
+        out["output_path"] = os.path.join(predict_output_dir, output_filename)
+        manifests.save_manifest(sups, out["output_path"])
+    if verbose:
+        print(f"Dataset: {dataset_name}, Buffer: {buffer}, Phase: {phase}")
+        print("\n")
+        print(f"Detection Error Rate: {out['detection_error']}")
+        print(f"False Alarm Rate: {out['false_alarm']}")
+        print(f"Missed Detection Rate: {out['missed_detection']}")
+        print("----------------")
+        print(f"Total Supervisions: {out['total_supervisions']}")
+    return out
 
 
 @torch.no_grad()
