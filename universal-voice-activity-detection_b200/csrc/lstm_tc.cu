@@ -262,7 +262,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     const f32x2 dig = mul2(di, dg);
                     float2* const cptr = reinterpret_cast<float2*>(cst + (n >> 1) * (2 * kHidden));
                     const float2 cold = *cptr;
-                    const f32x2 cn = mul2(fma2(pack2(cold.x, cold.y), dig, mul2(add2(eg, mone), df)), rcp2(mul2(df, dig)));
+                    const f32x2 den = mul2(df, dig);
+                    const f32x2 cn = mul2(fma2(pack2(cold.x, cold.y), dig, mul2(add2(eg, mone), df)), (p.flags & 8) ? rcp2_fma(den) : rcp2(den));
                     float cn0, cn1;
                     unpack2(cn, cn0, cn1);
                     *cptr = make_float2(cn0, cn1);
