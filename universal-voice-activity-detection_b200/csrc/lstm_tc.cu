@@ -69,7 +69,7 @@ int lstm_tc_set_tile(int nb) {
 struct LstmTcParams {
     const __half* whh;     // [2][512][128]
     int B, T;
-    int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs
+    int flags;             // debug ablations (B200VAD_LSTM_DEBUG): 1 = no xg, 2 = no MMAs, 4 = no h_lo MMAs, 8 = first reciprocal on the FMA pipe
     float h1_scale;        // first plane of h = fp16(h1_scale * h), second = fp16(h - first): 1 (hi / lo) or 1 - kPlaneScale
 };
 
