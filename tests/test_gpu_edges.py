@@ -141,3 +141,54 @@ def test_pcm16_input_equals_converted_float(dev, blob):
     p0, d0, s0, _ = torch.ops.b200vad.vad_pipeline(pcm.to(dev), None, b, 4, 0.5, 49)
     assert torch.equal(out["prob"], p0.cpu()) and torch.equal(out["dec"], d0.cpu()) and torch.equal(out["seg"], s0.cpu())
     sess.close()
+
+
+def test_pipeline_properties_at_the_baseline_size(dev):
+    """BASELINE configs[1] (4096 x 8 s) is too large for the CPU oracle; size-independent properties instead: a row's
+    result does not depend on the batch around it (sub-batches anywhere in the batch reproduce their rows bit for bit),
+    runs are bit-identical, decisions are the median filter of the probabilities, the segment list is the ordered RLE of the
+    decisions, and a spot-checked handful of rows matches the oracle."""
+    import b200vad
+    import oracle
+    B, N, T = 4096, 128000, 800
+    # bursts of a harmonic under slow on / off modulation over a noise floor, generated on the device
+    g = torch.Generator(device=dev).manual_seed(21)
+    t = torch.arange(N, device=dev, dtype=torch.float32) / 16000.0
+    f0 = 90.0 + 160.0 * torch.rand(B, 1, generator=g, device=dev)
+    am = (torch.sin(2 * torch.pi * (0.3 + torch.rand(B, 1, generator=g, device=dev)) * t + 6.28 * torch.rand(B, 1, generator=g, device=dev)) > 0).float()
+    wav = 0.1 * am * torch.sin(2 * torch.pi * f0 * t) + 0.005 * torch.randn(B, N, generator=g, device=dev)
+    del t, am
+    feats_head = torch.ops.b200vad.fbank(wav[:16].contiguous(), None).cpu()
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=feats_head)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    prob, dec, seg, counts = torch.ops.b200vad.vad_pipeline(wav, None, blob, 4, 0.5, 49)
+    assert prob.shape == (B, T) and dec.shape == (B, T) and counts.shape == (B,)
+    assert torch.isfinite(prob).all() and 0.05 < dec.float().mean().item() < 0.95
+    # bit-identical second run
+    prob2, dec2, seg2, counts2 = torch.ops.b200vad.vad_pipeline(wav, None, blob, 4, 0.5, 49)
+    assert torch.equal(prob, prob2) and torch.equal(dec, dec2) and torch.equal(seg, seg2) and torch.equal(counts, counts2)
+    del prob2, dec2, seg2, counts2
+    # batch-position invariance: sub-batches cut anywhere (not on 64-row blocks) reproduce their rows exactly
+    for lo, hi in ((0, 70), (1000, 1100), (4031, 4096)):
+        p, d, s, c = torch.ops.b200vad.vad_pipeline(wav[lo:hi].contiguous(), None, blob, 4, 0.5, 49)
+        assert torch.equal(p, prob[lo:hi]) and torch.equal(d, dec[lo:hi]) and torch.equal(c, counts[lo:hi]), (lo, hi)
+    # decisions = threshold + median(49) of the probabilities (zero-padded ends): sliding sum of 49 >= 25
+    b = (prob >= 0.5).float()
+    win = torch.nn.functional.avg_pool1d(b.unsqueeze(1), 49, 1, 24, count_include_pad=True).squeeze(1) * 49
+    assert torch.equal((win.round() >= 25).to(torch.uint8), dec)
+    # segments = ordered runs (>= 2 frames) of the decisions
+    d8 = torch.nn.functional.pad(dec.to(torch.int8), (1, 1))
+    diff = d8[:, 1:] - d8[:, :-1]
+    starts, ends = (diff == 1).nonzero(), (diff == -1).nonzero()
+    assert starts.shape == ends.shape and torch.equal(starts[:, 0], ends[:, 0])
+    keep = ends[:, 1] - 1 > starts[:, 1]
+    want = torch.stack([starts[keep, 0], starts[keep, 1], ends[keep, 1] - 1], 1).to(torch.int32)
+    assert torch.equal(seg, want)
+    assert torch.equal(counts.long(), torch.bincount(want[:, 0].long(), minlength=B))
+    # spot check against the oracle
+    rows = [0, 63, 64, 2047, 4095]
+    with torch.no_grad():
+        ref = o(oracle.lhotse_fbank(wav[rows].cpu())).squeeze(-1)
+    err = util.prob_err(prob[rows].cpu(), ref)
+    print(f"full-size spot check: rel err of p on 5 rows {err:.2e}, {seg.shape[0]} segments")
+    assert err <= util.PROB_RTOL

@@ -727,7 +727,7 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             tmem_ld32(lane_addr + ACC_COL + ab * SBM + half * 64 + 32, v1);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive_cluster(ab ? acc_empty1 : acc_empty0);
+            mbar_arrive_cluster_relaxed(ab ? acc_empty1 : acc_empty0);
             xg_store_chunk(base, half * 2, v0, bias, t1_ok);
             xg_store_chunk(base, half * 2 + 1, v1, bias, t1_ok);
         }

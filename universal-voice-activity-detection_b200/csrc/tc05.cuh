@@ -159,8 +159,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    // relaxed: the data handed over is tensor memory (ordered by tcgen05.wait / tcgen05.fence); a release at cluster scope
-    // would add a MEMBAR that waits for all of this thread's outstanding global stores (measured: the top stall reason)
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// Relaxed form for hand-overs whose payload is tensor memory already ordered by tcgen05.wait / tcgen05.fence ("I am done
+// reading this accumulator"): a release at cluster scope adds a MEMBAR that waits for all of the thread's outstanding
+// global stores (measured in the projection epilogue: the top stall reason).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the mbarrier at the same offset in the
