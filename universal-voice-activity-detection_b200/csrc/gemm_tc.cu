@@ -566,6 +566,7 @@ struct GemmXpParams {
     const float* bias;       // [1024]
     float* xg;
     int T, tiles_per_blk, num_tiles, kb, ldw, terms;
+    int k16;                 // k-steps of 16 that hold real inputs (K rounded up to 16): the zero padding up to kb * 64 is skipped
     int* sync;               // [groups][sync_stride] window arrival counters (zeroed per launch) or null
     int sync_stride;
 };
@@ -655,6 +656,7 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint32_t x_a = a_base + (2 * s) * XP_HALF_BYTES, x_b = x_a + XP_HALF_BYTES;
 #pragma unroll
                     for (int k = 0; k < SBK / 16; ++k) {
+                        if (kb * 4 + k >= p.k16) break;                                        // zero padding of K
                         const uint32_t w_a = tmem_base + (kb * 4 + k) * 8, w_b = w_a + wcols;
                         const uint64_t dx_a = smem_desc_sw128(x_a + k * 32), dx_b = smem_desc_sw128(x_b + k * 32);
                         if (p.terms == 3) {
@@ -1000,6 +1002,7 @@ int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B
     if (!w_lo || (terms != 2 && terms != 3)) { set_error("gemm_xg_pair: needs both weight planes and terms 2 or 3"); return B200VAD_EINVAL; }
     GemmXpParams p;
     p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.xg = xg; p.T = T; p.kb = Kp / SBK; p.ldw = ldw; p.terms = terms;
+    p.k16 = (K + 15) / 16;
     p.tiles_per_blk = (T + 1) / 2;
     const int64_t tiles = (int64_t)((B + 63) / 64) * p.tiles_per_blk;
     if (tiles >= (1LL << 31)) { set_error("gemm_xg_pair: too many tiles"); return B200VAD_EINVAL; }
