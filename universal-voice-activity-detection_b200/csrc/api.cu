@@ -48,6 +48,20 @@ void prof_end(int kind, cudaStream_t st) {
     ++g_prof_used;
 }
 
+int set_max_dynamic_smem(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done[64];          // per device: (kernel, bytes already granted)
+    int dev = 0;
+    B200VAD_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64)
+        for (auto& e : done[dev])
+            if (e.first == func && e.second >= bytes) return B200VAD_OK;
+    B200VAD_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < 64) done[dev].push_back({func, bytes});
+    return B200VAD_OK;
+}
+
 static int g_impl = 2;        // 2 = tcgen05 kernels (default), 1 = warp-MMA kernels (validation only)
 static int g_proj_terms = 2;  // fp16 products per k-step of the layer >= 1 input projections: 2 (default) or 3 (validation)
 static int g_proj_kernel = 2;  // input projections with K <= 256: 0 = gemm_ts_kernel<3>, 1 = gemm_xg2_kernel, 2 = gemm_xg_pair_kernel (default)

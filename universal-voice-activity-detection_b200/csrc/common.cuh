@@ -18,6 +18,8 @@ void count_launch();                       // bumps the process-wide kernel-laun
 // live timing of the hot kernels (bench.py roofline): when enabled, every launch of kind
 // 0 = LSTM recurrence, 1 = input-projection GEMM, 2 = head GEMMs / warp-MMA GEMMs, 3 = fbank
 // is bracketed by CUDA events on its own stream
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); thread safe.  Returns a B200VAD_* code.
+int set_max_dynamic_smem(const void* func, int bytes);
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);
 

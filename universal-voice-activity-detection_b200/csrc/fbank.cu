@@ -409,14 +409,10 @@ fbank_kernel(const WT* __restrict__ wav, const int32_t* __restrict__ lens, int64
 template <typename WT>
 static int fbank_launch_t(const WT* wav, const int32_t* lens, int B, int64_t N, int64_t stride, float* feats, __half* feats_hi,
                           __half* feats_lo, int64_t T_out, double* row_sums, const FbankTables* tab, cudaStream_t stream) {
-    static bool attr_set = false;          // one flag per waveform type
-    if (!attr_set) {
-        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<false, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
-        B200VAD_CUDA(cudaFuncSetAttribute(fbank_kernel<true, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbankSmem)));
-        attr_set = true;
-    }
-    int rc = zero_f64_launch(row_sums, B, stream);
-    if (rc) return rc;
+    int rc;
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(fbank_kernel<false, WT>), (int)sizeof(FbankSmem)))) return rc;
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(fbank_kernel<true, WT>), (int)sizeof(FbankSmem)))) return rc;
+    if ((rc = zero_f64_launch(row_sums, B, stream))) return rc;
     dim3 g1((unsigned)((N + 256 * 32 - 1) / (256 * 32)), B);
     row_sum_kernel<WT><<<g1, 256, 0, stream>>>(wav, lens, N, stride, row_sums);
     B200VAD_LAUNCH_CHECK();

@@ -871,8 +871,7 @@ static int gemm_ts_run(int mode, const CUtensorMap& tm_a_hi, const CUtensorMap& 
     if (grid > max_grid) grid = (int)max_grid;
     typedef void (*KernFn)(CUtensorMap, CUtensorMap, GemmTsParams);
     static const KernFn kerns[5] = {gemm_ts_kernel<0>, gemm_ts_kernel<1>, gemm_ts_kernel<2>, gemm_ts_kernel<3>, gemm_ts_kernel<4>};
-    static bool attr[5] = {false, false, false, false, false};
-    if (!attr[mode]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[mode] = true; }
+    if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(kerns[mode]), smem)) return rc;
     const int prof_kind = (mode == 0 || mode == 3) ? 1 : 2;
     prof_begin(prof_kind, st);
     kerns[mode]<<<grid, GEMM_TS_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
@@ -982,8 +981,7 @@ int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, 
         p.sync = sync;
         B200VAD_CUDA(cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)groups * stride, st));
     }
-    static bool attr = false;
-    if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_xg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_xg2_kernel), smem))) return rc;
     prof_begin(1, st);
     gemm_xg2_kernel<<<grid, X2_THREADS, smem, st>>>(tm_a_hi, tm_a_lo, p);
     prof_end(1, st);
@@ -1023,8 +1021,7 @@ int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B
         p.sync = sync;
         B200VAD_CUDA(cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)groups * stride, st));
     }
-    static bool attr = false;
-    if (!attr) { B200VAD_CUDA(cudaFuncSetAttribute(gemm_xg_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_xg_pair_kernel), smem))) return rc;
     prof_begin(1, st);
     gemm_xg_pair_kernel<<<grid, XP_THREADS, smem, st>>>(tm_a, tm_b, p);
     prof_end(1, st);

@@ -136,11 +136,7 @@ lstm_recurrent_kernel(const float* __restrict__ xg, const __half* __restrict__ w
 }
 
 int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, int T, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200VAD_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RecSmem)));
-        attr_set = true;
-    }
+    if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(lstm_recurrent_kernel), (int)sizeof(RecSmem))) return rc;
     dim3 grid((B + RB - 1) / RB, 2);
     prof_begin(0, stream);
     lstm_recurrent_kernel<<<grid, RTHREADS, sizeof(RecSmem), stream>>>(xg, whh, y, B, T);

@@ -339,12 +339,11 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     typedef void (*KernFn)(CUtensorMap, CUtensorMap, CUtensorMap, LstmTcParams);
     static const KernFn kerns[3] = {lstm_tc_kernel<2, 64>, lstm_tc_kernel<4, 64>, lstm_tc_kernel<1, 16>};
     static const int smems[3] = {LstmGeom<64>::SMEM, LstmGeom<64>::SMEM, LstmGeom<16>::SMEM};
-    static bool attr[3] = {false, false, false};
     const int ki = nb == 16 ? 2 : (parts == 4 ? 1 : 0);
     const int smem = smems[ki];
     dim3 grid((B + nb - 1) / nb, 2);
     prof_begin(0, st);
-    if (!attr[ki]) { B200VAD_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[ki] = true; }
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(kerns[ki]), smem))) return rc;
     kerns[ki]<<<grid, LTC_THREADS, smem, st>>>(tm_x, tm_yh, tm_yl, p);
     prof_end(0, st);
     B200VAD_LAUNCH_CHECK();
