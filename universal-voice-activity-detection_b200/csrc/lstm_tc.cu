@@ -148,16 +148,20 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xg, const __grid_constant_
                     tc_fence_after();
                     if (s < T) {
                         if (!(p.flags & 2)) {
+                            // k-major issue order (the four gate accumulators alternate; the descriptors of a k-step are built once)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t d = tmem_base + q * LNB + h * LPN;
+                            for (int kk = 0; kk < 8; ++kk) {
+                                const uint32_t hb = hbuf + (kk >> 2) * H_TILE + h * (LPN * 128) + (kk & 3) * 32;
+                                const uint64_t d_lo = smem_desc_sw128(hb + 2 * H_TILE), d_hi = smem_desc_sw128(hb);
+                                if (!(p.flags & 4)) {
 #pragma unroll
-                                for (int kk = 0; kk < 8; ++kk) {
-                                    const uint32_t a = tmem_base + TMEM_W + q * 64 + kk * 8;
-                                    const uint32_t hb = hbuf + (kk >> 2) * H_TILE + h * (LPN * 128) + (kk & 3) * 32;
-                                    if (!(p.flags & 4)) mma_f16_ts(d, a, smem_desc_sw128(hb + 2 * H_TILE), idesc, kk != 0);   // h_lo first
-                                    mma_f16_ts(d, a, smem_desc_sw128(hb), idesc, (p.flags & 4) ? (uint32_t)(kk != 0) : 1u); // h_hi
+                                    for (int q = 0; q < 4; ++q)                                                       // h_lo first
+                                        mma_f16_ts(tmem_base + q * LNB + h * LPN, tmem_base + TMEM_W + q * 64 + kk * 8, d_lo, idesc, kk != 0);
                                 }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    mma_f16_ts(tmem_base + q * LNB + h * LPN, tmem_base + TMEM_W + q * 64 + kk * 8, d_hi, idesc,
+                                               (p.flags & 4) ? (uint32_t)(kk != 0) : 1u);
                             }
                         }
                         // once acc_ready fires the pointwise warps rewrite buffer (s+1)&1, last read by the store group of
