@@ -11,6 +11,7 @@
 // accumulated in double while the max-pool output is written, then applied in place together
 // with the affine transform and LeakyReLU(0.01).
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace b200vad {
 
@@ -134,15 +135,49 @@ __global__ void __launch_bounds__(256) wave_norm_planes_kernel(const float* __re
     float rstd = (float)(1.0 / sqrt(fmax(var, 0.0) + 1e-5));
     float m = (float)mean, g = gamma[0], be = beta[0];
     const float* row = wav + (int64_t)b * stride;
-    for (int64_t i = (int64_t)blockIdx.x * 256 * 16 + threadIdx.x; i < min(Np + 8, ((int64_t)blockIdx.x + 1) * 256 * 16); i += 256) {
-        __half h = __float2half_rn(0.f), l = h;
-        if (i < N) split_f16((row[i] - m) * rstd * g + be, h, l);
+    // 8 consecutive samples per thread (Np and the copies' bases are multiples of 8 elements): copy e receives them at
+    // element i - 2 e, i.e. at a 16 / 4 / 8 / 4-byte aligned address for e = 0 / 1 / 2 / 3
+    const bool vec_ok = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(wav) & 15) == 0);
+    for (int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8; i < Np + 8; i += (int64_t)gridDim.x * 256 * 8) {
+        float v[8];
+        if (vec_ok && i + 8 <= N) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(row + i)), a1 = __ldg(reinterpret_cast<const float4*>(row + i + 4));
+            v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (i + j < N) ? row[i + j] : 0.f;
+        }
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = __float2half_rn(0.f); l[j] = h[j];
+            if (i + j < N) split_f16((v[j] - m) * rstd * g + be, h[j], l[j]);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int64_t d = i - 2 * e;                      // copy e: element d holds sample d + 2 e
-            if (d >= 0 && d < Np) {
-                hi[((int64_t)e * B + b) * Np + d] = h;
-                lo[((int64_t)e * B + b) * Np + d] = l;
+            __half* dh = hi + ((int64_t)e * B + b) * Np;
+            __half* dl = lo + ((int64_t)e * B + b) * Np;
+            if (d >= 0 && d + 8 <= Np) {
+                if (e == 0) {
+                    *reinterpret_cast<uint4*>(dh + d) = *reinterpret_cast<const uint4*>(h);
+                    *reinterpret_cast<uint4*>(dl + d) = *reinterpret_cast<const uint4*>(l);
+                } else if (e == 2) {
+                    *reinterpret_cast<uint2*>(dh + d) = *reinterpret_cast<const uint2*>(h);
+                    *reinterpret_cast<uint2*>(dh + d + 4) = *reinterpret_cast<const uint2*>(h + 4);
+                    *reinterpret_cast<uint2*>(dl + d) = *reinterpret_cast<const uint2*>(l);
+                    *reinterpret_cast<uint2*>(dl + d + 4) = *reinterpret_cast<const uint2*>(l + 4);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        *reinterpret_cast<uint32_t*>(dh + d + j) = *reinterpret_cast<const uint32_t*>(h + j);
+                        *reinterpret_cast<uint32_t*>(dl + d + j) = *reinterpret_cast<const uint32_t*>(l + j);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (d + j >= 0 && d + j < Np) { dh[d + j] = h[j]; dl[d + j] = l[j]; }
             }
         }
     }
@@ -153,7 +188,7 @@ int wave_norm_planes_launch(const float* wav, int B, int64_t N, int64_t stride, 
     dim3 g1((unsigned)((N + 8191) / 8192), B);
     wave_stats_kernel<<<g1, 256, 0, s>>>(wav, N, stride, stats);
     B200VAD_LAUNCH_CHECK();
-    dim3 g2((unsigned)((Np + 8 + 4095) / 4096), B);
+    dim3 g2((unsigned)((Np + 8 + 2047) / 2048), B);
     wave_norm_planes_kernel<<<g2, 256, 0, s>>>(wav, N, stride, Np, B, stats, gamma, beta, hi, lo);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
@@ -214,8 +249,9 @@ __global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict
         atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2 + 1, d);
     }
 }
-// in place: x = leaky_relu((x - mean) * rstd * gamma + beta); optionally also as fp16 (hi, lo) planes (B, P, Cp) with the
-// channels zero padded to Cp (the operand of the next convolution on the tcgen05 path)
+// x = leaky_relu((x - mean) * rstd * gamma + beta): written in place as fp32, or -- when planes are given -- only as fp16
+// (hi, lo) planes (B, P, Cp) with the channels zero padded to Cp (the operand of the next convolution on the tcgen05 path;
+// the fp32 copy has no reader there).  Four channels per thread (C % 4 == 0, Cp % 4 == 0).
 __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, int64_t P, int C, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          __half* __restrict__ p_hi, __half* __restrict__ p_lo, int Cp) {
@@ -230,18 +266,28 @@ __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, 
         sh[threadIdx.x] = beta[threadIdx.x] - (float)mean * rstd * g;
     }
     __syncthreads();
-    const int64_t tot = P * C;
-    float* base = x + (int64_t)b * tot;
-    for (int64_t i = (int64_t)blockIdx.x * 256 * 16 + threadIdx.x; i < min(tot, ((int64_t)blockIdx.x + 1) * 256 * 16); i += 256) {
-        int c = (int)(i % C);
-        float v = fmaf(base[i], sc[c], sh[c]);
-        v = v > 0.f ? v : 0.01f * v;
-        base[i] = v;
+    const int q = (p_hi ? Cp : C) / 4;                        // 4-channel groups per row (including the padding groups)
+    const int64_t groups = P * q;
+    float* base = x + (int64_t)b * P * C;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < groups; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / q;
+        const int c = (int)(i - r * q) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            v = *reinterpret_cast<const float4*>(base + r * C + c);
+            v.x = fmaf(v.x, sc[c], sh[c]); v.y = fmaf(v.y, sc[c + 1], sh[c + 1]);
+            v.z = fmaf(v.z, sc[c + 2], sh[c + 2]); v.w = fmaf(v.w, sc[c + 3], sh[c + 3]);
+            v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y;
+            v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
+        }
         if (p_hi) {
-            const int64_t o = ((int64_t)b * P + i / C) * Cp + c;
-            split_f16(v, p_hi[o], p_lo[o]);
-            if (c == C - 1)
-                for (int cc = C; cc < Cp; ++cc) { p_hi[o + cc - c] = __float2half_rn(0.f); p_lo[o + cc - c] = __float2half_rn(0.f); }
+            __align__(8) __half h[4], l[4];
+            split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+            const int64_t o = ((int64_t)b * P + r) * Cp + c;
+            *reinterpret_cast<uint2*>(p_hi + o) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(p_lo + o) = *reinterpret_cast<const uint2*>(l);
+        } else {
+            *reinterpret_cast<float4*>(base + r * C + c) = v;
         }
     }
 }
@@ -257,7 +303,12 @@ int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pool
     dim3 g1((unsigned)((P + kPoolRows - 1) / kPoolRows), B);
     pool_stats_kernel<<<g1, 256, 0, s>>>(in, L, C, P, pooled, stats);
     B200VAD_LAUNCH_CHECK();
-    dim3 g2((unsigned)((P * C + 4095) / 4096), B);
+    if (C % 4 != 0 || (p_hi && (Cp % 4 != 0 || Cp < C))) {
+        set_error("pool_norm: C and Cp must be multiples of 4, Cp >= C");
+        return B200VAD_EINVAL;
+    }
+    const int64_t groups = P * ((p_hi ? Cp : C) / 4);
+    dim3 g2((unsigned)std::min<int64_t>((groups + 1023) / 1024, 65535), B);
     norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta, p_hi, p_lo, Cp);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
