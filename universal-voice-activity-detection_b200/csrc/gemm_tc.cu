@@ -548,8 +548,8 @@ gemm_xg2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
 // ---------------------------------------------------------------- CTA-pair input projection (cta_group::2)
 // Every activation tile is consumed by the 8 feature-block CTAs of a group, so 8x the activation bytes cross the L2
-// fabric (26.8 GB per K = 256 launch next to 13.4 GB of xg writes); the single-CTA kernels above run at the fabric's
-// ~6300 B/clk whatever their tensor work (3-term and 2-MMA variants measured the same 4.05 ms -- profiles/r01_gemm.md).
+// fabric into shared memory (26.8 GB per K = 256 launch next to 13.4 GB of xg writes), and the chip sits at its power cap
+// during these kernels: the single-CTA 3-term and 2-MMA variants measured the same ~4.0 ms (profiles/r01_gemm.md).
 // Here two feature blocks form a CTA pair on one TPC: each CTA keeps its own 128 features' weights in its own TMEM and
 // loads HALF of the activation tile (32 sequences x 2 steps); one tcgen05.mma.cta_group::2 (M = 256, N = 128) issued
 // by the even CTA multiplies both CTAs' weights with both halves.  Activation bytes through L2 and per-CTA shared-memory
