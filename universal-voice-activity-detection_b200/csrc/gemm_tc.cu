@@ -424,14 +424,19 @@ gemm_xg2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             // costs bandwidth, never correctness), so co-residency of the group is not a requirement.
             int* const sync = p.sync ? p.sync + (size_t)tile0 * p.sync_stride : nullptr;
             int ti = 0;
+            bool lock_ok = true;
             for (int t = tile0; t < p.num_tiles; t += tile_step, ++ti) {
                 if (sync && (ti % X2_WINDOW) == 0) {
                     const int w = ti / X2_WINDOW;
                     if (w < p.sync_stride) {
                         atomicAdd(sync + w, 1);
-                        if (w > 0) {
+                        if (w > 0 && lock_ok) {
+                            // bounded: a group that is not co-resident (fewer free SMs than CTAs) times out ONCE and then
+                            // free-runs -- lockstep only ever saves bandwidth
                             const long long t0c = clock64();
-                            while (*reinterpret_cast<volatile int*>(sync + w - 1) < 8 && clock64() - t0c < 2000000LL) { }
+                            while (*reinterpret_cast<volatile int*>(sync + w - 1) < 8) {
+                                if (clock64() - t0c > 400000LL) { lock_ok = false; break; }
+                            }
                         }
                     }
                 }
@@ -613,14 +618,19 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             // lockstep of the 8 CTAs of a group, as in gemm_xg2_kernel: bounded waits, bandwidth only
             int* const sync = p.sync ? p.sync + (size_t)tile0 * p.sync_stride : nullptr;
             int ti = 0;
+            bool lock_ok = true;
             for (int t = tile0; t < p.num_tiles; t += tile_step, ++ti) {
                 if (sync && (ti % X2_WINDOW) == 0) {
                     const int w = ti / X2_WINDOW;
                     if (w < p.sync_stride) {
                         atomicAdd(sync + w, 1);
-                        if (w > 0) {
+                        if (w > 0 && lock_ok) {
+                            // bounded: a group that is not co-resident (fewer free SMs than CTAs) times out ONCE and then
+                            // free-runs -- lockstep only ever saves bandwidth
                             const long long t0c = clock64();
-                            while (*reinterpret_cast<volatile int*>(sync + w - 1) < 8 && clock64() - t0c < 2000000LL) { }
+                            while (*reinterpret_cast<volatile int*>(sync + w - 1) < 8) {
+                                if (clock64() - t0c > 400000LL) { lock_ok = false; break; }
+                            }
                         }
                     }
                 }
