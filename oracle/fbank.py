@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED: lhotse is a
 un-pinned editable checkout in the reference (requirements.txt:13) and is absent
 from /root/reference; the arithmetic below restates upstream
 ``lhotse/features/kaldi/layers.py::Wav2Win / Wav2LogFilterBank`` and
-``extractors.py::Fbank`` with ``FbankConfig`` defaults.  Reference call sites:
+``extractors.py::Fbank`` with ``FbankConfig`` defaults.  Every stage after the whole-signal DC removal / pre-emphasis
+is cross-checked against torchaudio.compliance.kaldi.fbank (tests/test_oracle.py), the mel banks bit for bit.  Reference call sites:
 src/utils/helper.py:120-130, src/datasets/ami/utils.py:152-163 (and the 17
 sibling ``src/datasets/*/utils.py``).
 """

@@ -134,3 +134,22 @@ def test_vadmodel_predict_step_shapes():
     o2 = util.make_oracle("PyanNet", {})
     p = o2.probabilities({"inputs": 0.1 * torch.randn(2, 16000)})
     assert p.shape == (2, oracle.get_num_frames(16000), 1)
+
+
+@pytest.mark.parametrize("n", [16000, 12345, 80000, 128000, 400])        # torchaudio needs n >= one frame
+def test_fbank_stages_match_torchaudio_kaldi(n):
+    """lhotse's Fbank differs from torchaudio.compliance.kaldi.fbank only in WHERE the DC offset and the pre-emphasis are
+    applied (whole signal instead of per frame).  With those two steps applied by hand and switched
+    off in torchaudio, everything else -- snip_edges=False mirror framing, povey window, 512-point power spectrum, Kaldi
+    mel banks, log(max(x, eps)) -- must agree: an independent implementation of those stages."""
+    ta = pytest.importorskip("torchaudio.compliance.kaldi")
+    g = torch.Generator().manual_seed(n)
+    w = 0.1 * torch.randn(1, n, generator=g) + 0.01
+    ours = oracle.lhotse_fbank(w)[0]
+    x = w - w.mean(dim=1, keepdim=True)
+    x = x - 0.97 * torch.cat([x[:, :1], x[:, :-1]], dim=1)
+    ref = ta.fbank(x, dither=0.0, remove_dc_offset=False, preemphasis_coefficient=0.0, snip_edges=False, window_type="povey",
+                   num_mel_bins=80, low_freq=20.0, high_freq=-400.0, frame_length=25.0, frame_shift=10.0, sample_frequency=16000.0,
+                   use_energy=False, round_to_power_of_two=True, use_log_fbank=True, use_power=True, subtract_mean=False)
+    assert ours.shape == ref.shape == ((n + 80) // 160, 80)
+    assert util.feat_err(ours, ref) <= 2e-5, util.feat_err(ours, ref)
