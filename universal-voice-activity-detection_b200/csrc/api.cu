@@ -3,6 +3,7 @@
 #include "../../include/b200vad.h"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <atomic>
 #include <mutex>
@@ -304,12 +305,20 @@ static SincDims sinc_dims(int64_t N) {
     d.P3 = d.L3 / 3;
     return d;
 }
+// B200VAD_SINC_FUSED=0 selects the unfused sinc layer (four row-class GEMMs + pooling kernel; validation): it needs the
+// (B, L1, 80) convolution output in the workspace, the fused kernel does not
+static bool sinc_fused() {
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("B200VAD_SINC_FUSED"); fused = (e && atoi(e) == 0) ? 0 : 1; }
+    return fused != 0;
+}
 static inline int64_t sinc_np(int64_t N) { return (N + 16 + 7) / 8 * 8; }     // padded length of a shifted waveform copy
 static size_t sinc_ws_per_row(int64_t N) {
     SincDims d = sinc_dims(N);
     // normalised wave (fp32, or 4 shifted fp16 hi/lo copies) + conv1 out + pooled1 (+ planes) + conv2 out + pooled2 (+ planes)
     // + conv3 out, stats
-    return align_up(std::max<size_t>(sizeof(float) * N, 16 * (size_t)sinc_np(N))) + align_up(sizeof(float) * d.L1 * 80) +
+    const bool conv1_out = !(sinc_fused() && g_impl == 2);
+    return align_up(std::max<size_t>(sizeof(float) * N, 16 * (size_t)sinc_np(N))) + (conv1_out ? align_up(sizeof(float) * d.L1 * 80) : 0) +
            2 * align_up(sizeof(float) * d.P1 * 80) + align_up(sizeof(float) * d.L2 * 60) + align_up(sizeof(float) * d.P2 * 60) +
            align_up(sizeof(float) * d.P2 * kC2Cp) + align_up(sizeof(float) * d.L3 * 60) + align_up(sizeof(double) * 2 * 80) + 4096;
 }
@@ -564,7 +573,7 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
         const int64_t Np = sinc_np(N);
         char* wn_raw = take(std::max<size_t>(sizeof(float) * N, 16 * (size_t)Np) * bc);
         float* wn = reinterpret_cast<float*>(wn_raw);
-        float* c1 = reinterpret_cast<float*>(take(sizeof(float) * d.L1 * 80 * bc));
+        float* c1 = (sinc_fused() && g_impl == 2) ? nullptr : reinterpret_cast<float*>(take(sizeof(float) * d.L1 * 80 * bc));
         float* p1 = reinterpret_cast<float*>(take(sizeof(float) * d.P1 * 80 * bc));
         __half* p1_hi = reinterpret_cast<__half*>(take(sizeof(float) * d.P1 * 80 * bc));
         __half* p1_lo = p1_hi + d.P1 * 80 * bc;
@@ -582,18 +591,28 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
             __half* wn_lo = wn_hi + 4 * (int64_t)bc * Np;
             if ((rc = wave_norm_planes_launch(wav + b0 * wav_stride, bc, N, wav_stride, Np, reinterpret_cast<const float*>(pk + s.wn_w),
                                               reinterpret_cast<const float*>(pk + s.wn_b), stats, wn_hi, wn_lo, st))) return rc;
+            if (sinc_fused()) {
+                // sinc conv + |x| + MaxPool3 + InstanceNorm sums in one launch: the (B, L1, 80) convolution output never exists
+                if ((rc = zero_f64_launch(stats, (int64_t)2 * bc * 80, st))) return rc;
+                if ((rc = sinc_pool_gemm_launch(wn_hi, wn_lo, Np, bc, d.L1, reinterpret_cast<const __half*>(pk + s.sinc_t_hi),
+                                                reinterpret_cast<const __half*>(pk + s.sinc_t_lo), kSincTLd, kSincTLd, 80, p1, 80, stats,
+                                                sms, st))) return rc;
+                if ((rc = norm_lrelu_launch(p1, bc, d.P1, 80, stats, reinterpret_cast<const float*>(pk + s.n0_w),
+                                            reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80))) return rc;
+            } else {
             // sinc conv, stride 10: rows t = 4 m + r start at 40 m + 10 r -> copy shifted by (10 r) % 8, offset 8 * ((10 r) / 8)
-            for (int r = 0; r < 4; ++r) {
-                const int64_t rows_r = (d.L1 - r + 3) / 4;
-                if (rows_r <= 0) continue;
-                const int e = ((10 * r) % 8) / 2, q = ((10 * r) / 8) * 8;
-                if ((rc = gemm_ts_rows_launch(wn_hi + (int64_t)e * bc * Np + q, wn_lo + (int64_t)e * bc * Np + q, 40, Np, bc, (int)rows_r,
-                                              kSincTLd, reinterpret_cast<const __half*>(pk + s.sinc_t_hi),
-                                              reinterpret_cast<const __half*>(pk + s.sinc_t_lo), kSincTLd, kSincTLd, 80, nullptr, 0, 1,
-                                              c1, 80, d.L1, 4, r, sms, st))) return rc;
+                for (int r = 0; r < 4; ++r) {
+                    const int64_t rows_r = (d.L1 - r + 3) / 4;
+                    if (rows_r <= 0) continue;
+                    const int e = ((10 * r) % 8) / 2, q = ((10 * r) / 8) * 8;
+                    if ((rc = gemm_ts_rows_launch(wn_hi + (int64_t)e * bc * Np + q, wn_lo + (int64_t)e * bc * Np + q, 40, Np, bc, (int)rows_r,
+                                                  kSincTLd, reinterpret_cast<const __half*>(pk + s.sinc_t_hi),
+                                                  reinterpret_cast<const __half*>(pk + s.sinc_t_lo), kSincTLd, kSincTLd, 80, nullptr, 0, 1,
+                                                  c1, 80, d.L1, 4, r, sms, st))) return rc;
+                }
+                if ((rc = pool_norm_lrelu_launch(c1, bc, d.L1, 80, p1, stats, reinterpret_cast<const float*>(pk + s.n0_w),
+                                                 reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80))) return rc;
             }
-            if ((rc = pool_norm_lrelu_launch(c1, bc, d.L1, 80, p1, stats, reinterpret_cast<const float*>(pk + s.n0_w),
-                                             reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80))) return rc;
             // Conv1d(80, 60, 5): row t = p1[b, t : t + 5, :] = 400 contiguous values, K split 256 + 144
             const __half* w1h = reinterpret_cast<const __half*>(pk + s.c1_t_hi);
             const __half* w1l = reinterpret_cast<const __half*>(pk + s.c1_t_lo);

@@ -749,6 +749,171 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------- sinc convolution + |x| + MaxPool1d(3) + InstanceNorm sums
+// The stride-10 sinc layer (sincnet.py:50-61, 95-99) as ONE overlapping-row GEMM whose epilogue pools.  Rows t = 4 m + r of
+// residue class r come from their own tensor map (80-byte row stride on the waveform copy shifted by 10 r mod 8 samples,
+// see sincnet.cu); a tile takes a 32-row box from each of the four classes into smem rows [32 r, 32 r + 32), so accumulator
+// column 32 r + m is convolution row t0 + 4 m + r: the MMA does not care about row order, and the epilogue thread of a
+// feature holds all 128 columns in registers, where the three rows of every pooling group meet.  A tile advances by 120
+// rows (30 per class: 40 pooling groups; box rows 30, 31 are recomputed by the next tile).  Written: pooled (B, P, C) fp32
+// and the per-(item, channel) sum / sum of squares for InstanceNorm -- the (B, L, C) convolution output (4 MB per 8 s row)
+// never exists.
+constexpr int SP_THREADS = 192;
+constexpr int SP_STAGES = 6;
+constexpr int SP_TILE_ROWS = 120;                     // convolution rows per tile
+struct alignas(64) SincMaps {
+    CUtensorMap hi[4], lo[4];
+};
+struct SincPoolParams {
+    const __half* w_hi;      // [128][ldw], rows >= n_valid zero
+    const __half* w_lo;
+    float* pooled;           // [B][P][ldc]
+    double* stats;           // [B][n_valid][2]
+    int64_t P;
+    int ldc, n_valid, ldw, kb, tiles_per_batch, num_tiles;
+};
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sinc_pool_gemm_kernel(const __grid_constant__ SincMaps maps, SincPoolParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;                                        // [stages][hi, lo] tiles of 128 x 64
+    const uint32_t bar_base = a_base + SP_STAGES * 2 * S_TILE_BYTES;
+    auto bar_a_full = [&](int s) { return bar_base + 8 * s; };
+    auto bar_a_empty = [&](int s) { return bar_base + 64 + 8 * s; };
+    auto bar_acc_full = [&](int b) { return bar_base + 128 + 8 * b; };
+    auto bar_acc_empty = [&](int b) { return bar_base + 144 + 8 * b; };
+    const uint32_t bar_w = bar_base + 160;
+    const uint32_t tmem_slot = bar_base + 168;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SP_STAGES; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 128); }
+        mbar_init(bar_w, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int wcols = p.kb * 32;                                              // TMEM columns per weight plane
+
+    if (warp == 0) {
+        // ===================== TMA producer: four 32-row class boxes per plane and k-block =====================
+        if (elect_one()) {
+            for (int r = 0; r < 4; ++r) { tma_prefetch_desc(&maps.hi[r]); tma_prefetch_desc(&maps.lo[r]); }
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int bi = t / p.tiles_per_batch, rt = t - bi * p.tiles_per_batch;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_a_full(s), 2 * S_TILE_BYTES);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        tma_load_3d(a_base + (2 * s) * S_TILE_BYTES + r * 4096, &maps.hi[r], kb * SBK, rt * 30, bi, bar_a_full(s));
+                        tma_load_3d(a_base + (2 * s + 1) * S_TILE_BYTES + r * 4096, &maps.lo[r], kb * SBK, rt * 30, bi, bar_a_full(s));
+                    }
+                    if (++s == SP_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (three split-precision products, as gemm_ts_kernel) =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_f16(128, SBM);
+            mbar_wait(bar_w, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                const int ab = it & 1;
+                const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(bar_acc_empty(ab), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ACC_COL + ab * SBM;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t x_hi = a_base + (2 * s) * S_TILE_BYTES, x_lo = x_hi + S_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_lo = w_hi + wcols;
+                        const uint64_t dx_hi = smem_desc_sw128(x_hi + k * 32), dx_lo = smem_desc_sw128(x_lo + k * 32);
+                        mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);            // small terms first
+                        mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        mma_f16_ts(d_tmem, w_hi, dx_hi, idesc, 1);
+                    }
+                    mma_commit(bar_a_empty(s));
+                    if (++s == SP_STAGES) { s = 0; ph ^= 1; }
+                }
+                mma_commit(bar_acc_full(ab));
+            }
+        }
+    } else {
+        // ===================== weights -> TMEM, then the pooling epilogue (warps 2..5 -> lane quarters 2,3,0,1) =====================
+        const int q = warp & 3;
+        const int out = q * 32 + lane;                                          // output channel == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int w = 0; w < 2; ++w) {
+            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.ldw);
+            for (int part = 0; part < p.kb * 2; ++part) {
+                uint32_t r[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 v = __ldg(wrow + part * 4 + i);
+                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+                }
+                tmem_st16(lane_addr + w * wcols + part * 16, r);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_w);
+        const bool out_ok = out < p.n_valid;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const uint32_t acc_ph = (it >> 1) & 1;
+            const int bi = t / p.tiles_per_batch, rt = t - bi * p.tiles_per_batch;
+            mbar_wait(bar_acc_full(ab), acc_ph);
+            tc_fence_after();
+            float v[4][32];                                                     // v[r][m] = row 4 m + r of the tile
+#pragma unroll
+            for (int r = 0; r < 4; ++r) tmem_ld32(lane_addr + ACC_COL + ab * SBM + r * 32, v[r]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty(ab));
+            if (!out_ok) continue;
+            const int64_t p0 = (int64_t)rt * (SP_TILE_ROWS / 3);
+            float* dst = p.pooled + ((int64_t)bi * p.P + p0) * p.ldc + out;
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int g = 0; g < SP_TILE_ROWS / 3; ++g) {
+                // rows 3 g, 3 g + 1, 3 g + 2 of the tile: compile-time (class, slot) after unrolling
+                const float a0 = fabsf(v[(3 * g) & 3][(3 * g) >> 2]);
+                const float a1 = fabsf(v[(3 * g + 1) & 3][(3 * g + 1) >> 2]);
+                const float a2 = fabsf(v[(3 * g + 2) & 3][(3 * g + 2) >> 2]);
+                const float m = fmaxf(fmaxf(a0, a1), a2);
+                if (p0 + g < p.P) {
+                    dst[(int64_t)g * p.ldc] = m;
+                    sum += m;
+                    sq = fmaf(m, m, sq);
+                }
+            }
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2, (double)sum);
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2 + 1, (double)sq);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ---------------------------------------------------------------- fp32 -> fp16 (hi, lo) planes
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t n, __half* __restrict__ hi,
                                                            __half* __restrict__ lo) {
@@ -957,6 +1122,49 @@ int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stri
     if ((rc = make_tmap_3d(&tm_a_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, rows_per_batch, B, row_stride * 2, batch_stride * 2,
                            SBK, SBM, 1, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     return gemm_ts_run(0, tm_a_hi, tm_a_lo, p, 128, num_sms, st);
+}
+
+// Sinc convolution + |x| + MaxPool1d(3) + InstanceNorm sums in one launch (sinc_pool_gemm_kernel).  wn_hi / wn_lo: the four
+// shifted copies of the normalised waveform, copy e at + e * B * Np (sincnet.cu); L1 = convolution rows per item;
+// pooled (B, L1 / 3, ldc) fp32 and stats (B, n_valid, 2) -- zeroed by the caller -- are written.
+int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, int B, int64_t L1, const __half* w_hi,
+                          const __half* w_lo, int Kp, int ldw, int n_valid, float* pooled, int ldc, double* stats, int num_sms,
+                          cudaStream_t st) {
+    const int64_t P = L1 / 3;
+    if (B <= 0 || P <= 0) return B200VAD_OK;
+    int rc = gemm_ts_check(Kp, Kp, ldw, 128, 8, 2);
+    if (rc) return rc;
+    if (n_valid < 1 || n_valid > 128 || (Np * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(wn_hi) & 15) || (reinterpret_cast<uintptr_t>(wn_lo) & 15)) {
+        set_error("sinc_pool_gemm: bad arguments");
+        return B200VAD_EINVAL;
+    }
+    SincMaps maps;
+    for (int r = 0; r < 4; ++r) {
+        // rows t = 4 m + r start at sample 40 m + 10 r = (40 m + 8 floor(10 r / 8)) + (10 r mod 8): copy (10 r mod 8) / 2
+        const int64_t rows_r = (L1 - r + 3) / 4;
+        const int e = ((10 * r) % 8) / 2, q = ((10 * r) / 8) * 8;
+        const __half* bh = wn_hi + (int64_t)e * B * Np + q;
+        const __half* bl = wn_lo + (int64_t)e * B * Np + q;
+        if ((rc = make_tmap_3d(&maps.hi[r], bh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kp, std::max<int64_t>(rows_r, 1), B, 80, Np * 2, SBK, 32, 1,
+                               CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_3d(&maps.lo[r], bl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kp, std::max<int64_t>(rows_r, 1), B, 80, Np * 2, SBK, 32, 1,
+                               CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    SincPoolParams p;
+    p.w_hi = w_hi; p.w_lo = w_lo; p.pooled = pooled; p.stats = stats; p.P = P; p.ldc = ldc; p.n_valid = n_valid; p.ldw = ldw;
+    p.kb = Kp / SBK;
+    p.tiles_per_batch = (int)((P + SP_TILE_ROWS / 3 - 1) / (SP_TILE_ROWS / 3));
+    const int64_t tiles = (int64_t)B * p.tiles_per_batch;
+    if (tiles >= (1LL << 31)) { set_error("sinc_pool_gemm: too many tiles"); return B200VAD_EINVAL; }
+    p.num_tiles = (int)tiles;
+    const int smem = 1024 + SP_STAGES * 2 * S_TILE_BYTES + 256;
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(sinc_pool_gemm_kernel), smem))) return rc;
+    const int grid = (int)std::min<int64_t>(num_sms, tiles);
+    prof_begin(1, st);
+    sinc_pool_gemm_kernel<<<grid, SP_THREADS, smem, st>>>(maps, p);
+    prof_end(1, st);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
 }
 
 // 2-MMA input projection (K <= 256, both weight planes given): same contract as gemm_ts_xg_launch without `accumulate`;

@@ -40,6 +40,9 @@ int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stri
 int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, int T, int K, const __half* w_hi,
                     const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
                     size_t sync_bytes, int num_sms, cudaStream_t st);
+int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, int B, int64_t L1, const __half* w_hi,
+                          const __half* w_lo, int Kp, int ldw, int n_valid, float* pooled, int ldc, double* stats, int num_sms,
+                          cudaStream_t st);
 int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int K, const __half* w_hi,
                         const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
                         size_t sync_bytes, int num_sms, cudaStream_t st);
@@ -60,6 +63,8 @@ int sinc_filters_launch(const float* low, const float* band, const float* window
 int repack_conv_launch(const float* w, int Cout, int Cin, int k, float* out, cudaStream_t s);
 int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, const float* gamma, const float* beta,
                          double* stats, float* out, cudaStream_t s);
+int norm_lrelu_launch(float* pooled, int B, int64_t P, int C, const double* stats, const float* gamma, const float* beta,
+                      cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0);
 int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
                            const float* beta, cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0);
 int wave_norm_planes_launch(const float* wav, int B, int64_t N, int64_t stride, int64_t Np, const float* gamma, const float* beta,

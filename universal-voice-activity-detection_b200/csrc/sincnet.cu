@@ -291,6 +291,20 @@ __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, 
         }
     }
 }
+int norm_lrelu_launch(float* pooled, int B, int64_t P, int C, const double* stats, const float* gamma, const float* beta,
+                      cudaStream_t s, __half* p_hi, __half* p_lo, int Cp) {
+    if (P <= 0 || B == 0) return B200VAD_OK;
+    if (C > 128 || C < 1 || C % 4 != 0 || (p_hi && (Cp % 4 != 0 || Cp < C))) {
+        set_error("norm_lrelu: C in [1,128], C and Cp multiples of 4, Cp >= C");
+        return B200VAD_EINVAL;
+    }
+    const int64_t groups = P * ((p_hi ? Cp : C) / 4);
+    dim3 g2((unsigned)std::min<int64_t>((groups + 1023) / 1024, 65535), B);
+    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta, p_hi, p_lo, Cp);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
 int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
                            const float* beta, cudaStream_t s, __half* p_hi, __half* p_lo, int Cp) {
     if (C > 128 || C < 1) {
@@ -303,15 +317,7 @@ int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pool
     dim3 g1((unsigned)((P + kPoolRows - 1) / kPoolRows), B);
     pool_stats_kernel<<<g1, 256, 0, s>>>(in, L, C, P, pooled, stats);
     B200VAD_LAUNCH_CHECK();
-    if (C % 4 != 0 || (p_hi && (Cp % 4 != 0 || Cp < C))) {
-        set_error("pool_norm: C and Cp must be multiples of 4, Cp >= C");
-        return B200VAD_EINVAL;
-    }
-    const int64_t groups = P * ((p_hi ? Cp : C) / 4);
-    dim3 g2((unsigned)std::min<int64_t>((groups + 1023) / 1024, 65535), B);
-    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta, p_hi, p_lo, Cp);
-    B200VAD_LAUNCH_CHECK();
-    return B200VAD_OK;
+    return norm_lrelu_launch(pooled, B, P, C, stats, gamma, beta, s, p_hi, p_lo, Cp);
 }
 
 }  // namespace b200vad
