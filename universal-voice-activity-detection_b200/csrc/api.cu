@@ -319,8 +319,8 @@ static size_t sinc_ws_per_row(int64_t N) {
     // + conv3 out, stats
     const bool conv1_out = !(sinc_fused() && g_impl == 2);
     return align_up(std::max<size_t>(sizeof(float) * N, 16 * (size_t)sinc_np(N))) + (conv1_out ? align_up(sizeof(float) * d.L1 * 80) : 0) +
-           2 * align_up(sizeof(float) * d.P1 * 80) + align_up(sizeof(float) * d.L2 * 60) + align_up(sizeof(float) * d.P2 * 60) +
-           align_up(sizeof(float) * d.P2 * kC2Cp) + align_up(sizeof(float) * d.L3 * 60) + align_up(sizeof(double) * 2 * 80) + 4096;
+           2 * align_up(sizeof(float) * d.P1 * 80) + (conv1_out ? align_up(sizeof(float) * d.L2 * 60) : 0) + align_up(sizeof(float) * d.P2 * 60) +
+           align_up(sizeof(float) * d.P2 * kC2Cp) + (conv1_out ? align_up(sizeof(float) * d.L3 * 60) : 0) + align_up(sizeof(double) * 2 * 80) + 4096;
 }
 
 }  // namespace b200vad
@@ -577,11 +577,12 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
         float* p1 = reinterpret_cast<float*>(take(sizeof(float) * d.P1 * 80 * bc));
         __half* p1_hi = reinterpret_cast<__half*>(take(sizeof(float) * d.P1 * 80 * bc));
         __half* p1_lo = p1_hi + d.P1 * 80 * bc;
-        float* c2 = reinterpret_cast<float*>(take(sizeof(float) * d.L2 * 60 * bc));
+        const bool fused_convs = sinc_fused() && g_impl == 2;
+        float* c2 = fused_convs ? nullptr : reinterpret_cast<float*>(take(sizeof(float) * d.L2 * 60 * bc));
         float* p2 = reinterpret_cast<float*>(take(sizeof(float) * d.P2 * 60 * bc));
         __half* p2_hi = reinterpret_cast<__half*>(take(sizeof(float) * d.P2 * kC2Cp * bc));
         __half* p2_lo = p2_hi + d.P2 * kC2Cp * bc;
-        float* c3 = reinterpret_cast<float*>(take(sizeof(float) * d.L3 * 60 * bc));
+        float* c3 = fused_convs ? nullptr : reinterpret_cast<float*>(take(sizeof(float) * d.L3 * 60 * bc));
         double* stats = reinterpret_cast<double*>(take(sizeof(double) * 2 * 80 * bc));
         int rc;
         if (g_impl == 2) {
@@ -613,10 +614,29 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
                 if ((rc = pool_norm_lrelu_launch(c1, bc, d.L1, 80, p1, stats, reinterpret_cast<const float*>(pk + s.n0_w),
                                                  reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80))) return rc;
             }
-            // Conv1d(80, 60, 5): row t = p1[b, t : t + 5, :] = 400 contiguous values, K split 256 + 144
             const __half* w1h = reinterpret_cast<const __half*>(pk + s.c1_t_hi);
             const __half* w1l = reinterpret_cast<const __half*>(pk + s.c1_t_lo);
             const float* b1 = reinterpret_cast<const float*>(pk + s.c1_b);
+            const __half* w2h = reinterpret_cast<const __half*>(pk + s.c2_t_hi);
+            const __half* w2l = reinterpret_cast<const __half*>(pk + s.c2_t_lo);
+            const float* b2 = reinterpret_cast<const float*>(pk + s.c2_b);
+            if (sinc_fused()) {
+                // Conv1d(80, 60, 5) / Conv1d(60 -> 64 padded, 60, 5): whole K resident in TMEM, bias + MaxPool3 + InstanceNorm sums
+                // in the epilogue (conv_pool_gemm_kernel): neither the convolution outputs nor a K-split partial sum exist
+                if ((rc = zero_f64_launch(stats, (int64_t)2 * bc * 60, st))) return rc;
+                if ((rc = conv_pool_gemm_launch(p1_hi, p1_lo, 80, d.P1 * 80, bc, d.L2, kC1K, w1h, w1l, kC1TLd, kC1TLd, 60, b1, p2, 60, stats,
+                                                sms, st))) return rc;
+                if ((rc = norm_lrelu_launch(p2, bc, d.P2, 60, stats, reinterpret_cast<const float*>(pk + s.n1_w),
+                                            reinterpret_cast<const float*>(pk + s.n1_b), st, p2_hi, p2_lo, kC2Cp))) return rc;
+                float* o3 = out + b0 * d.P3 * 60;
+                if ((rc = zero_f64_launch(stats, (int64_t)2 * bc * 60, st))) return rc;
+                if ((rc = conv_pool_gemm_launch(p2_hi, p2_lo, kC2Cp, d.P2 * kC2Cp, bc, d.L3, kC2TLd, w2h, w2l, kC2TLd, kC2TLd, 60, b2, o3, 60,
+                                                stats, sms, st))) return rc;
+                if ((rc = norm_lrelu_launch(o3, bc, d.P3, 60, stats, reinterpret_cast<const float*>(pk + s.n2_w),
+                                            reinterpret_cast<const float*>(pk + s.n2_b), st))) return rc;
+                continue;
+            }
+            // Conv1d(80, 60, 5): row t = p1[b, t : t + 5, :] = 400 contiguous values, K split 256 + 144
             if ((rc = gemm_ts_rows_launch(p1_hi, p1_lo, 80, d.P1 * 80, bc, (int)d.L2, 256, w1h, w1l, 256, kC1TLd, 60, b1, 0, 0, c2, 60,
                                           d.L2, 1, 0, sms, st))) return rc;
             if ((rc = gemm_ts_rows_launch(p1_hi + 256, p1_lo + 256, 80, d.P1 * 80, bc, (int)d.L2, 144, w1h + 256, w1l + 256, 192, kC1TLd,
@@ -624,9 +644,6 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
             if ((rc = pool_norm_lrelu_launch(c2, bc, d.L2, 60, p2, stats, reinterpret_cast<const float*>(pk + s.n1_w),
                                              reinterpret_cast<const float*>(pk + s.n1_b), st, p2_hi, p2_lo, kC2Cp))) return rc;
             // Conv1d(60, 60, 5) on channels padded to 64: row t = 320 contiguous values, K split 256 + 64
-            const __half* w2h = reinterpret_cast<const __half*>(pk + s.c2_t_hi);
-            const __half* w2l = reinterpret_cast<const __half*>(pk + s.c2_t_lo);
-            const float* b2 = reinterpret_cast<const float*>(pk + s.c2_b);
             if ((rc = gemm_ts_rows_launch(p2_hi, p2_lo, kC2Cp, d.P2 * kC2Cp, bc, (int)d.L3, 256, w2h, w2l, 256, kC2TLd, 60, b2, 0, 0, c3,
                                           60, d.L3, 1, 0, sms, st))) return rc;
             if ((rc = gemm_ts_rows_launch(p2_hi + 256, p2_lo + 256, kC2Cp, d.P2 * kC2Cp, bc, (int)d.L3, 64, w2h + 256, w2l + 256, 64,

@@ -914,6 +914,167 @@ sinc_pool_gemm_kernel(const __grid_constant__ SincMaps maps, SincPoolParams p) {
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------- Conv1d(k = 5) + bias + MaxPool1d(3) + InstanceNorm sums
+// The 5-tap convolutions of SincNet (sincnet.py:62-71, 100-101) over channel-last fp16 planes: row t of the GEMM is the
+// 5 * Cin contiguous values starting at frame t (overlapping rows, one 3-D tensor map), K = 400 / 320.  Both weight
+// planes of the WHOLE K stay in tensor memory (2 x Kp / 2 <= 448 columns), which leaves room for 64-column accumulators
+// only -- one (K = 448) or two (K = 320) of them -- but removes the second, read-add-store pass of a K-split launch pair.  A
+// tile is 64 rows, advances by 63 (21 pooling groups; the last row is recomputed by the next tile), and the epilogue thread
+// of a channel pools its 64 accumulator columns in registers: written are pooled (B, P, C) fp32 and the InstanceNorm
+// sums; the convolution output itself never exists.
+constexpr int CP_THREADS = 192;
+constexpr int CP_STAGES = 8;
+constexpr int CP_ROWS = 64;                           // MMA N
+constexpr int CP_TILE_BYTES = CP_ROWS * SBK * 2;      // 8 KB
+constexpr int CP_ADV = 63;                            // rows a tile advances by (21 pooling groups)
+struct ConvPoolParams {
+    const __half* w_hi;      // [128][ldw], rows >= n_valid and columns >= K zero
+    const __half* w_lo;
+    const float* bias;       // [n_valid]
+    float* pooled;           // [B][P][ldc]
+    double* stats;           // [B][n_valid][2]
+    int64_t P;
+    int ldc, n_valid, ldw, kb, nacc, tiles_per_batch, num_tiles;
+};
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+conv_pool_gemm_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, ConvPoolParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;                                        // [stages][hi, lo] tiles of 64 x 64
+    const uint32_t bar_base = a_base + CP_STAGES * 2 * CP_TILE_BYTES;
+    auto bar_a_full = [&](int s) { return bar_base + 8 * s; };
+    auto bar_a_empty = [&](int s) { return bar_base + 64 + 8 * s; };
+    auto bar_acc_full = [&](int b) { return bar_base + 128 + 8 * b; };
+    auto bar_acc_empty = [&](int b) { return bar_base + 144 + 8 * b; };
+    const uint32_t bar_w = bar_base + 160;
+    const uint32_t tmem_slot = bar_base + 168;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CP_STAGES; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 128); }
+        mbar_init(bar_w, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int wcols = p.kb * 32;                                              // TMEM columns per weight plane
+    const uint32_t acc_col = 2 * wcols;                                       // accumulators follow the two weight planes
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int bi = t / p.tiles_per_batch, rt = t - bi * p.tiles_per_batch;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_a_full(s), 2 * CP_TILE_BYTES);
+                    tma_load_3d(a_base + (2 * s) * CP_TILE_BYTES, &tm_hi, kb * SBK, rt * CP_ADV, bi, bar_a_full(s));
+                    tma_load_3d(a_base + (2 * s + 1) * CP_TILE_BYTES, &tm_lo, kb * SBK, rt * CP_ADV, bi, bar_a_full(s));
+                    if (++s == CP_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_f16(128, CP_ROWS);
+            mbar_wait(bar_w, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                const int ab = it % p.nacc;
+                const uint32_t acc_ph = (it / p.nacc) & 1;
+                mbar_wait(bar_acc_empty(ab), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc_col + ab * CP_ROWS;
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    mbar_wait(bar_a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t x_hi = a_base + (2 * s) * CP_TILE_BYTES, x_lo = x_hi + CP_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_lo = w_hi + wcols;
+                        const uint64_t dx_hi = smem_desc_sw128(x_hi + k * 32), dx_lo = smem_desc_sw128(x_lo + k * 32);
+                        mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);            // small terms first
+                        mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        mma_f16_ts(d_tmem, w_hi, dx_hi, idesc, 1);
+                    }
+                    mma_commit(bar_a_empty(s));
+                    if (++s == CP_STAGES) { s = 0; ph ^= 1; }
+                }
+                mma_commit(bar_acc_full(ab));
+            }
+        }
+    } else {
+        // ===================== weights -> TMEM, then the pooling epilogue =====================
+        const int q = warp & 3;
+        const int out = q * 32 + lane;                                          // output channel == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int w = 0; w < 2; ++w) {
+            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.ldw);
+            for (int part = 0; part < p.kb * 2; ++part) {
+                uint32_t r[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 v = __ldg(wrow + part * 4 + i);
+                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+                }
+                tmem_st16(lane_addr + w * wcols + part * 16, r);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_w);
+        const bool out_ok = out < p.n_valid;
+        const float bias = (p.bias && out_ok) ? __ldg(p.bias + out) : 0.f;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int ab = it % p.nacc;
+            const uint32_t acc_ph = (it / p.nacc) & 1;
+            const int bi = t / p.tiles_per_batch, rt = t - bi * p.tiles_per_batch;
+            mbar_wait(bar_acc_full(ab), acc_ph);
+            tc_fence_after();
+            float v[2][32];
+            tmem_ld32(lane_addr + acc_col + ab * CP_ROWS, v[0]);
+            tmem_ld32(lane_addr + acc_col + ab * CP_ROWS + 32, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty(ab));
+            if (!out_ok) continue;
+            const int64_t p0 = (int64_t)rt * (CP_ADV / 3);
+            float* dst = p.pooled + ((int64_t)bi * p.P + p0) * p.ldc + out;
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int g = 0; g < CP_ADV / 3; ++g) {
+                // max commutes with the bias add
+                const float m = fmaxf(fmaxf(v[(3 * g) >> 5][(3 * g) & 31], v[(3 * g + 1) >> 5][(3 * g + 1) & 31]),
+                                      v[(3 * g + 2) >> 5][(3 * g + 2) & 31]) + bias;
+                if (p0 + g < p.P) {
+                    dst[(int64_t)g * p.ldc] = m;
+                    sum += m;
+                    sq = fmaf(m, m, sq);
+                }
+            }
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2, (double)sum);
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2 + 1, (double)sq);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ---------------------------------------------------------------- fp32 -> fp16 (hi, lo) planes
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t n, __half* __restrict__ hi,
                                                            __half* __restrict__ lo) {
@@ -1162,6 +1323,44 @@ int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, 
     const int grid = (int)std::min<int64_t>(num_sms, tiles);
     prof_begin(1, st);
     sinc_pool_gemm_kernel<<<grid, SP_THREADS, smem, st>>>(maps, p);
+    prof_end(1, st);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// Conv1d(k = 5) + bias + MaxPool1d(3) + InstanceNorm sums in one launch (conv_pool_gemm_kernel).  a_hi / a_lo: channel-last
+// planes (B, rows_in, row_stride) whose GEMM row t is the K contiguous values from element t * row_stride; L = convolution
+// rows per item; weights [128][ldw] with Kp = ldw rounded-up K columns resident (Kp <= 448).  pooled (B, L / 3, ldc) fp32 and
+// stats (B, n_valid, 2) -- zeroed by the caller -- are written.
+int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int64_t L, int K,
+                          const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, float* pooled,
+                          int ldc, double* stats, int num_sms, cudaStream_t st) {
+    const int64_t P = L / 3;
+    if (B <= 0 || P <= 0) return B200VAD_OK;
+    if (Kp % 64 != 0 || Kp > 448 || K > Kp || ldw < Kp || ldw % 8 != 0 || n_valid < 1 || n_valid > 128 || (row_stride * 2) % 16 != 0 ||
+        (batch_stride * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(a_hi) & 15) || (reinterpret_cast<uintptr_t>(a_lo) & 15)) {
+        set_error("conv_pool_gemm: unsupported shape K=%d Kp=%d ldw=%d n_valid=%d", K, Kp, ldw, n_valid);
+        return B200VAD_EINVAL;
+    }
+    CUtensorMap tm_hi, tm_lo;
+    int rc;
+    if ((rc = make_tmap_3d(&tm_hi, a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, L, B, row_stride * 2, batch_stride * 2, SBK, CP_ROWS, 1,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_3d(&tm_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, K, L, B, row_stride * 2, batch_stride * 2, SBK, CP_ROWS, 1,
+                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    ConvPoolParams p;
+    p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.pooled = pooled; p.stats = stats; p.P = P; p.ldc = ldc; p.n_valid = n_valid;
+    p.ldw = ldw; p.kb = Kp / SBK;
+    p.nacc = (Kp + 2 * CP_ROWS <= 512) ? 2 : 1;                 // 2 * (Kp / 2) weight columns + nacc * 64 accumulator columns <= 512
+    p.tiles_per_batch = (int)((P + CP_ADV / 3 - 1) / (CP_ADV / 3));
+    const int64_t tiles = (int64_t)B * p.tiles_per_batch;
+    if (tiles >= (1LL << 31)) { set_error("conv_pool_gemm: too many tiles"); return B200VAD_EINVAL; }
+    p.num_tiles = (int)tiles;
+    const int smem = 1024 + CP_STAGES * 2 * CP_TILE_BYTES + 256;
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(conv_pool_gemm_kernel), smem))) return rc;
+    const int grid = (int)std::min<int64_t>(num_sms, tiles);
+    prof_begin(1, st);
+    conv_pool_gemm_kernel<<<grid, CP_THREADS, smem, st>>>(tm_hi, tm_lo, p);
     prof_end(1, st);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;

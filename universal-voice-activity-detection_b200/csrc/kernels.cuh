@@ -43,6 +43,9 @@ int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, 
 int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, int B, int64_t L1, const __half* w_hi,
                           const __half* w_lo, int Kp, int ldw, int n_valid, float* pooled, int ldc, double* stats, int num_sms,
                           cudaStream_t st);
+int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int64_t L, int K,
+                          const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, float* pooled,
+                          int ldc, double* stats, int num_sms, cudaStream_t st);
 int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int K, const __half* w_hi,
                         const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
                         size_t sync_bytes, int num_sms, cudaStream_t st);
