@@ -591,15 +591,17 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
             __half* wn_hi = reinterpret_cast<__half*>(wn_raw);
             __half* wn_lo = wn_hi + 4 * (int64_t)bc * Np;
             if ((rc = wave_norm_planes_launch(wav + b0 * wav_stride, bc, N, wav_stride, Np, reinterpret_cast<const float*>(pk + s.wn_w),
-                                              reinterpret_cast<const float*>(pk + s.wn_b), stats, wn_hi, wn_lo, st))) return rc;
+                                              reinterpret_cast<const float*>(pk + s.wn_b), stats, wn_hi, wn_lo, st, 0))) return rc;
             if (sinc_fused()) {
-                // sinc conv + |x| + MaxPool3 + InstanceNorm sums in one launch: the (B, L1, 80) convolution output never exists
+                // (three fp16 products per k-step: the 2-product scheme of the LSTM projections costs 3e-3 on the normalised SincNet
+            // output -- three convolutions and InstanceNorms amplify it -- for 4 % of the front-end time; the kernels keep the option)
+            // sinc conv + |x| + MaxPool3 + InstanceNorm sums in one launch: the (B, L1, 80) convolution output never exists
                 if ((rc = zero_f64_launch(stats, (int64_t)2 * bc * 80, st))) return rc;
                 if ((rc = sinc_pool_gemm_launch(wn_hi, wn_lo, Np, bc, d.L1, reinterpret_cast<const __half*>(pk + s.sinc_t_hi),
-                                                reinterpret_cast<const __half*>(pk + s.sinc_t_lo), kSincTLd, kSincTLd, 80, p1, 80, stats,
+                                                reinterpret_cast<const __half*>(pk + s.sinc_t_lo), kSincTLd, kSincTLd, 80, 3, p1, 80, stats,
                                                 sms, st))) return rc;
                 if ((rc = norm_lrelu_launch(p1, bc, d.P1, 80, stats, reinterpret_cast<const float*>(pk + s.n0_w),
-                                            reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80))) return rc;
+                                            reinterpret_cast<const float*>(pk + s.n0_b), st, p1_hi, p1_lo, 80, 0))) return rc;
             } else {
             // sinc conv, stride 10: rows t = 4 m + r start at 40 m + 10 r -> copy shifted by (10 r) % 8, offset 8 * ((10 r) / 8)
                 for (int r = 0; r < 4; ++r) {
@@ -624,13 +626,13 @@ int b200vad_sincnet_forward_f32(const void* packed, const float* wav, int B, int
                 // Conv1d(80, 60, 5) / Conv1d(60 -> 64 padded, 60, 5): whole K resident in TMEM, bias + MaxPool3 + InstanceNorm sums
                 // in the epilogue (conv_pool_gemm_kernel): neither the convolution outputs nor a K-split partial sum exist
                 if ((rc = zero_f64_launch(stats, (int64_t)2 * bc * 60, st))) return rc;
-                if ((rc = conv_pool_gemm_launch(p1_hi, p1_lo, 80, d.P1 * 80, bc, d.L2, kC1K, w1h, w1l, kC1TLd, kC1TLd, 60, b1, p2, 60, stats,
+                if ((rc = conv_pool_gemm_launch(p1_hi, p1_lo, 80, d.P1 * 80, bc, d.L2, kC1K, w1h, w1l, kC1TLd, kC1TLd, 60, b1, 3, p2, 60, stats,
                                                 sms, st))) return rc;
                 if ((rc = norm_lrelu_launch(p2, bc, d.P2, 60, stats, reinterpret_cast<const float*>(pk + s.n1_w),
-                                            reinterpret_cast<const float*>(pk + s.n1_b), st, p2_hi, p2_lo, kC2Cp))) return rc;
+                                            reinterpret_cast<const float*>(pk + s.n1_b), st, p2_hi, p2_lo, kC2Cp, 0))) return rc;
                 float* o3 = out + b0 * d.P3 * 60;
                 if ((rc = zero_f64_launch(stats, (int64_t)2 * bc * 60, st))) return rc;
-                if ((rc = conv_pool_gemm_launch(p2_hi, p2_lo, kC2Cp, d.P2 * kC2Cp, bc, d.L3, kC2TLd, w2h, w2l, kC2TLd, kC2TLd, 60, b2, o3, 60,
+                if ((rc = conv_pool_gemm_launch(p2_hi, p2_lo, kC2Cp, d.P2 * kC2Cp, bc, d.L3, kC2TLd, w2h, w2l, kC2TLd, kC2TLd, 60, b2, 3, o3, 60,
                                                 stats, sms, st))) return rc;
                 if ((rc = norm_lrelu_launch(o3, bc, d.P3, 60, stats, reinterpret_cast<const float*>(pk + s.n2_w),
                                             reinterpret_cast<const float*>(pk + s.n2_b), st))) return rc;

@@ -180,6 +180,12 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
 }
 
 // fp32 -> (hi, lo) fp16 pair with hi + lo ~= x to ~22 bits
+// two fp16 planes that sum to x: first = fp16(s1 * x), second = fp16(x - first).  s1 = 1: the hi / lo split; s1 = 1 - 2^-6:
+// the scaled split of the 2-product GEMMs (gemm_tc.cu)
+__device__ __forceinline__ void split_scaled_f16(float x, float s1, __half& a, __half& b) {
+    a = __float2half_rn(x * s1);
+    b = __float2half_rn(x - __half2float(a));
+}
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));

@@ -749,6 +749,35 @@ gemm_xg_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
+// Loads the two weight planes of output row `wrow_*` into TMEM (lane = this thread's row): plane 0 = W_hi, plane 1 = W_lo
+// (terms = 3) or W' = fp16(W_hi + W_lo / s) (terms = 2, the scaled-plane product described at gemm_xg2_kernel).
+__device__ __forceinline__ void load_weight_planes(const __half* w_hi_row, const __half* w_lo_row, int parts, uint32_t lane_addr, int wcols, int terms) {
+    const uint4* whi = reinterpret_cast<const uint4*>(w_hi_row);
+    const uint4* wlo = reinterpret_cast<const uint4*>(w_lo_row);
+    for (int part = 0; part < parts; ++part) {                                  // 32 fp16 = 16 packed columns
+        uint32_t ra[16], rb[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 vh = __ldg(whi + part * 4 + i), vl = __ldg(wlo + part * 4 + i);
+            const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                ra[4 * i + e] = hw[e];
+                if (terms == 3) {
+                    rb[4 * i + e] = lw[e];
+                } else {
+                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                    const __half2 wp = __floats2half2_rn(fmaf(fl.x, 1.f / kPlaneScale, fh.x), fmaf(fl.y, 1.f / kPlaneScale, fh.y));
+                    rb[4 * i + e] = *reinterpret_cast<const uint32_t*>(&wp);
+                }
+            }
+        }
+        tmem_st16(lane_addr + part * 16, ra);
+        tmem_st16(lane_addr + wcols + part * 16, rb);
+    }
+}
+
 // ---------------------------------------------------------------- sinc convolution + |x| + MaxPool1d(3) + InstanceNorm sums
 // The stride-10 sinc layer (sincnet.py:50-61, 95-99) as ONE overlapping-row GEMM whose epilogue pools.  Rows t = 4 m + r of
 // residue class r come from their own tensor map (80-byte row stride on the waveform copy shifted by 10 r mod 8 samples,
@@ -770,7 +799,7 @@ struct SincPoolParams {
     float* pooled;           // [B][P][ldc]
     double* stats;           // [B][n_valid][2]
     int64_t P;
-    int ldc, n_valid, ldw, kb, tiles_per_batch, num_tiles;
+    int ldc, n_valid, ldw, kb, tiles_per_batch, num_tiles, terms;
 };
 
 __global__ void __launch_bounds__(SP_THREADS, 1)
@@ -844,8 +873,12 @@ sinc_pool_gemm_kernel(const __grid_constant__ SincMaps maps, SincPoolParams p) {
                     for (int k = 0; k < SBK / 16; ++k) {
                         const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_lo = w_hi + wcols;
                         const uint64_t dx_hi = smem_desc_sw128(x_hi + k * 32), dx_lo = smem_desc_sw128(x_lo + k * 32);
-                        mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);            // small terms first
-                        mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        if (p.terms == 3) {
+                            mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);        // small terms first
+                            mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        } else {
+                            mma_f16_ts(d_tmem, w_lo, dx_lo, idesc, (kb | k) != 0);        // x2 . W' (scaled planes)
+                        }
                         mma_f16_ts(d_tmem, w_hi, dx_hi, idesc, 1);
                     }
                     mma_commit(bar_a_empty(s));
@@ -859,18 +892,7 @@ sinc_pool_gemm_kernel(const __grid_constant__ SincMaps maps, SincPoolParams p) {
         const int q = warp & 3;
         const int out = q * 32 + lane;                                          // output channel == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int w = 0; w < 2; ++w) {
-            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.ldw);
-            for (int part = 0; part < p.kb * 2; ++part) {
-                uint32_t r[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 v = __ldg(wrow + part * 4 + i);
-                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-                }
-                tmem_st16(lane_addr + w * wcols + part * 16, r);
-            }
-        }
+        load_weight_planes(p.w_hi + (size_t)out * p.ldw, p.w_lo + (size_t)out * p.ldw, p.kb * 2, lane_addr, wcols, p.terms);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_w);
@@ -934,7 +956,7 @@ struct ConvPoolParams {
     float* pooled;           // [B][P][ldc]
     double* stats;           // [B][n_valid][2]
     int64_t P;
-    int ldc, n_valid, ldw, kb, nacc, tiles_per_batch, num_tiles;
+    int ldc, n_valid, ldw, kb, nacc, tiles_per_batch, num_tiles, terms;
 };
 
 __global__ void __launch_bounds__(CP_THREADS, 1)
@@ -1006,8 +1028,12 @@ conv_pool_gemm_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
                     for (int k = 0; k < SBK / 16; ++k) {
                         const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_lo = w_hi + wcols;
                         const uint64_t dx_hi = smem_desc_sw128(x_hi + k * 32), dx_lo = smem_desc_sw128(x_lo + k * 32);
-                        mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);            // small terms first
-                        mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        if (p.terms == 3) {
+                            mma_f16_ts(d_tmem, w_hi, dx_lo, idesc, (kb | k) != 0);        // small terms first
+                            mma_f16_ts(d_tmem, w_lo, dx_hi, idesc, 1);
+                        } else {
+                            mma_f16_ts(d_tmem, w_lo, dx_lo, idesc, (kb | k) != 0);        // x2 . W' (scaled planes)
+                        }
                         mma_f16_ts(d_tmem, w_hi, dx_hi, idesc, 1);
                     }
                     mma_commit(bar_a_empty(s));
@@ -1021,18 +1047,7 @@ conv_pool_gemm_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         const int q = warp & 3;
         const int out = q * 32 + lane;                                          // output channel == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int w = 0; w < 2; ++w) {
-            const uint4* wrow = reinterpret_cast<const uint4*>((w == 0 ? p.w_hi : p.w_lo) + (size_t)out * p.ldw);
-            for (int part = 0; part < p.kb * 2; ++part) {
-                uint32_t r[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 v = __ldg(wrow + part * 4 + i);
-                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-                }
-                tmem_st16(lane_addr + w * wcols + part * 16, r);
-            }
-        }
+        load_weight_planes(p.w_hi + (size_t)out * p.ldw, p.w_lo + (size_t)out * p.ldw, p.kb * 2, lane_addr, wcols, p.terms);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_w);
@@ -1289,13 +1304,13 @@ int gemm_ts_rows_launch(const __half* a_hi, const __half* a_lo, int64_t row_stri
 // shifted copies of the normalised waveform, copy e at + e * B * Np (sincnet.cu); L1 = convolution rows per item;
 // pooled (B, L1 / 3, ldc) fp32 and stats (B, n_valid, 2) -- zeroed by the caller -- are written.
 int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, int B, int64_t L1, const __half* w_hi,
-                          const __half* w_lo, int Kp, int ldw, int n_valid, float* pooled, int ldc, double* stats, int num_sms,
-                          cudaStream_t st) {
+                          const __half* w_lo, int Kp, int ldw, int n_valid, int terms, float* pooled, int ldc, double* stats,
+                          int num_sms, cudaStream_t st) {
     const int64_t P = L1 / 3;
     if (B <= 0 || P <= 0) return B200VAD_OK;
     int rc = gemm_ts_check(Kp, Kp, ldw, 128, 8, 2);
     if (rc) return rc;
-    if (n_valid < 1 || n_valid > 128 || (Np * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(wn_hi) & 15) || (reinterpret_cast<uintptr_t>(wn_lo) & 15)) {
+    if ((terms != 2 && terms != 3) || n_valid < 1 || n_valid > 128 || (Np * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(wn_hi) & 15) || (reinterpret_cast<uintptr_t>(wn_lo) & 15)) {
         set_error("sinc_pool_gemm: bad arguments");
         return B200VAD_EINVAL;
     }
@@ -1313,7 +1328,7 @@ int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, 
     }
     SincPoolParams p;
     p.w_hi = w_hi; p.w_lo = w_lo; p.pooled = pooled; p.stats = stats; p.P = P; p.ldc = ldc; p.n_valid = n_valid; p.ldw = ldw;
-    p.kb = Kp / SBK;
+    p.kb = Kp / SBK; p.terms = terms;
     p.tiles_per_batch = (int)((P + SP_TILE_ROWS / 3 - 1) / (SP_TILE_ROWS / 3));
     const int64_t tiles = (int64_t)B * p.tiles_per_batch;
     if (tiles >= (1LL << 31)) { set_error("sinc_pool_gemm: too many tiles"); return B200VAD_EINVAL; }
@@ -1333,11 +1348,11 @@ int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, 
 // rows per item; weights [128][ldw] with Kp = ldw rounded-up K columns resident (Kp <= 448).  pooled (B, L / 3, ldc) fp32 and
 // stats (B, n_valid, 2) -- zeroed by the caller -- are written.
 int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int64_t L, int K,
-                          const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, float* pooled,
-                          int ldc, double* stats, int num_sms, cudaStream_t st) {
+                          const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, int terms,
+                          float* pooled, int ldc, double* stats, int num_sms, cudaStream_t st) {
     const int64_t P = L / 3;
     if (B <= 0 || P <= 0) return B200VAD_OK;
-    if (Kp % 64 != 0 || Kp > 448 || K > Kp || ldw < Kp || ldw % 8 != 0 || n_valid < 1 || n_valid > 128 || (row_stride * 2) % 16 != 0 ||
+    if ((terms != 2 && terms != 3) || Kp % 64 != 0 || Kp > 448 || K > Kp || ldw < Kp || ldw % 8 != 0 || n_valid < 1 || n_valid > 128 || (row_stride * 2) % 16 != 0 ||
         (batch_stride * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(a_hi) & 15) || (reinterpret_cast<uintptr_t>(a_lo) & 15)) {
         set_error("conv_pool_gemm: unsupported shape K=%d Kp=%d ldw=%d n_valid=%d", K, Kp, ldw, n_valid);
         return B200VAD_EINVAL;
@@ -1350,7 +1365,7 @@ int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_st
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     ConvPoolParams p;
     p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.pooled = pooled; p.stats = stats; p.P = P; p.ldc = ldc; p.n_valid = n_valid;
-    p.ldw = ldw; p.kb = Kp / SBK;
+    p.ldw = ldw; p.kb = Kp / SBK; p.terms = terms;
     p.nacc = (Kp + 2 * CP_ROWS <= 512) ? 2 : 1;                 // 2 * (Kp / 2) weight columns + nacc * 64 accumulator columns <= 512
     p.tiles_per_batch = (int)((P + CP_ADV / 3 - 1) / (CP_ADV / 3));
     const int64_t tiles = (int64_t)B * p.tiles_per_batch;

@@ -41,11 +41,11 @@ int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, 
                     const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
                     size_t sync_bytes, int num_sms, cudaStream_t st);
 int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, int B, int64_t L1, const __half* w_hi,
-                          const __half* w_lo, int Kp, int ldw, int n_valid, float* pooled, int ldc, double* stats, int num_sms,
-                          cudaStream_t st);
+                          const __half* w_lo, int Kp, int ldw, int n_valid, int terms, float* pooled, int ldc, double* stats,
+                          int num_sms, cudaStream_t st);
 int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int64_t L, int K,
-                          const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, float* pooled,
-                          int ldc, double* stats, int num_sms, cudaStream_t st);
+                          const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, int terms,
+                          float* pooled, int ldc, double* stats, int num_sms, cudaStream_t st);
 int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int K, const __half* w_hi,
                         const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
                         size_t sync_bytes, int num_sms, cudaStream_t st);
@@ -67,11 +67,11 @@ int repack_conv_launch(const float* w, int Cout, int Cin, int k, float* out, cud
 int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, const float* gamma, const float* beta,
                          double* stats, float* out, cudaStream_t s);
 int norm_lrelu_launch(float* pooled, int B, int64_t P, int C, const double* stats, const float* gamma, const float* beta,
-                      cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0);
+                      cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0, int scaled_planes = 0);
 int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
-                           const float* beta, cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0);
+                           const float* beta, cudaStream_t s, __half* p_hi = nullptr, __half* p_lo = nullptr, int Cp = 0, int scaled_planes = 0);
 int wave_norm_planes_launch(const float* wav, int B, int64_t N, int64_t stride, int64_t Np, const float* gamma, const float* beta,
-                            double* stats, __half* hi, __half* lo, cudaStream_t s);
+                            double* stats, __half* hi, __half* lo, cudaStream_t s, int scaled_planes = 0);
 int pad_rows_launch(const float* w, int Cout, int K, int ld, float* out, cudaStream_t s);
 int repack_conv_pad_launch(const float* w, int Cout, int Cin, int k, int Cp, int ld, float* out, cudaStream_t s);
 

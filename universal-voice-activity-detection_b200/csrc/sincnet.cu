@@ -128,7 +128,7 @@ int wave_instnorm_launch(const float* wav, int B, int64_t N, int64_t stride, con
 __global__ void __launch_bounds__(256) wave_norm_planes_kernel(const float* __restrict__ wav, int64_t N, int64_t stride, int64_t Np,
                                                                int B, const double* __restrict__ stats, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, __half* __restrict__ hi,
-                                                               __half* __restrict__ lo) {
+                                                               __half* __restrict__ lo, float s1) {
     const int b = blockIdx.y;
     double mean = stats[2 * b] / (double)N;
     double var = stats[2 * b + 1] / (double)N - mean * mean;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) wave_norm_planes_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             h[j] = __float2half_rn(0.f); l[j] = h[j];
-            if (i + j < N) split_f16((v[j] - m) * rstd * g + be, h[j], l[j]);
+            if (i + j < N) split_scaled_f16((v[j] - m) * rstd * g + be, s1, h[j], l[j]);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -183,13 +183,13 @@ __global__ void __launch_bounds__(256) wave_norm_planes_kernel(const float* __re
     }
 }
 int wave_norm_planes_launch(const float* wav, int B, int64_t N, int64_t stride, int64_t Np, const float* gamma, const float* beta,
-                            double* stats, __half* hi, __half* lo, cudaStream_t s) {
+                            double* stats, __half* hi, __half* lo, cudaStream_t s, int scaled_planes) {
     { int rc = zero_f64_launch(stats, (int64_t)2 * B, s); if (rc) return rc; }
     dim3 g1((unsigned)((N + 8191) / 8192), B);
     wave_stats_kernel<<<g1, 256, 0, s>>>(wav, N, stride, stats);
     B200VAD_LAUNCH_CHECK();
     dim3 g2((unsigned)((Np + 8 + 2047) / 2048), B);
-    wave_norm_planes_kernel<<<g2, 256, 0, s>>>(wav, N, stride, Np, B, stats, gamma, beta, hi, lo);
+    wave_norm_planes_kernel<<<g2, 256, 0, s>>>(wav, N, stride, Np, B, stats, gamma, beta, hi, lo, scaled_planes ? 1.f - kPlaneScale : 1.f);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict
 // the fp32 copy has no reader there).  Four channels per thread (C % 4 == 0, Cp % 4 == 0).
 __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, int64_t P, int C, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         __half* __restrict__ p_hi, __half* __restrict__ p_lo, int Cp) {
+                                                         __half* __restrict__ p_hi, __half* __restrict__ p_lo, int Cp, float s1) {
     const int b = blockIdx.y;
     __shared__ float sc[128], sh[128];
     if (threadIdx.x < C) {
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, 
         }
         if (p_hi) {
             __align__(8) __half h[4], l[4];
-            split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+            split_scaled_f16(v.x, s1, h[0], l[0]); split_scaled_f16(v.y, s1, h[1], l[1]);
+            split_scaled_f16(v.z, s1, h[2], l[2]); split_scaled_f16(v.w, s1, h[3], l[3]);
             const int64_t o = ((int64_t)b * P + r) * Cp + c;
             *reinterpret_cast<uint2*>(p_hi + o) = *reinterpret_cast<const uint2*>(h);
             *reinterpret_cast<uint2*>(p_lo + o) = *reinterpret_cast<const uint2*>(l);
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(256) norm_lrelu_kernel(float* __restrict__ x, 
     }
 }
 int norm_lrelu_launch(float* pooled, int B, int64_t P, int C, const double* stats, const float* gamma, const float* beta,
-                      cudaStream_t s, __half* p_hi, __half* p_lo, int Cp) {
+                      cudaStream_t s, __half* p_hi, __half* p_lo, int Cp, int scaled_planes) {
     if (P <= 0 || B == 0) return B200VAD_OK;
     if (C > 128 || C < 1 || C % 4 != 0 || (p_hi && (Cp % 4 != 0 || Cp < C))) {
         set_error("norm_lrelu: C in [1,128], C and Cp multiples of 4, Cp >= C");
@@ -300,13 +301,13 @@ int norm_lrelu_launch(float* pooled, int B, int64_t P, int C, const double* stat
     }
     const int64_t groups = P * ((p_hi ? Cp : C) / 4);
     dim3 g2((unsigned)std::min<int64_t>((groups + 1023) / 1024, 65535), B);
-    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta, p_hi, p_lo, Cp);
+    norm_lrelu_kernel<<<g2, 256, 0, s>>>(pooled, P, C, stats, gamma, beta, p_hi, p_lo, Cp, scaled_planes ? 1.f - kPlaneScale : 1.f);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }
 
 int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pooled, double* stats, const float* gamma,
-                           const float* beta, cudaStream_t s, __half* p_hi, __half* p_lo, int Cp) {
+                           const float* beta, cudaStream_t s, __half* p_hi, __half* p_lo, int Cp, int scaled_planes) {
     if (C > 128 || C < 1) {
         set_error("pool_norm: C must be in [1,128]");
         return B200VAD_EINVAL;
@@ -317,7 +318,7 @@ int pool_norm_lrelu_launch(const float* in, int B, int64_t L, int C, float* pool
     dim3 g1((unsigned)((P + kPoolRows - 1) / kPoolRows), B);
     pool_stats_kernel<<<g1, 256, 0, s>>>(in, L, C, P, pooled, stats);
     B200VAD_LAUNCH_CHECK();
-    return norm_lrelu_launch(pooled, B, P, C, stats, gamma, beta, s, p_hi, p_lo, Cp);
+    return norm_lrelu_launch(pooled, B, P, C, stats, gamma, beta, s, p_hi, p_lo, Cp, scaled_planes);
 }
 
 }  // namespace b200vad
