@@ -331,6 +331,11 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+__global__ void zero_i32_kernel(int* __restrict__ p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
 // ---------------------------------------------------------------- 2-MMA input projection (layers >= 1)
 // xg = x . W^T with x and W as fp16 (hi, lo) planes needs three fp16 products for ~2^-21 accuracy (x_lo.W_hi + x_hi.W_lo
 // + x_hi.W_hi) and that makes the K = 256 projections tensor bound.  Two products into ONE accumulator are enough when
@@ -1411,7 +1416,9 @@ int gemm_xg2_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B, 
     p.sync = nullptr; p.sync_stride = (int)std::min<int64_t>(stride, 1 << 30);
     if (sync && stride < (1 << 30) && sizeof(int) * (size_t)groups * stride <= sync_bytes) {
         p.sync = sync;
-        B200VAD_CUDA(cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)groups * stride, st));
+        // (a kernel, not cudaMemsetAsync: a memset may run on a copy engine and queue behind the host session's H2D copies)
+        zero_i32_kernel<<<(unsigned)(((int64_t)groups * stride + 255) / 256), 256, 0, st>>>(sync, (int64_t)groups * stride);
+        B200VAD_LAUNCH_CHECK();
     }
     if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_xg2_kernel), smem))) return rc;
     prof_begin(1, st);
@@ -1451,7 +1458,9 @@ int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B
     p.sync = nullptr; p.sync_stride = (int)std::min<int64_t>(stride, 1 << 30);
     if (sync && stride < (1 << 30) && sizeof(int) * (size_t)groups * stride <= sync_bytes) {
         p.sync = sync;
-        B200VAD_CUDA(cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)groups * stride, st));
+        // (a kernel, not cudaMemsetAsync: a memset may run on a copy engine and queue behind the host session's H2D copies)
+        zero_i32_kernel<<<(unsigned)(((int64_t)groups * stride + 255) / 256), 256, 0, st>>>(sync, (int64_t)groups * stride);
+        B200VAD_LAUNCH_CHECK();
     }
     if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_xg_pair_kernel), smem))) return rc;
     prof_begin(1, st);
