@@ -133,7 +133,8 @@ def test_pyannet2_spread_head_decisions(dev):
 
 
 # ---------------------------------------------------------------- a3/a4 SincNet + PyanNet
-@pytest.mark.parametrize("B,N", [(2, 80000), (3, 16000), (1, 128000)])
+# short inputs: a single pooled tile per layer / a single output frame (tile and pooling-group boundaries of the fused kernels)
+@pytest.mark.parametrize("B,N", [(2, 80000), (3, 16000), (1, 128000), (2, 2000), (1, 1540), (5, 12345)])
 def test_sincnet_and_pyannet(dev, B, N):
     from src.engines import VadModel
     wav = util.synth_wave(B, N, seed=N + 1)
