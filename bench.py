@@ -49,10 +49,10 @@ KERNELS = {
         # stream (and, at 1.3 GHz under the power cap, 81 % of the sustained tensor peak: profiles/r01_ncu_full_summary_v8.md)
         "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
         "executed_over_algorithmic": (3 * 80 + 2 * 3 * 256) / (80 + 3 * 256.0), "traffic": (14.76e9 + 3 * 16.76e9) / 4},
-    2: {"name": "gemm_ts_kernel<1,4> (head linears + classifier, 2 launches/step)", "bound": "hbm", "tensor": True,
-        # y planes 1024 B read -> z1 planes 512 B written, read again -> 4 B probability (classifier fused)
-        "bytes_per_frame": (1024 + 512 + 512 + 4) / 2.0, "flop_per_frame": 2 * (256 * 128 + 128 * 128) / 2.0,
-        "executed_over_algorithmic": 3.0, "traffic": 3.35e9},
+    2: {"name": "head_fused_kernel (head linears + classifier + sigmoid, 1 launch/step)", "bound": "hbm", "tensor": True,
+        # y planes 1024 B read -> 4 B probability (the hidden activations stay in shared memory)
+        "bytes_per_frame": 1024 + 4, "flop_per_frame": 2 * (256 * 128 + 128 * 128),
+        "executed_over_algorithmic": 3.0, "traffic": None},
     3: {"name": "fbank_kernel (frame/window/FFT/mel/log, 1 launch/step)", "bound": "hbm", "tensor": False,
         "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": 3.12e9},
 }

@@ -58,6 +58,10 @@ B200VAD_API int b200vad_set_projection_terms(int terms);
  * k-step (see above); 1 = the same on single CTAs with an 8-warp epilogue; 0 = the general K-split kernel (always 3
  * products; validation, and the path of inputs wider than 256). */
 B200VAD_API int b200vad_set_projection_kernel(int which);
+/* 1 (default): the head (two Linear + LeakyReLU, classifier, sigmoid -- PyanNet2.py:183-187) runs as one kernel whose hidden
+ * activations stay in shared memory; 0: two GEMM launches with the hidden activations as fp16 planes in HBM (validation;
+ * bit-identical probabilities). */
+B200VAD_API int b200vad_set_head_fused(int on);
 /* Sequences per CTA of the tcgen05 recurrence: 0 = automatic (16 while the batch fits one wave of CTAs -- low latency
  * for small batches / streaming --, else 64), or 16 / 64 to force one (validation, tuning). */
 B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);

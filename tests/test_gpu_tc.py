@@ -128,3 +128,26 @@ def test_projection_kernels_agree(dev, B, T):
     assert torch.equal(out[(2, 2)], out[(1, 2)])
     assert util.prob_err(out[(2, 2)], out[(0, 3)]) <= 1e-4
     assert L.b200vad_set_projection_kernel(3) != 0 and L.b200vad_set_projection_terms(4) != 0
+
+
+@pytest.mark.parametrize("B,T", [(70, 64), (7, 333), (1, 2), (129, 41)])
+def test_fused_head_is_bit_identical(dev, B, T):
+    """The one-kernel head (hidden activations in shared memory) issues the same products in the same order as the two-launch
+    head (hidden activations as fp16 planes in HBM): identical probabilities, and both match the oracle."""
+    import b200vad
+    g = torch.Generator().manual_seed(3 * B + T)
+    x = torch.randn(B, T, 80, generator=g) * 3 - 5
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=x)
+    with torch.no_grad():
+        ref = o(x).squeeze(-1)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    L = b200vad.lib()
+    out = {}
+    try:
+        for fused in (0, 1):
+            b200vad._lib.check(L.b200vad_set_head_fused(fused), "set_head_fused")
+            out[fused] = torch.ops.b200vad.lstm_head(x.to(dev), blob, 4).cpu()
+    finally:
+        L.b200vad_set_head_fused(1)
+    assert torch.equal(out[0], out[1])
+    assert util.prob_err(out[1], ref) <= util.PROB_RTOL

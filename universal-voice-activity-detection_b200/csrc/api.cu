@@ -65,6 +65,7 @@ int set_max_dynamic_smem(const void* func, int bytes) {
 
 static int g_impl = 2;        // 2 = tcgen05 kernels (default), 1 = warp-MMA kernels (validation only)
 static int g_proj_terms = 2;  // fp16 products per k-step of the layer >= 1 input projections: 2 (default) or 3 (validation)
+static int g_head_fused = 1;   // head as one kernel (z1 planes stay on chip, default) or as two launches (validation)
 static int g_proj_kernel = 2;  // input projections with K <= 256: 0 = gemm_ts_kernel<3>, 1 = gemm_xg2_kernel, 2 = gemm_xg_pair_kernel (default)
 static int num_sms_cached() {
     static int n = 0;
@@ -245,6 +246,14 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
         // head (PyanNet2.py:183-187) on the same GEMM: planes -> lrelu -> planes -> lrelu -> classifier -> sigmoid;
         // the classifier + sigmoid are the epilogue of the second GEMM; the z1 planes live in the xg buffer (free after
         // the last recurrence).
+        if (g_head_fused) {
+            if ((rc = head_fused_launch(a_hi, a_lo, rows, reinterpret_cast<const __half*>(pk + m.w1_hi),
+                                        reinterpret_cast<const __half*>(pk + m.w1_lo), reinterpret_cast<const __half*>(pk + m.w2_hi),
+                                        reinterpret_cast<const __half*>(pk + m.w2_lo), reinterpret_cast<const float*>(pk + m.b1),
+                                        reinterpret_cast<const float*>(pk + m.b2), reinterpret_cast<const float*>(pk + m.wc),
+                                        reinterpret_cast<const float*>(pk + m.bc), prob + b0 * T, sms, st))) return rc;
+            continue;
+        }
         __half* z1_hi = reinterpret_cast<__half*>(xg);
         __half* z1_lo = z1_hi + rows * kHidden;
         if ((rc = gemm_ts_launch(a_hi, a_lo, 2 * kHidden, rows, 2 * kHidden, reinterpret_cast<const __half*>(pk + m.w1_hi),
@@ -366,6 +375,11 @@ int b200vad_set_impl(int impl) {
 int b200vad_set_projection_terms(int terms) {
     B200VAD_CHECK_ARG(terms == 2 || terms == 3, "terms must be 2 or 3");
     g_proj_terms = terms;
+    return B200VAD_OK;
+}
+
+int b200vad_set_head_fused(int on) {
+    g_head_fused = on != 0;
     return B200VAD_OK;
 }
 

@@ -1095,6 +1095,245 @@ conv_pool_gemm_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------- fused head: Linear(256,128) + LeakyReLU -> Linear(128,128) + LeakyReLU
+//                                                                   -> Linear(128,1) + Sigmoid   (PyanNet2.py:183-187)
+// One kernel instead of two: both weight matrices (hi + lo planes: 256 + 128 TMEM columns) stay in tensor memory next to two
+// 64-column accumulators.  Per tile of 64 frames: acc1 = W1 . y^T (y planes through a TMA ring); the epilogue warps turn acc1
+// into z1 = leaky_relu(acc1 + b1) as fp16 (hi, lo) planes written straight into a swizzled K-major operand tile in shared
+// memory (the way the recurrence writes h); acc2 = W2 . z1^T; the epilogue applies bias, LeakyReLU, the classifier dot
+// product (register transpose-reduction + 4-warp exchange) and the sigmoid.  The z1 planes (1 KB per frame written and read
+// back) never touch HBM.  Same products in the same order as gemm_ts_kernel<1> + <4>: bit-identical probabilities.
+constexpr int HF_THREADS = 320;                      // TMA, MMA, 4 phase-1 warps, 4 phase-2 warps
+constexpr int HF_STAGES = 8;
+constexpr int HF_ROWS = 64;
+constexpr int HF_TILE_BYTES = HF_ROWS * SBK * 2;      // 8 KB
+constexpr int HF_W2_COL = 256, HF_ACC1_COL = 384, HF_ACC2_COL = 448;
+struct HeadFusedParams {
+    const __half* w1_hi;     // [128][256]
+    const __half* w1_lo;
+    const __half* w2_hi;     // [128][128]
+    const __half* w2_lo;
+    const float* b1;         // [128]
+    const float* b2;         // [128]
+    const float* wc;         // [128]
+    const float* bc;         // [1]
+    float* prob;             // [M]
+    int64_t M;
+    int num_tiles;
+};
+
+__global__ void __launch_bounds__(HF_THREADS, 1)
+head_fused_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo, HeadFusedParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* const smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    const uint32_t a_base = smem_base;                                        // [stages][hi, lo] tiles of 64 x 64
+    const uint32_t z_off = HF_STAGES * 2 * HF_TILE_BYTES;                     // z1 operand: [plane 2][kb 2] tiles of 64 x 64
+    const uint32_t z_base = smem_base + z_off;
+    const uint32_t bar_base = z_base + 4 * HF_TILE_BYTES;
+    auto bar_a_full = [&](int s) { return bar_base + 8 * s; };
+    auto bar_a_empty = [&](int s) { return bar_base + 64 + 8 * s; };
+    const uint32_t bar_acc1_full = bar_base + 128, bar_acc1_empty = bar_base + 136, bar_z_full = bar_base + 144,
+                   bar_z_empty = bar_base + 152, bar_acc2_full = bar_base + 160, bar_acc2_empty = bar_base + 168,
+                   bar_w = bar_base + 176, tmem_slot = bar_base + 184;
+    const uint32_t part_smem = bar_base + 192;                                // [2][4 warps][32 rows] fp32 partial dots
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HF_STAGES; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_empty(s), 1); }
+        mbar_init(bar_acc1_full, 1); mbar_init(bar_acc1_empty, 128); mbar_init(bar_z_full, 128); mbar_init(bar_z_empty, 1);
+        mbar_init(bar_acc2_full, 1); mbar_init(bar_acc2_empty, 128); mbar_init(bar_w, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer: y planes, 4 k-blocks per tile =====================
+        if (elect_one()) {
+            tma_prefetch_desc(&tm_y_hi); tma_prefetch_desc(&tm_y_lo);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(bar_a_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_a_full(s), 2 * HF_TILE_BYTES);
+                    tma_load_2d(a_base + (2 * s) * HF_TILE_BYTES, &tm_y_hi, kb * SBK, t * HF_ROWS, bar_a_full(s));
+                    tma_load_2d(a_base + (2 * s + 1) * HF_TILE_BYTES, &tm_y_lo, kb * SBK, t * HF_ROWS, bar_a_full(s));
+                    if (++s == HF_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_f16(128, HF_ROWS);
+            mbar_wait(bar_w, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            auto first_gemm = [&](int i) {                                      // acc1 = W1 . y^T of this CTA's i-th tile
+                mbar_wait(bar_acc1_empty, (i & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(bar_a_full(s), ph);
+                    tc_fence_after();
+                    const uint32_t x_hi = a_base + (2 * s) * HF_TILE_BYTES, x_lo = x_hi + HF_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_hi = tmem_base + (kb * 4 + k) * 8, w_lo = w_hi + 128;
+                        const uint64_t dx_hi = smem_desc_sw128(x_hi + k * 32), dx_lo = smem_desc_sw128(x_lo + k * 32);
+                        mma_f16_ts(tmem_base + HF_ACC1_COL, w_hi, dx_lo, idesc, (kb | k) != 0);
+                        mma_f16_ts(tmem_base + HF_ACC1_COL, w_lo, dx_hi, idesc, 1);
+                        mma_f16_ts(tmem_base + HF_ACC1_COL, w_hi, dx_hi, idesc, 1);
+                    }
+                    mma_commit(bar_a_empty(s));
+                    if (++s == HF_STAGES) { s = 0; ph ^= 1; }
+                }
+                mma_commit(bar_acc1_full);
+            };
+            if (blockIdx.x < p.num_tiles) first_gemm(0);
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                // the next tile's first GEMM needs only acc1 to be drained (the start of phase 1 of this tile): issued first, it
+                // runs while the phase-1 warps are still writing this tile's z1
+                if (t + (int)gridDim.x < p.num_tiles) first_gemm(it + 1);
+                // acc2 = W2 . z1^T once z1 of this tile is in shared memory
+                mbar_wait(bar_z_full, it & 1);
+                mbar_wait(bar_acc2_empty, (it & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < SBK / 16; ++k) {
+                        const uint32_t w_hi = tmem_base + HF_W2_COL + (kb * 4 + k) * 8, w_lo = w_hi + 64;
+                        const uint64_t dz_hi = smem_desc_sw128(z_base + kb * HF_TILE_BYTES + k * 32);
+                        const uint64_t dz_lo = smem_desc_sw128(z_base + (2 + kb) * HF_TILE_BYTES + k * 32);
+                        mma_f16_ts(tmem_base + HF_ACC2_COL, w_hi, dz_lo, idesc, (kb | k) != 0);
+                        mma_f16_ts(tmem_base + HF_ACC2_COL, w_lo, dz_hi, idesc, 1);
+                        mma_f16_ts(tmem_base + HF_ACC2_COL, w_hi, dz_hi, idesc, 1);
+                    }
+                }
+                mma_commit(bar_z_empty);
+                mma_commit(bar_acc2_full);
+            }
+        }
+    } else {
+        // ===================== two epilogue warpgroups: warps 2..5 = phase 1 (weights -> TMEM, then acc1 -> z1 operand tile),
+        //                       warps 6..9 = phase 2 (acc2 -> classifier -> sigmoid); consecutive tiles overlap =====================
+        const int q = warp & 3;
+        const int out = q * 32 + lane;                                          // feature == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (warp < 6) {
+            for (int w = 0; w < 2; ++w) {
+                const uint4* w1 = reinterpret_cast<const uint4*>((w == 0 ? p.w1_hi : p.w1_lo) + (size_t)out * 256);
+                for (int part = 0; part < 8; ++part) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { uint4 v = __ldg(w1 + part * 4 + i); r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
+                    tmem_st16(lane_addr + w * 128 + part * 16, r);
+                }
+                const uint4* w2 = reinterpret_cast<const uint4*>((w == 0 ? p.w2_hi : p.w2_lo) + (size_t)out * 128);
+                for (int part = 0; part < 4; ++part) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { uint4 v = __ldg(w2 + part * 4 + i); r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
+                    tmem_st16(lane_addr + HF_W2_COL + w * 64 + part * 16, r);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_w);
+            const float b1 = __ldg(p.b1 + out);
+            // z1 element (row j, k = out): tile kb = out / 64, 16-byte chunk (out % 64) / 8 XOR (j % 8), byte (out % 8) * 2
+            unsigned char* const z_hi0 = smem_gen + z_off + (out >> 6) * HF_TILE_BYTES + (out & 7) * 2;
+            const uint32_t zc = (out & 63) >> 3;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                mbar_wait(bar_acc1_full, it & 1);
+                tc_fence_after();
+                float v[2][32];
+                tmem_ld32(lane_addr + HF_ACC1_COL, v[0]);
+                tmem_ld32(lane_addr + HF_ACC1_COL + 32, v[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar_acc1_empty);
+                mbar_wait(bar_z_empty, (it & 1) ^ 1);                           // the previous tile's second GEMM has read z1
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = c * 32 + j;
+                        float x = v[c][j] + b1;
+                        x = x > 0.f ? x : 0.01f * x;
+                        __half h, l;
+                        split_f16(x, h, l);
+                        unsigned char* dst = z_hi0 + n * 128 + ((zc ^ (n & 7)) << 4);
+                        *reinterpret_cast<__half*>(dst) = h;
+                        *reinterpret_cast<__half*>(dst + 2 * HF_TILE_BYTES) = l;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(bar_z_full);
+            }
+        } else {
+            const float b2 = __ldg(p.b2 + out), wc = __ldg(p.wc + out);
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                const int64_t row0 = (int64_t)t * HF_ROWS;
+                const int nrows = (int)min((int64_t)HF_ROWS, p.M - row0);
+                mbar_wait(bar_acc2_full, it & 1);
+                tc_fence_after();
+                float v[2][32];
+                tmem_ld32(lane_addr + HF_ACC2_COL, v[0]);
+                tmem_ld32(lane_addr + HF_ACC2_COL + 32, v[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar_acc2_empty);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = v[c][j] + b2;
+                        v[c][j] = wc * (x > 0.f ? x : 0.01f * x);
+                    }
+                    // transpose-reduction: after the step with offset o a lane keeps the rows whose bit o equals its own
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float keep = up ? v[c][i + o] : v[c][i];
+                            const float send = up ? v[c][i] : v[c][i + o];
+                            v[c][i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    const int pb = (it * 2 + c) & 1;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(part_smem + 4 * ((pb * 4 + q) * 32 + lane)), "f"(v[c][0]) : "memory");
+                    named_bar_sync(1, 128);
+                    if (q == 0) {
+                        float sacc = __ldg(p.bc);
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            float pv;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pv) : "r"(part_smem + 4 * ((pb * 4 + w4) * 32 + lane)));
+                            sacc += pv;
+                        }
+                        if (c * 32 + lane < nrows) p.prob[row0 + c * 32 + lane] = 1.f / (1.f + __expf(-sacc));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ---------------------------------------------------------------- fp32 -> fp16 (hi, lo) planes
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t n, __half* __restrict__ hi,
                                                            __half* __restrict__ lo) {
@@ -1382,6 +1621,30 @@ int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_st
     prof_begin(1, st);
     conv_pool_gemm_kernel<<<grid, CP_THREADS, smem, st>>>(tm_hi, tm_lo, p);
     prof_end(1, st);
+    B200VAD_LAUNCH_CHECK();
+    return B200VAD_OK;
+}
+
+// Fused head (head_fused_kernel): y planes [M][256] -> prob [M].  W1 [128][256], W2 [128][128] as fp16 hi / lo planes.
+int head_fused_launch(const __half* y_hi, const __half* y_lo, int64_t M, const __half* w1_hi, const __half* w1_lo, const __half* w2_hi,
+                      const __half* w2_lo, const float* b1, const float* b2, const float* wc, const float* bc, float* prob, int num_sms,
+                      cudaStream_t st) {
+    if (M <= 0) return B200VAD_OK;
+    const int64_t tiles = (M + HF_ROWS - 1) / HF_ROWS;
+    if (tiles >= (1LL << 31)) { set_error("head_fused: too many tiles"); return B200VAD_EINVAL; }
+    CUtensorMap tm_hi, tm_lo;
+    int rc;
+    if ((rc = make_tmap_2d(&tm_hi, y_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 256, M, 256 * 2, SBK, HF_ROWS, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_2d(&tm_lo, y_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 256, M, 256 * 2, SBK, HF_ROWS, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    HeadFusedParams p;
+    p.w1_hi = w1_hi; p.w1_lo = w1_lo; p.w2_hi = w2_hi; p.w2_lo = w2_lo; p.b1 = b1; p.b2 = b2; p.wc = wc; p.bc = bc; p.prob = prob;
+    p.M = M; p.num_tiles = (int)tiles;
+    const int smem = 1024 + HF_STAGES * 2 * HF_TILE_BYTES + 4 * HF_TILE_BYTES + 192 + 1024 + 64;
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(head_fused_kernel), smem))) return rc;
+    const int grid = (int)std::min<int64_t>(num_sms, tiles);
+    prof_begin(2, st);
+    head_fused_kernel<<<grid, HF_THREADS, smem, st>>>(tm_hi, tm_lo, p);
+    prof_end(2, st);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

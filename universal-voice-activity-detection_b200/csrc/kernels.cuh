@@ -46,6 +46,9 @@ int sinc_pool_gemm_launch(const __half* wn_hi, const __half* wn_lo, int64_t Np, 
 int conv_pool_gemm_launch(const __half* a_hi, const __half* a_lo, int64_t row_stride, int64_t batch_stride, int B, int64_t L, int K,
                           const __half* w_hi, const __half* w_lo, int Kp, int ldw, int n_valid, const float* bias, int terms,
                           float* pooled, int ldc, double* stats, int num_sms, cudaStream_t st);
+int head_fused_launch(const __half* y_hi, const __half* y_lo, int64_t M, const __half* w1_hi, const __half* w1_lo, const __half* w2_hi,
+                      const __half* w2_lo, const float* b1, const float* b2, const float* wc, const float* bc, float* prob, int num_sms,
+                      cudaStream_t st);
 int gemm_xg_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int K, const __half* w_hi,
                         const __half* w_lo, int Kp, int ldw, const float* bias, int terms, float* xg, int* sync,
                         size_t sync_bytes, int num_sms, cudaStream_t st);
