@@ -38,7 +38,7 @@ N_SAMPLES = int(SECONDS * 16000)
 T_FRAMES = (N_SAMPLES + 80) // 160
 # Per-kernel algorithmic work per FRAME (10 ms of one utterance; 3 276 800 frames per launch at 4096 x 8 s), DESIGN.md
 # section 4.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture
-# (profiles/r01_ncu_full_summary_v8.md; average over the launches of a kind), bytes per launch at 4096 x 8 s.  `executed_over_algorithmic`: the split-precision
+# (profiles/r01_ncu_full_summary_v10.md; average over the launches of a kind), bytes per launch at 4096 x 8 s.  `executed_over_algorithmic`: the split-precision
 # products execute 3 (layer-0 projection, head) / 2 (layer 1-3 projections; recurrence: two h planes) fp16 MMAs per algorithmic one.
 KERNELS = {
     0: {"name": "lstm_tc_kernel (LSTM recurrence, 4 launches/step)", "bound": "hbm", "tensor": True,
@@ -52,7 +52,7 @@ KERNELS = {
     2: {"name": "head_fused_kernel (head linears + classifier + sigmoid, 1 launch/step)", "bound": "hbm", "tensor": True,
         # y planes 1024 B read -> 4 B probability (the hidden activations stay in shared memory)
         "bytes_per_frame": 1024 + 4, "flop_per_frame": 2 * (256 * 128 + 128 * 128),
-        "executed_over_algorithmic": 3.0, "traffic": None},
+        "executed_over_algorithmic": 3.0, "traffic": 3.38e9},
     3: {"name": "fbank_kernel (frame/window/FFT/mel/log, 1 launch/step)", "bound": "hbm", "tensor": False,
         "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": 3.12e9},
 }
