@@ -151,3 +151,41 @@ def test_fused_head_is_bit_identical(dev, B, T):
         L.b200vad_set_head_fused(1)
     assert torch.equal(out[0], out[1])
     assert util.prob_err(out[1], ref) <= util.PROB_RTOL
+
+
+def test_random_shapes_cross_variants(dev):
+    """Seeded sweep over awkward shapes: the default kernels (CTA-pair projections, one-kernel head) against the general
+    kernels (single-CTA 3-product projections, two-launch head) -- bit-identical with three products, within 1e-4 with two --
+    and the fused SincNet convolutions against the unfused ones' oracle tolerance."""
+    import random
+    import b200vad
+    rnd = random.Random(20261018)
+    o = util.make_oracle("PyanNet2", {"encoding_dim": 80}, spread=True, feats=torch.randn(4, 50, 80) * 3 - 5)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
+    L = b200vad.lib()
+    shapes = [(rnd.randint(1, 200), rnd.randint(1, 90)) for _ in range(10)] + [(1, 1), (64, 1), (65, 2), (31, 3), (33, 127)]
+    try:
+        for B, T in shapes:
+            x = (torch.randn(B, T, 80, generator=torch.Generator().manual_seed(B * 1000 + T)) * 3 - 5).to(dev)
+            outs = {}
+            for name, kern, terms, head in (("general", 0, 3, 0), ("pair3", 2, 3, 1), ("default", 2, 2, 1)):
+                L.b200vad_set_projection_kernel(kern); L.b200vad_set_projection_terms(terms); L.b200vad_set_head_fused(head)
+                outs[name] = torch.ops.b200vad.lstm_head(x, blob, 4).cpu()
+            assert torch.isfinite(outs["default"]).all(), (B, T)
+            assert torch.equal(outs["general"], outs["pair3"]), (B, T)
+            assert util.prob_err(outs["default"], outs["general"]) <= 1e-4, (B, T)
+    finally:
+        L.b200vad_set_projection_kernel(2); L.b200vad_set_projection_terms(2); L.b200vad_set_head_fused(1)
+    # SincNet: odd lengths around tile / pooling-group boundaries of the fused kernels
+    op = util.make_oracle("PyanNet", {})
+    from src.engines import VadModel
+    m = VadModel("PyanNet", {}).eval()
+    m.load_state_dict(op.state_dict())
+    m = m.to(dev)
+    for N in [1540 + 270 * k + rnd.randint(0, 269) for k in (0, 1, 5, 20, 41, 63, 64, 127)]:
+        wav = util.synth_wave(2, N, seed=N)
+        with torch.no_grad():
+            ref = op.model.sincnet(wav.unsqueeze(1))
+            got = m.model.sincnet(wav.to(dev).unsqueeze(1)).cpu()
+        assert got.shape == ref.shape, N
+        assert util.feat_err(got, ref) <= util.FEAT_RTOL, (N, util.feat_err(got, ref))
