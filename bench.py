@@ -214,6 +214,13 @@ def main():
     lo, hi = b200vad.shard_range(rows * world, rank, world)
     wav_host = synth.noise_batch(hi - lo, N_SAMPLES, seed=1234 + rank, pin=True)
     wav_dev = wav_host.to(dev)
+    host_mem = "pinned (cudaHostAlloc via torch)"
+    if os.environ.get("B200VAD_BENCH_WC", "0") == "1":
+        # write-combined pinned staging buffer (b200vad_host_alloc): written once by the producer, read only by the GPU's DMA
+        wc = b200vad.host_buffer(tuple(wav_host.shape), torch.float32, write_combined=True)
+        wc.copy_(wav_host)
+        wav_host = wc
+        host_mem = "pinned write-combined (b200vad_host_alloc)"
     hours_step_global = rows * world * SECONDS / 3600.0
 
     def device_step():
@@ -358,7 +365,7 @@ def main():
                        "frames_per_row": T_FRAMES, "parallelism": f"utterance-sharded x{world}",
                        "l2": f"inputs ({rows * N_SAMPLES * 4 / 1e9:.2f} GB waveforms + GBs of intermediates per step) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "host_numa_node": numa,
+                    "ms_per_step": e2e_ms, "host_numa_node": numa, "host_memory": host_mem,
                     "pcm16_input": {"value": hours_step_global / (pcm_ms / 1e3), "ms_per_step": pcm_ms, "h2d_bytes_per_step": h2d // 2,
                                     "note": "same API fed int16 PCM host waveforms (b200vad_session_submit_host_i16); informational"},
                     "api": "b200vad_session_submit_host / b200vad_session_wait, 2 steps in flight (pinned host waveforms -> host decisions + segments)"},

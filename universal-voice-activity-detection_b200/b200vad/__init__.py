@@ -9,7 +9,7 @@ from . import host  # noqa: F401
 from ._lib import B200VadError, LIB_PATH, lib  # noqa: F401
 from . import ops  # noqa: F401  (registers torch.ops.b200vad.*)
 from .packing import pack_model, pack_sincnet  # noqa: F401
-from .runtime import HostSession, bind_to_gpu_numa, gather_segments, shard_range  # noqa: F401
+from .runtime import HostSession, bind_to_gpu_numa, gather_segments, host_buffer, shard_range  # noqa: F401
 from . import synth  # noqa: F401
 from . import score  # noqa: F401
 from . import corpus  # noqa: F401

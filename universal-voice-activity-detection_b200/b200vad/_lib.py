@@ -30,6 +30,8 @@ PROTOTYPES = {
     "b200vad_set_projection_terms": (c_int, [c_int]),
     "b200vad_set_projection_kernel": (c_int, [c_int]),
     "b200vad_set_head_fused": (c_int, [c_int]),
+    "b200vad_host_alloc": (c_void_p, [c_size_t, c_int]),
+    "b200vad_host_free": (None, [c_void_p]),
     "b200vad_linear_split_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200vad_init": (c_int, [c_int]),
     "b200vad_fbank_num_frames": (c_int64, [c_int64]),

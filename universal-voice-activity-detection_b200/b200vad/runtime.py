@@ -38,6 +38,36 @@ def bind_to_gpu_numa(device_index: int) -> Optional[int]:
         return None
 
 
+class _HostBlock:
+    """Owner of one b200vad_host_alloc allocation (freed when the last tensor view goes away)."""
+
+    def __init__(self, nbytes: int, write_combined: bool):
+        self.ptr = _lib.lib().b200vad_host_alloc(int(nbytes), 1 if write_combined else 0)
+        if not self.ptr:
+            raise _lib.B200VadError("b200vad_host_alloc failed: " + (_lib.lib().b200vad_last_error() or b"").decode())
+        self.buf = (C.c_char * max(int(nbytes), 1)).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                _lib.lib().b200vad_host_free(self.ptr)
+                self.ptr = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def host_buffer(shape, dtype=torch.float32, write_combined: bool = False) -> torch.Tensor:
+    """Page-locked host tensor from ``b200vad_host_alloc`` (optionally write-combined: write it, never read it on the CPU)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    blk = _HostBlock(nbytes, write_combined)
+    t = torch.frombuffer(blk.buf, dtype=dtype, count=n).view(*shape)
+    t._b200vad_block = blk          # keeps the allocation alive as long as this tensor object
+    return t
+
+
 class HostSession:
     """waveforms on the HOST -> decisions / probabilities / segments on the HOST.
 

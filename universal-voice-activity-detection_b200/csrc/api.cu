@@ -378,6 +378,20 @@ int b200vad_set_projection_terms(int terms) {
     return B200VAD_OK;
 }
 
+void* b200vad_host_alloc(size_t bytes, int write_combined) {
+    void* p = nullptr;
+    const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, flags) != cudaSuccess) {
+        set_error("b200vad_host_alloc: cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+void b200vad_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int b200vad_set_head_fused(int on) {
     g_head_fused = on != 0;
     return B200VAD_OK;
