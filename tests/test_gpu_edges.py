@@ -192,3 +192,20 @@ def test_pipeline_properties_at_the_baseline_size(dev):
     err = util.prob_err(prob[rows].cpu(), ref)
     print(f"full-size spot check: rel err of p on 5 rows {err:.2e}, {seg.shape[0]} segments")
     assert err <= util.PROB_RTOL
+
+
+def test_host_buffer_feeds_the_session(dev, blob):
+    """b200vad_host_alloc memory (plain and write-combined) as the session's pinned input: same results as a torch-pinned tensor."""
+    import b200vad
+    _, b = blob
+    wav = util.synth_wave(6, 32000, seed=9)
+    sess = b200vad.HostSession(b, 4, 32000, chunk_rows=8)
+    ref = sess.run(wav.pin_memory(), 0.5, 49, want_dec=True, want_prob=True)
+    for wc in (False, True):
+        hb = b200vad.host_buffer((6, 32000), torch.float32, write_combined=wc)
+        assert hb.shape == (6, 32000) and hb.is_contiguous() and not hb.is_cuda
+        hb.copy_(wav)
+        res = sess.run(hb, 0.5, 49, want_dec=True, want_prob=True)
+        assert torch.equal(res["dec"], ref["dec"]) and torch.equal(res["prob"], ref["prob"]) and torch.equal(res["seg"], ref["seg"])
+        del hb
+    sess.close()
