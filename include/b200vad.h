@@ -70,8 +70,8 @@ B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);
 B200VAD_API int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo,
                              float* c, void* ws, size_t ws_bytes, void* stream);
 
-/* Page-locked host memory for the host-facing session calls (b200vad_session_submit_host ...): what `tensor.pin_memory()` gives in
- * the reference's DataLoader (pin_memory=True).  write_combined != 0 asks for write-combined pages: the producer writes them
+/* Page-locked host memory for the host-facing session calls (b200vad_session_submit_host ...); the reference's DataLoaders
+ * (src/datasets/data_module.py:171-206) hand Lightning pageable batches.  write_combined != 0 asks for write-combined pages: the producer writes them
  * (streaming stores), only the GPU's DMA reads them -- no CPU-cache snooping on the H2D path.  Returns NULL on failure. */
 B200VAD_API void* b200vad_host_alloc(size_t bytes, int write_combined);
 B200VAD_API void b200vad_host_free(void* p);
