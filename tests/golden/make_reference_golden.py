@@ -348,9 +348,9 @@ def main():
         recs.append(rec)
         cuts.append({"id": f"rec{i}-0", "start": 0, "duration": d, "channel": 0, "supervisions": sups, "recording": rec, "type": "MonoCut"})
     for name, items in (("recordings.jsonl.gz", recs), ("cuts.jsonl.gz", cuts)):
-        with gzip.open(os.path.join(mdir, name), "wt") as f:
+        with open(os.path.join(mdir, name), "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as f:   # reproducible bytes
             for it in items:
-                f.write(json.dumps(it) + "\n")
+                f.write((json.dumps(it) + "\n").encode())
     nfr = sum(math.ceil(d / 0.01) + 1 for d in durs)
     rows = (nfr + 499) // 500
     preds = (torch.cumsum(torch.randn(rows * 500, generator=g), 0).reshape(rows, 500, 1) > 0).long()
