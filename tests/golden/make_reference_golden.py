@@ -373,6 +373,72 @@ def main():
                                      "intervals": log["split"] if split else log["merged"], "report": buf.getvalue()}
     meta["get_new_cuts"]["durations"] = durs
 
+    # ---- the SincNet variant: predict_sincnet.get_new_cuts (predict_sincnet.py:294-489): slices of ceil(get_num_frames(16000 d)) + 1
+    # frames, RLE in frame indices, get_timestamp_from_sample_boundary (whole seconds), scoring at 20 ms.  Its tail builds lhotse cuts
+    # (cut.truncate / CutSet.to_file): inert fakes stand in for those objects, which carry no arithmetic.
+    import tempfile
+    import src.scripts.predict_sincnet as PS
+
+    class _Cut(_Obj):
+        def index_supervisions(self, **k):
+            return None
+
+        def truncate(self, **k):
+            return _Cut({"id": self["id"], "start": k.get("offset", 0), "duration": k.get("duration", 0), "supervisions": []})
+
+        def with_id(self, i):
+            self["id"] = i
+            return self
+
+    class _CutSet:
+        @classmethod
+        def from_cuts(cls, cuts):
+            return cls()
+
+        def to_file(self, path):
+            pass
+
+    def _load_s(path):
+        with gzip.open(path, "rt") as f:
+            objs = [json.loads(line) for line in f if line.strip()]
+        return [(_Cut(o) if "supervisions" in o else _Obj(o)) for o in objs]
+
+    PS.load_manifest_lazy = _load_s
+    PS.CutSet = _CutSet
+    sdurs = [4.99, 13.0, 1.5, 20.2, 7.77, 31.4]
+    srecs, scuts = [], []
+    for i, d in enumerate(sdurs):
+        rec = dict(recs[i], duration=d, num_samples=int(round(d * 16000))) if i < len(recs) else None
+        srecs.append(rec)
+        sups = [x for x in cuts[i]["supervisions"] if x["start"] + x["duration"] <= d]
+        scuts.append({"id": f"rec{i}-0", "start": 0, "duration": d, "channel": 0, "supervisions": sups, "recording": rec, "type": "MonoCut"})
+    for name, items in (("recordings_sincnet.jsonl.gz", srecs), ("cuts_sincnet.jsonl.gz", scuts)):
+        with open(os.path.join(mdir, name), "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as f:
+            for it in items:
+                f.write((json.dumps(it) + "\n").encode())
+    nfr_s = sum(math.ceil(rf.get_num_frames(16000 * d)) + 1 for d in sdurs)
+    rows_s = (nfr_s + 292) // 293
+    spreds = (torch.cumsum(torch.randn(rows_s * 293, generator=g), 0).reshape(rows_s, 293, 1) > 0).long()
+    out["gnc_sincnet_preds"] = spreds.numpy().astype(np.uint8)
+    sorig = {k: getattr(PS, k) for k in ("get_false_alarm", "get_missed_detection", "merge_intervals_with_buffer", "split_into_windows")}
+    meta["get_new_cuts_sincnet"] = {"durations": sdurs}
+    with tempfile.TemporaryDirectory() as td:
+        torch.save(spreds, os.path.join(td, "preds.pt"))
+        for tag, buffer, split in (("b0", 0, False), ("b1_split", 1, True)):
+            log = {"fa": [], "md": [], "merged": [], "split": []}
+            PS.get_false_alarm = lambda a, b, log=log: (log["fa"].append(float(sorig["get_false_alarm"](a, b))), sorig["get_false_alarm"](a, b))[1]
+            PS.get_missed_detection = lambda a, b, log=log: (log["md"].append(float(sorig["get_missed_detection"](a, b))), sorig["get_missed_detection"](a, b))[1]
+            PS.merge_intervals_with_buffer = lambda iv, d, b, log=log: (lambda r: (log["merged"].append([list(x) for x in r]), r)[1])(sorig["merge_intervals_with_buffer"](iv, d, b))
+            PS.split_into_windows = lambda iv, window=10, log=log: (lambda r: (log["split"].append([list(x) for x in r]), r)[1])(sorig["split_into_windows"](iv, window=window))
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                PS.get_new_cuts("synthetic", "test", "preds.pt", os.path.join(mdir, "recordings_sincnet.jsonl.gz"),
+                                os.path.join(mdir, "cuts_sincnet.jsonl.gz"), td, "unused.jsonl.gz", buffer=buffer, split=split)
+            for k, v in sorig.items():
+                setattr(PS, k, v)
+            meta["get_new_cuts_sincnet"][tag] = {"buffer": buffer, "split": split, "fa": log["fa"], "md": log["md"],
+                                                 "intervals": log["split"] if split else log["merged"], "report": buf.getvalue()}
+
     # ---- a12: load_config
     cfg = load_config()
     meta["config"] = {k: cfg[k] for k in ("seed", "device", "feature_extractor", "frame_shift", "model_name", "supported_models",

@@ -153,3 +153,30 @@ def test_get_new_cuts_matches_reference(dev, ref, golden_dir, tmp_path):
         sups = manifests.load_manifest(out["output_path"])
         assert len(sups) == sum(len(iv) for iv in want["intervals"])
         assert all(s.recording_id.startswith("rec") and s.duration > 0 for s in sups)
+
+
+def test_get_new_cuts_sincnet_matches_reference(dev, ref, golden_dir, tmp_path):
+    """The drop-in predict_sincnet.get_new_cuts against the reference's own run (predict_sincnet.py:294-489)."""
+    from src.scripts.predict_sincnet import get_new_cuts, get_timestamp_from_sample_boundary
+    z, meta = ref
+    g = meta["get_new_cuts_sincnet"]
+    torch.save(torch.from_numpy(z["gnc_sincnet_preds"].astype(np.int64)), str(tmp_path / "preds.pt"))
+    rp = os.path.join(golden_dir, "manifests", "recordings_sincnet.jsonl.gz")
+    cp = os.path.join(golden_dir, "manifests", "cuts_sincnet.jsonl.gz")
+
+    def report_value(report, name):
+        line = next(l for l in report.splitlines() if l.startswith(name))
+        return float(line.split(":")[1].strip())
+
+    for tag in ("b0", "b1_split"):
+        want = g[tag]
+        out = get_new_cuts("synthetic", "test", "preds.pt", rp, cp, str(tmp_path), f"pred_{tag}.jsonl.gz", buffer=want["buffer"],
+                           split=want["split"], verbose=False)
+        assert [[list(x) for x in iv] for iv in out["intervals"]] == want["intervals"], tag
+        fa = [float(out["fa_frames"][i] / out["nframes"][i]) for i in range(len(want["fa"]))]
+        md = [float(out["md_frames"][i] / out["nframes"][i]) for i in range(len(want["md"]))]
+        assert fa == want["fa"] and md == want["md"], tag
+        for key, name in (("detection_error", "Detection Error Rate"), ("false_alarm", "False Alarm Rate"), ("missed_detection", "Missed Detection Rate")):
+            assert float(out[key]) == report_value(want["report"], name), (tag, key)
+    for (a, b, d), w in zip(z["sinc_ts_in"].tolist(), z["sinc_ts_out"].tolist()):
+        assert list(get_timestamp_from_sample_boundary(a, b, d)) == w

@@ -232,3 +232,41 @@ def test_manifest_round_trip(tmp_path, golden_dir):
     assert np.array_equal(manifests.load_recording_pcm16(rec, root=str(tmp_path)), x)
     with pytest.raises(ValueError):
         manifests.load_recording_pcm16(dict(rec, sources=[{"type": "url", "source": "x"}]))
+
+
+def test_get_new_cuts_sincnet_chain(ref, golden_dir):
+    """predict_sincnet.get_new_cuts (predict_sincnet.py:294-489), run in full by the reference's own code: SincNet frame counts per
+    recording, frame-index RLE, whole-second timestamps, scoring on the 20 ms grid."""
+    import b200vad.host as host
+    from b200vad import manifests
+    z, meta = ref
+    g = meta["get_new_cuts_sincnet"]
+    recs = manifests.load_manifest(os.path.join(golden_dir, "manifests", "recordings_sincnet.jsonl.gz"))
+    cuts = manifests.load_manifest(os.path.join(golden_dir, "manifests", "cuts_sincnet.jsonl.gz"))
+    durs = [r.duration for r in recs]
+    assert durs == g["durations"]
+    preds = torch.from_numpy(z["gnc_sincnet_preds"].astype(np.int64))
+    streams = oracle.slice_recordings(preds.reshape(-1), durs, sincnet=True)
+    offs = host.recording_offsets(durs, preds.numel(), 0.02, sincnet=True)
+    assert [len(s) for s in streams] == [b - a for a, b in zip(offs[:-1], offs[1:])]
+    for tag in ("b0", "b1_split"):
+        want = g[tag]
+        for i, s in enumerate(streams):
+            iv = oracle.merge_intervals_with_buffer(oracle.rle_segments_sincnet(s.tolist(), durs[i]), durs[i], want["buffer"])
+            if want["split"]:
+                iv = oracle.split_into_windows(iv, window=10)
+            assert [list(x) for x in iv] == want["intervals"][i], (tag, i)
+            # integer runs (min_run = 1) + the host epilogue give the same intervals
+            rows = [(0, a, b) for a, b in zip(*_runs(s.numpy()))]
+            hv = host.merge_intervals_with_buffer(host.segments_to_intervals(rows, 1, 0.02, sincnet_durations=[durs[i]])[0], durs[i], want["buffer"])
+            if want["split"]:
+                hv = host.split_into_windows(hv, window=10)
+            assert [list(x) for x in hv] == want["intervals"][i], (tag, i)
+            gt = oracle.get_binary_tensor([(sup.start, sup.start + sup.duration) for sup in cuts[i].supervisions], durs[i], 0.02)
+            pr = oracle.get_binary_tensor(iv, durs[i], 0.02)
+            assert float(oracle.get_false_alarm(gt, pr)) == want["fa"][i] and float(oracle.get_missed_detection(gt, pr)) == want["md"][i]
+
+
+def _runs(a):
+    d = np.diff(np.concatenate([[0], (np.asarray(a) >= 0.5).astype(np.int8), [0]]))
+    return np.nonzero(d == 1)[0].tolist(), (np.nonzero(d == -1)[0] - 1).tolist()
