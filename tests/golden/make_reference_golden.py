@@ -439,6 +439,15 @@ def main():
             meta["get_new_cuts_sincnet"][tag] = {"buffer": buffer, "split": split, "fa": log["fa"], "md": log["md"],
                                                  "intervals": log["split"] if split else log["merged"], "report": buf.getvalue()}
 
+    # ---- a6 glue: binary_cross_entropy / interpolate (src/utils/loss.py:29-89), evaluated (and discarded) by _common_step
+    from src.utils.loss import binary_cross_entropy
+    bp = torch.rand(3, 40, 1, generator=g) * 0.98 + 0.01
+    bt = (torch.rand(3, 40, generator=g) > 0.5).float()
+    bw = torch.rand(3, 10, 1, generator=g)
+    out["bce_pred"], out["bce_target"], out["bce_weight"] = bp.numpy(), bt.numpy(), bw.numpy()
+    out["bce_plain"] = binary_cross_entropy(bp, bt, weight=None).numpy()
+    out["bce_weighted"] = binary_cross_entropy(bp, bt, weight=bw).numpy()
+
     # ---- a12: load_config
     cfg = load_config()
     meta["config"] = {k: cfg[k] for k in ("seed", "device", "feature_extractor", "frame_shift", "model_name", "supported_models",

@@ -270,3 +270,12 @@ def test_get_new_cuts_sincnet_chain(ref, golden_dir):
 def _runs(a):
     d = np.diff(np.concatenate([[0], (np.asarray(a) >= 0.5).astype(np.int8), [0]]))
     return np.nonzero(d == 1)[0].tolist(), (np.nonzero(d == -1)[0] - 1).tolist()
+
+
+def test_loss_glue(ref):
+    """binary_cross_entropy (src/utils/loss.py:56-89): the value _common_step computes and predict_step discards."""
+    from src.utils.loss import binary_cross_entropy
+    z, _ = ref
+    bp, bt, bw = (torch.from_numpy(z[k]) for k in ("bce_pred", "bce_target", "bce_weight"))
+    assert abs(float(binary_cross_entropy(bp, bt)) - float(z["bce_plain"])) <= 1e-7
+    assert abs(float(binary_cross_entropy(bp, bt, weight=bw)) - float(z["bce_weighted"])) <= 1e-7
