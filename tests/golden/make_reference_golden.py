@@ -271,6 +271,13 @@ def main():
     out["rf_conv1d"] = np.array([rf.conv1d_num_frames(n, 5, 1) for n in (5, 6, 100)] + [rf.conv1d_num_frames(n, 251, 10) for n in (251, 1000)],
                                 dtype=np.int64)
 
+    KS, ST, PD, DL = [251, 3, 5, 3, 5, 3], [10, 3, 1, 3, 1, 3], [0] * 6, [1] * 6
+    out["rf_multi_frames"] = np.array([rf.multi_conv_num_frames(n, kernel_size=KS, stride=ST, padding=PD, dilation=DL) for n in (991, 16000, 80000)], dtype=np.int64)
+    out["rf_multi_size"] = np.array([rf.multi_conv_receptive_field_size(k, kernel_size=KS, stride=ST, dilation=DL) for k in (1, 2, 471)], dtype=np.int64)
+    out["rf_conv_size"] = np.array([rf.conv1d_receptive_field_size(k, kernel_size=5, stride=3, dilation=1) for k in (1, 2, 10)], dtype=np.int64)
+    out["rf_conv_center"] = np.array([rf.conv1d_receptive_field_center(f, kernel_size=251, stride=10, padding=0, dilation=1) for f in (0, 1, 100)], dtype=np.int64)
+    out["rf_multi_center"] = np.array([rf.multi_conv_receptive_field_center(f, kernel_size=KS, stride=ST, padding=PD, dilation=DL) for f in (0, 1, 292)], dtype=np.int64)
+
     # ---- a8 / a8' / a10 / f1: predict.py and predict_sincnet.py pieces
     pred_py = os.path.join(REF, "src/scripts/predict.py")
     psinc_py = os.path.join(REF, "src/scripts/predict_sincnet.py")

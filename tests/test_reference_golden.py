@@ -279,3 +279,15 @@ def test_loss_glue(ref):
     bp, bt, bw = (torch.from_numpy(z[k]) for k in ("bce_pred", "bce_target", "bce_weight"))
     assert abs(float(binary_cross_entropy(bp, bt)) - float(z["bce_plain"])) <= 1e-7
     assert abs(float(binary_cross_entropy(bp, bt, weight=bw)) - float(z["bce_weighted"])) <= 1e-7
+
+
+def test_receptive_field_module_functions(ref):
+    """Every function of src/utils/receptive_field.py (:28-219) against the reference's own values."""
+    from src.utils import receptive_field as rf
+    z, _ = ref
+    KS, ST, PD, DL = [251, 3, 5, 3, 5, 3], [10, 3, 1, 3, 1, 3], [0] * 6, [1] * 6
+    assert [rf.multi_conv_num_frames(n, kernel_size=KS, stride=ST, padding=PD, dilation=DL) for n in (991, 16000, 80000)] == z["rf_multi_frames"].tolist()
+    assert [rf.multi_conv_receptive_field_size(k, kernel_size=KS, stride=ST, dilation=DL) for k in (1, 2, 471)] == z["rf_multi_size"].tolist()
+    assert [rf.conv1d_receptive_field_size(k, kernel_size=5, stride=3, dilation=1) for k in (1, 2, 10)] == z["rf_conv_size"].tolist()
+    assert [rf.conv1d_receptive_field_center(f, kernel_size=251, stride=10, padding=0, dilation=1) for f in (0, 1, 100)] == z["rf_conv_center"].tolist()
+    assert [rf.multi_conv_receptive_field_center(f, kernel_size=KS, stride=ST, padding=PD, dilation=DL) for f in (0, 1, 292)] == z["rf_multi_center"].tolist()
