@@ -18,7 +18,8 @@ absent, no network).  What pins the oracle:
     arithmetic on these paths; fixtures tests/golden/reference_golden.{npz,json}; checked by
     tests/test_reference_golden.py): PyanNet2 construction + forward and VadModel.forward / predict_step (models.py),
     median_filter, the RLE + seconds arithmetic of both time bases, merge / split, the DER helpers (postproc.py), the
-    frame arithmetic (receptive_field.py).  Under manual_seed(42) the oracle's weights equal the reference's bit for bit.
+    frame arithmetic (receptive_field.py); SincNet / PyanNet structure (the reference's classes run with this package's
+    ParamSincFB / Encoder as their filterbank).  Under manual_seed(42) the oracle's weights equal the reference's bit for bit.
   * PARITY UNPINNED for the two pieces whose arithmetic lives in third-party code that is not under /root/reference:
     lhotse ``Fbank`` (un-pinned editable checkout, requirements.txt:13; fbank.py) and asteroid-filterbanks==0.4
     ``ParamSincFB`` (requirements.txt:1; the filter synthesis inside models.SincNet -- the rest of SincNet is

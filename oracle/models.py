@@ -7,6 +7,8 @@ TEST INFRASTRUCTURE ONLY.  Module structure and state-dict keys follow
   src/engines/vad_engine.py:30-42,204-211,247-278 (VadModel forward / predict_step)
 PyanNet2 and VadModel are PINNED to the reference's own code (weights under a seed, forward, predict_step:
 tests/golden/make_reference_golden.py, tests/test_reference_golden.py).
+SincNet and PyanNet are PINNED in structure: the reference's own classes, run with this module's ParamSincFB / Encoder as their
+asteroid_filterbanks, give the same seeded weights and outputs (same generator / tests).
 ``ParamSincFB`` / ``Encoder`` restate asteroid-filterbanks==0.4 (requirements.txt:1),
 which is not under /root/reference and not installed here: PARITY UNPINNED for that
 filter synthesis.

@@ -175,6 +175,15 @@ def main():
         a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
         return orig_to(self, *a, **k)
 
+    # asteroid-filterbanks (requirements.txt:1) is absent: the reference's SincNet gets the oracle's restatement of
+    # Encoder / ParamSincFB as its filterbank, so that everything ELSE in sincnet.py / PyanNet.py (the convolution stack, |x| on the
+    # sinc layer only, MaxPool3 -> InstanceNorm -> LeakyReLU order, the "b f t -> b t f" rearrange, the head) is the reference's own
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import oracle.models as oracle_models
+    afb = types.ModuleType("asteroid_filterbanks")
+    afb.Encoder, afb.ParamSincFB = oracle_models.Encoder, oracle_models.ParamSincFB
+    sys.modules["asteroid_filterbanks"] = afb
+
     from src.engines.vad_engine import VadModel                      # the reference's own modules
     from src.models.segmentation.PyanNet2 import PyanNet2
     from src.utils.helper import median_filter
@@ -226,6 +235,23 @@ def main():
             out[f"{tag}_prob"] = m(x).numpy()
         for k, v in m.state_dict().items():
             out[f"{tag}_w_{k}"] = v.numpy()
+
+    # ---- a3 / a4: the reference's PyanNet / SincNet classes around the restated filterbank
+    torch.manual_seed(42)
+    vmp = VadModel("PyanNet", {}).eval()
+    meta["pyannet_seed42_state_sha256"] = state_hash(vmp.state_dict())
+    meta["pyannet_state_keys"] = {k: list(v.shape) for k, v in vmp.state_dict().items()}
+    wavp = 0.1 * torch.randn(2, 16000, generator=g)
+    wavp[1] *= torch.linspace(0.0, 1.0, 16000)
+    with torch.no_grad():
+        out["pyannet_wav"] = wavp.numpy()
+        out["pyannet_sincnet"] = vmp.model.sincnet(wavp.unsqueeze(1)).numpy()
+        out["pyannet_prob"] = vmp.model(wavp.unsqueeze(1)).numpy()
+        torch.Tensor.to = to_cpu_for_cuda
+        try:
+            out["pyannet_predict"] = vmp.predict_step({"inputs": wavp, "is_voice": torch.zeros(2, out["pyannet_prob"].shape[1])}, 0).numpy()
+        finally:
+            torch.Tensor.to = orig_to
 
     # ---- a6: SSL-dim model -> median window 25 (vad_engine.py:207)
     torch.manual_seed(42)

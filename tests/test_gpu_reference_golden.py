@@ -180,3 +180,21 @@ def test_get_new_cuts_sincnet_matches_reference(dev, ref, golden_dir, tmp_path):
             assert float(out[key]) == report_value(want["report"], name), (tag, key)
     for (a, b, d), w in zip(z["sinc_ts_in"].tolist(), z["sinc_ts_out"].tolist()):
         assert list(get_timestamp_from_sample_boundary(a, b, d)) == w
+
+
+def test_pyannet_against_reference_classes(dev, ref):
+    """The drop-in PyanNet on the GPU against the reference's own SincNet / PyanNet classes (run with the restated filterbank)."""
+    from src.engines import VadModel
+    z, meta = ref
+    torch.manual_seed(42)
+    m = VadModel("PyanNet", {}).eval()
+    assert state_hash(m.state_dict()) == meta["pyannet_seed42_state_sha256"]
+    m = m.to(dev)
+    wav = torch.from_numpy(z["pyannet_wav"]).to(dev)
+    with torch.no_grad():
+        s = m.model.sincnet(wav.unsqueeze(1)).cpu()
+        p = m.model(wav.unsqueeze(1)).cpu()
+        d = m.predict_step({"inputs": wav, "is_voice": torch.zeros(2, p.shape[1], device=dev)}, 0).cpu()
+    assert util.feat_err(s, torch.from_numpy(z["pyannet_sincnet"])) <= util.FEAT_RTOL
+    assert util.prob_err(p, torch.from_numpy(z["pyannet_prob"])) <= util.PROB_RTOL
+    assert np.array_equal(d.numpy(), z["pyannet_predict"])

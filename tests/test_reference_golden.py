@@ -291,3 +291,27 @@ def test_receptive_field_module_functions(ref):
     assert [rf.conv1d_receptive_field_size(k, kernel_size=5, stride=3, dilation=1) for k in (1, 2, 10)] == z["rf_conv_size"].tolist()
     assert [rf.conv1d_receptive_field_center(f, kernel_size=251, stride=10, padding=0, dilation=1) for f in (0, 1, 100)] == z["rf_conv_center"].tolist()
     assert [rf.multi_conv_receptive_field_center(f, kernel_size=KS, stride=ST, padding=PD, dilation=DL) for f in (0, 1, 292)] == z["rf_multi_center"].tolist()
+
+
+def test_pyannet_structure_against_reference_classes(ref):
+    """The reference's own SincNet / PyanNet / VadModel classes, run with the oracle's restatement of asteroid's filterbank as
+    their `asteroid_filterbanks` (the one absent piece): the oracle's -- and the drop-in's -- seeded weights are identical and
+    the oracle reproduces SincNet output, probabilities and decisions.  Pins a3 / a4 except the filter synthesis itself."""
+    from src.engines import VadModel as DropIn
+    z, meta = ref
+    if meta["torch_version"] != torch.__version__:
+        pytest.skip("fixtures were generated with another torch version")
+    o = util.make_oracle("PyanNet", {}, seed=42)
+    assert {k: list(v.shape) for k, v in o.state_dict().items()} == meta["pyannet_state_keys"]
+    assert state_hash(o.state_dict()) == meta["pyannet_seed42_state_sha256"]
+    torch.manual_seed(42)
+    d = DropIn("PyanNet", {})
+    assert state_hash(d.state_dict()) == meta["pyannet_seed42_state_sha256"]
+    wav = torch.from_numpy(z["pyannet_wav"])
+    with torch.no_grad():
+        s = o.model.sincnet(wav.unsqueeze(1))
+        p = o.model(wav.unsqueeze(1))
+        dec = o.predict_step({"inputs": wav})
+    assert np.abs(s.numpy() - z["pyannet_sincnet"]).max() <= 1e-5
+    assert np.abs(p.numpy() - z["pyannet_prob"]).max() <= ATOL
+    assert np.array_equal(dec.numpy(), z["pyannet_predict"])
