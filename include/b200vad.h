@@ -65,6 +65,13 @@ B200VAD_API int b200vad_set_head_fused(int on);
 /* Sequences per CTA of the tcgen05 recurrence: 0 = automatic (16 while the batch fits one wave of CTAs -- low latency
  * for small batches / streaming --, else 64), or 16 / 64 to force one (validation, tuning). */
 B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);
+/* LSTM layers with input width <= 256 (PyanNet2.py:95,170): 1 (default) = one fused kernel per layer on 4-CTA clusters
+ * (input projection + recurrence, W_ih and W_hh as two fp16 planes each in tensor memory, no intermediate in HBM);
+ * 0 = the round-1 path (projection GEMM -> xg in HBM -> recurrence with a single-plane W_hh), kept for cross-validation
+ * and for wider inputs (768-dim SSL features on layer 0). */
+B200VAD_API int b200vad_set_lstm_fused(int on);
+/* clusters of 4 CTAs of the fused LSTM kernel that are co-resident on the current device (cudaOccupancyMaxActiveClusters) */
+B200VAD_API int b200vad_lstm_fused_clusters(void);
 /* Split-precision linear layer on the tcgen05 GEMM: c[M,N] = a[M,K] . w[N,K]^T + bias, fp32 in / out, operands
  * split into fp16 (hi, lo) planes in `ws` (K % 8 == 0, N % 128 == 0; weights must fit in shared memory). */
 B200VAD_API int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo,

@@ -16,10 +16,12 @@ def prob_err(a, ref):
     return ((a.double() - ref.double()).abs() / ref.double().abs().clamp_min(1e-12)).max().item()
 
 
-def make_oracle(model_name="PyanNet2", model_dict=None, seed=42, spread=False, feats=None):
+def make_oracle(model_name="PyanNet2", model_dict=None, seed=42, spread=False, feats=None, sigma=0.5):
     """Reference-layout model with torch default init under manual_seed(seed).  ``spread`` rescales the
     classifier so probabilities span (0, 1) on ``feats`` (random-init outputs sit within 1e-3 of a
-    constant, SURVEY 7 'hard parts'), which makes decisions / segments non-degenerate."""
+    constant, SURVEY 7 'hard parts'), which makes decisions / segments non-degenerate.  ``sigma`` is the
+    standard deviation of the logits after rescaling: 0.5 gives p in about (0.2, 0.8); 2 and 4 are what a
+    TRAINED detector looks like (p from 1e-4 to 1 - 1e-4) and are where operand rounding shows."""
     import oracle
     torch.manual_seed(seed)
     m = oracle.VadModel(model_name, dict(model_dict or {})).eval()
@@ -35,7 +37,7 @@ def make_oracle(model_name="PyanNet2", model_dict=None, seed=42, spread=False, f
                 y = torch.nn.functional.leaky_relu(lin(y))
             z = net.classifier(y)
             mu, sd = z.mean(), z.std().clamp_min(1e-6)
-            scale = 0.5 / sd     # logits ~ N(0, 0.5): p spans about (0.2, 0.8)
+            scale = sigma / sd   # logits ~ N(0, sigma)
             net.classifier.weight.mul_(scale)
             net.classifier.bias.copy_((net.classifier.bias - mu) * scale)
     return m

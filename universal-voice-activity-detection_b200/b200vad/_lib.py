@@ -27,6 +27,8 @@ PROTOTYPES = {
     "b200vad_profile_collect": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_int)]),
     "b200vad_set_impl": (c_int, [c_int]),
     "b200vad_set_lstm_tile": (c_int, [c_int]),
+    "b200vad_set_lstm_fused": (c_int, [c_int]),
+    "b200vad_lstm_fused_clusters": (c_int, []),
     "b200vad_set_projection_terms": (c_int, [c_int]),
     "b200vad_set_projection_kernel": (c_int, [c_int]),
     "b200vad_set_head_fused": (c_int, [c_int]),

@@ -66,6 +66,7 @@ int set_max_dynamic_smem(const void* func, int bytes) {
 static int g_impl = 2;        // 2 = tcgen05 kernels (default), 1 = warp-MMA kernels (validation only)
 static int g_proj_terms = 2;  // fp16 products per k-step of the layer >= 1 input projections: 2 (default) or 3 (validation)
 static int g_head_fused = 1;   // head as one kernel (z1 planes stay on chip, default) or as two launches (validation)
+static int g_lstm_fused = 1;   // layers with D <= 256: 1 = fused projection + recurrence on 4-CTA clusters (default), 0 = projection GEMM -> xg -> recurrence
 static int g_proj_kernel = 2;  // input projections with K <= 256: 0 = gemm_ts_kernel<3>, 1 = gemm_xg2_kernel, 2 = gemm_xg_pair_kernel (default)
 static int num_sms_cached() {
     static int n = 0;
@@ -83,7 +84,7 @@ static inline int round64(int k) { return (k + 63) / 64 * 64; }
 
 // ---------------------------------------------------------------- packed model layout
 struct LayerOff {
-    size_t wih_hi, wih_lo, bias, whh;
+    size_t wih_hi, wih_lo, bias, whh, whh_lo;
     int D, Kp;
 };
 struct ModelLayout {
@@ -101,6 +102,7 @@ static ModelLayout model_layout(int D, int L) {
         o.wih_lo = off; off = align_up(off + sizeof(__half) * 2 * kGates * o.Kp);
         o.bias = off;   off = align_up(off + sizeof(float) * 2 * kGates);
         o.whh = off;    off = align_up(off + sizeof(__half) * 2 * kGates * kHidden);
+        o.whh_lo = off; off = align_up(off + sizeof(__half) * 2 * kGates * kHidden);
         m.layers.push_back(o);
     }
     m.w1_hi = off; off = align_up(off + sizeof(__half) * kHidden * 2 * kHidden);
@@ -219,6 +221,17 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
             int* const sync = reinterpret_cast<int*>(x_hi);
             const size_t sync_bytes = 2 * align_up(sizeof(__half) * D8 * rows);
             const int terms = (l > 0 && g_proj_terms == 2) ? 2 : 3;
+            if (g_lstm_fused && lstm_fused_supported(lo.D)) {
+                // one kernel per layer: W_ih and W_hh (two planes each) resident in tensor memory, no xg round trip
+                __half* fyh = reinterpret_cast<__half*>(outbuf);
+                __half* fyl = fyh + rows * 2 * kHidden;
+                const int fscaled = (g_proj_terms == 2 && l + 1 < L) ? 1 : 0;
+                if ((rc = lstm_fused_launch(a_hi, a_lo, lda, bc, (int)T, lo.D, w_hi, w_lo, lo.Kp, reinterpret_cast<const __half*>(pk + lo.whh),
+                                            reinterpret_cast<const __half*>(pk + lo.whh_lo), bias, terms, fyh, fyl, fscaled, st))) return rc;
+                a_hi = fyh; a_lo = fyl; lda = 2 * kHidden;
+                outbuf = (outbuf == buf0) ? buf1 : buf0;
+                continue;
+            }
             if (g_proj_kernel != 0 && lo.D <= 256) {
                 // one launch, both weight planes resident in TMEM; the lockstep counters live in the layer-0 input planes'
                 // workspace, which is free when the planes come from the fused fbank and dead after layer 0
@@ -403,6 +416,11 @@ int b200vad_set_projection_kernel(int which) {
     return B200VAD_OK;
 }
 
+int b200vad_set_lstm_fused(int on) {
+    g_lstm_fused = on ? 1 : 0;
+    return B200VAD_OK;
+}
+int b200vad_lstm_fused_clusters(void) { return lstm_fused_clusters(); }
 int b200vad_set_lstm_tile(int sequences_per_cta) {
     int rc = lstm_tc_set_tile(sequences_per_cta);
     if (rc) set_error("b200vad_set_lstm_tile: must be 0 (automatic), 16 or 64");
@@ -463,7 +481,8 @@ int b200vad_model_pack_lstm(void* packed, int D, int L, int layer, int dir, cons
     if (rc) return rc;
     rc = add_bias(b_ih, b_hh, reinterpret_cast<float*>(pk + lo.bias) + dir * kGates, kGates, st);
     if (rc) return rc;
-    return pack_whh(w_hh, reinterpret_cast<__half*>(pk + lo.whh) + (size_t)dir * kGates * kHidden, st);
+    return pack_whh(w_hh, reinterpret_cast<__half*>(pk + lo.whh) + (size_t)dir * kGates * kHidden, st,
+                    reinterpret_cast<__half*>(pk + lo.whh_lo) + (size_t)dir * kGates * kHidden);
 }
 
 int b200vad_model_pack_head(void* packed, int D, int L, const float* w1, const float* b1, const float* w2, const float* b2,

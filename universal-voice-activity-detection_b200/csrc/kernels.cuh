@@ -58,7 +58,13 @@ int gemm_ts_xg_launch(const __half* x_hi, const __half* x_lo, int64_t lda, int B
 int split_planes_pad_launch(const float* x, int64_t rows, int D, int D8, __half* hi, __half* lo, cudaStream_t st);
 int split_planes_launch(const float* x, int64_t n, __half* hi, __half* lo, cudaStream_t st);
 int classifier_launch(const float* z, int64_t rows, const float* wc, const float* bc, float* prob, cudaStream_t stream);
-int pack_whh(const float* w, __half* out, cudaStream_t stream);
+int pack_whh(const float* w, __half* out, cudaStream_t stream, __half* out_lo = nullptr);
+// fused projection + recurrence on 4-CTA clusters (lstm_fused.cu); D <= 256
+int lstm_fused_supported(int D);
+int lstm_fused_clusters();
+int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int D, const __half* wih_hi,
+                      const __half* wih_lo, int ldw, const __half* whh_hi, const __half* whh_lo, const float* bias, int terms,
+                      __half* y_a, __half* y_b, int y_scaled, cudaStream_t st);
 int add_bias(const float* a, const float* b, float* out, int n, cudaStream_t stream);
 int threshold_median_launch(const float* prob, int B, int64_t T, float thr, int kernel, void* out, int elem,
                             int32_t* near_count, float near_tol, cudaStream_t stream);

@@ -166,18 +166,23 @@ int classifier_launch(const float* z, int64_t rows, const float* wc, const float
 
 // fp16 gate-major copy of W_hh
 // W_hh and the summed biases carry the gate exponent scaling (common.cuh lstm_gate_scale)
-__global__ void pack_whh_kernel(const float* __restrict__ w, __half* __restrict__ out, int n) {
+__global__ void pack_whh_kernel(const float* __restrict__ w, __half* __restrict__ out, __half* __restrict__ out_lo, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2half_rn(w[i] * lstm_gate_scale(i / kHidden));
+    if (i < n) {
+        __half hi, lo;
+        split_f16(w[i] * lstm_gate_scale(i / kHidden), hi, lo);
+        out[i] = hi;
+        if (out_lo) out_lo[i] = lo;                      // second plane: the fused layer (lstm_fused.cu) forms W' from it
+    }
 }
 __global__ void add_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (a[i] + b[i]) * lstm_gate_scale(i);
 }
 
-int pack_whh(const float* w, __half* out, cudaStream_t stream) {
+int pack_whh(const float* w, __half* out, cudaStream_t stream, __half* out_lo) {
     int n = kGates * kHidden;
-    pack_whh_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, out, n);
+    pack_whh_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, out, out_lo, n);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }

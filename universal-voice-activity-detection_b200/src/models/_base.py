@@ -27,16 +27,52 @@ except Exception:  # noqa: BLE001
 
 
 class PackedWeights:
-    """Lazily (re)built kernel-layout copy of a module's fp32 parameters."""
+    """Lazily (re)built kernel-layout copy of a module's fp32 parameters.
+
+    The copy is rebuilt when a parameter / buffer was replaced or written in place through autograd-visible ops (the key is
+    ``(device, data_ptr, _version)`` per tensor), after ``load_state_dict`` and after ``.to()`` / ``.cuda()`` / ``.half()``
+    (hooks in the owning module call :meth:`invalidate`).  Writes that bypass the version counter -- ``p.data.copy_(ema)``,
+    ``p.data.mul_()``, numpy views, shared storage -- are NOT visible to that key: call ``module.invalidate_packed()`` after
+    them, or set ``module.repack_always = True`` to rebuild the copy on every forward (about 30 tiny launches), which is
+    what the reference's "read the live weights on every forward" amounts to.
+    """
 
     def __init__(self):
         self.blob = None
         self.key = None
 
-    def get(self, module: nn.Module, device, build):
+    def invalidate(self):
+        self.blob = None
+        self.key = None
+
+    def get(self, module: nn.Module, device, build, always: bool = False):
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters()) + \
             tuple((b.data_ptr(), b._version) for b in module.buffers())
-        if self.blob is None or key != self.key:
+        if always or self.blob is None or key != self.key:
             self.blob = build()
             self.key = key
         return self.blob
+
+
+class PackedOwner:
+    """Mixin for modules that own PackedWeights: invalidation hooks + the explicit knobs documented above."""
+
+    repack_always = False
+
+    def _packed_caches(self):
+        return [v for v in self.__dict__.values() if isinstance(v, PackedWeights)]
+
+    def invalidate_packed(self):
+        for c in self._packed_caches():
+            c.invalidate()
+        for m in self.children():
+            if isinstance(m, PackedOwner):
+                m.invalidate_packed()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
