@@ -72,6 +72,13 @@ B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);
 B200VAD_API int b200vad_set_lstm_fused(int on);
 /* clusters of 4 CTAs of the fused LSTM kernel that are co-resident on the current device (cudaOccupancyMaxActiveClusters) */
 B200VAD_API int b200vad_lstm_fused_clusters(void);
+/* timing probes of the fused kernel for tools/fused_ablate.py (RESULTS ARE WRONG while flags != 0): 1 no h exchange, 2 no
+ * layer-output store, 4 no cell arithmetic, 8 no recurrent MMAs, 16 no input-projection MMAs; lag >= 0 sets how many part
+ * slots the input MMAs of a part trail its recurrent MMAs (default 3).  flags = 0 restores the product path. */
+B200VAD_API int b200vad_set_lstm_fused_debug(int flags, int lag);
+/* with flag 32 set, the last fused launch leaves per (CTA, warp, wait site) cycle totals / counts of its mbarrier waits in a
+ * device table; this copies the first n int64 values [cta 148][warp 18][site 8][cycles, count] to host (synchronises) */
+B200VAD_API int b200vad_lstm_fused_read_debug(long long* host, int n);
 /* Split-precision linear layer on the tcgen05 GEMM: c[M,N] = a[M,K] . w[N,K]^T + bias, fp32 in / out, operands
  * split into fp16 (hi, lo) planes in `ws` (K % 8 == 0, N % 128 == 0; weights must fit in shared memory). */
 B200VAD_API int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo,

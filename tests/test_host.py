@@ -154,6 +154,51 @@ def _gather_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gatherer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import b200vad
+    g = b200vad.SegmentGatherer(device="cpu")
+    outs = []
+    for step in range(3):
+        lo, hi = b200vad.shard_range(10, rank, world)
+        n = (hi - lo) * (rank + 1) if step != 1 else 0       # an empty batch on every rank in the middle
+        seg = torch.full((40, 3), -7, dtype=torch.int32)      # padded to a fixed capacity, garbage past the valid rows
+        for i in range(n):
+            seg[i] = torch.tensor([i % (hi - lo), 100 * step + i, 100 * step + i + 5], dtype=torch.int32)
+        seg_off = torch.tensor([0, n], dtype=torch.int64)
+        g.push(seg, seg_off, row_base=lo)
+    outs = [o.tolist() for o in g.drain()]
+    q.put((rank, outs))
+    dist.destroy_process_group()
+
+
+def test_segment_gatherer_world2_gloo():
+    """The side-stream gatherer of bench.py / corpus runs over gloo: fixed-capacity inputs, deferred completion,
+    identical results on both ranks, in push order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1] and len(res[0]) == 3
+    for step, out in enumerate(res[0]):
+        if step == 1:
+            assert out == []
+            continue
+        want = [[i % 5, 100 * step + i, 100 * step + i + 5] for i in range(5)] + \
+               [[5 + i % 5, 100 * step + i, 100 * step + i + 5] for i in range(10)]
+        assert out == want, (step, out)
+
+
 def test_gather_segments_world2_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

@@ -29,6 +29,8 @@ PROTOTYPES = {
     "b200vad_set_lstm_tile": (c_int, [c_int]),
     "b200vad_set_lstm_fused": (c_int, [c_int]),
     "b200vad_lstm_fused_clusters": (c_int, []),
+    "b200vad_set_lstm_fused_debug": (c_int, [c_int, c_int]),
+    "b200vad_lstm_fused_read_debug": (c_int, [c_void_p, c_int]),
     "b200vad_set_projection_terms": (c_int, [c_int]),
     "b200vad_set_projection_kernel": (c_int, [c_int]),
     "b200vad_set_head_fused": (c_int, [c_int]),

@@ -217,9 +217,10 @@ def _(dec, offsets=None, min_run=2):
 
 
 # ------------------------------------------------------------------ whole path
-@torch.library.custom_op("b200vad::vad_pipeline", mutates_args=(), device_types="cuda")
-def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.Tensor, num_layers: int, thr: float,
-                 kernel: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+def _pipeline_launch(wav, lens, packed, num_layers, thr, kernel):
+    """Enqueues the whole path on the current stream; returns device buffers only (nothing synchronises):
+    prob (B, T) f32, dec (B, T) u8, seg (cap, 3) i32 of which the first seg_off[B] rows are valid, counts (B,) i32,
+    seg_off (B + 1,) i64."""
     wav = _prep_rows(wav, "wav")
     if wav.dim() != 2:
         raise _lib.B200VadError("wav must be (B, N)")
@@ -230,14 +231,14 @@ def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.
     prob = torch.empty((B, T), dtype=torch.float32, device=dev)
     dec = torch.empty((B, T), dtype=torch.uint8, device=dev)
     counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    seg_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
     if B == 0 or T == 0:
-        return prob, dec, torch.empty((0, 3), dtype=torch.int32, device=dev), counts
-    if B > 65535:
-        raise _lib.B200VadError("vad_pipeline handles at most 65535 rows per call; shard the batch")
+        return prob, dec, torch.empty((0, 3), dtype=torch.int32, device=dev), counts, seg_off
+    if B > _MAX_PIPELINE_ROWS:
+        raise _lib.B200VadError(f"one pipeline launch handles at most {_MAX_PIPELINE_ROWS} rows (vad_pipeline splits larger batches)")
     per_row = (T + 2) // 3
     cap = B * per_row
     seg = torch.empty((cap, 3), dtype=torch.int32, device=dev)
-    seg_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _ensure(dev)
         lens_ptr = None
@@ -250,11 +251,53 @@ def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.
         ws = _ws(min(need, max(_MAX_WS_BYTES, minimum)), dev)
         fn = L.b200vad_pipeline_fbank_i16 if wav.dtype == torch.int16 else L.b200vad_pipeline_fbank_f32
         _lib.check(fn(packed.data_ptr(), num_layers, wav.data_ptr(), lens_ptr, B, N, wav.stride(0),
-                                                float(thr), int(kernel), prob.data_ptr(), dec.data_ptr(), counts.data_ptr(),
-                                                seg_off.data_ptr(), seg.data_ptr(), cap, ws.data_ptr(), ws.numel(),
-                                                _stream_ptr(dev)), "b200vad_pipeline_fbank_f32")
-    total = int(seg_off[B].item())
-    return prob, dec, seg[:total].clone(), counts
+                      float(thr), int(kernel), prob.data_ptr(), dec.data_ptr(), counts.data_ptr(),
+                      seg_off.data_ptr(), seg.data_ptr(), cap, ws.data_ptr(), ws.numel(),
+                      _stream_ptr(dev)), "b200vad_pipeline_fbank_f32")
+    return prob, dec, seg, counts, seg_off
+
+
+_MAX_PIPELINE_ROWS = 65535        # grid limit of the per-row kernels behind one C call
+
+
+@torch.library.custom_op("b200vad::vad_pipeline_padded", mutates_args=(), device_types="cuda")
+def vad_pipeline_padded(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.Tensor, num_layers: int, thr: float,
+                        kernel: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The whole path without any host synchronisation: the segment list comes back at its fixed capacity
+    (B * ceil(T / 3) rows) together with the per-row offsets; rows [0, seg_off[B]) are valid.  For pipelines that keep the
+    stream full (bench.py, b200vad.SegmentGatherer)."""
+    return _pipeline_launch(wav, lens, packed, num_layers, thr, kernel)
+
+
+@vad_pipeline_padded.register_fake
+def _(wav, lens, packed, num_layers, thr, kernel):
+    B, N = wav.shape
+    T = (N + 80) // 160
+    return (wav.new_empty((B, T), dtype=torch.float32), wav.new_empty((B, T), dtype=torch.uint8),
+            wav.new_empty((B * ((T + 2) // 3), 3), dtype=torch.int32), wav.new_empty((B,), dtype=torch.int32),
+            wav.new_empty((B + 1,), dtype=torch.int64))
+
+
+@torch.library.custom_op("b200vad::vad_pipeline", mutates_args=(), device_types="cuda")
+def vad_pipeline(wav: torch.Tensor, lens: Optional[torch.Tensor], packed: torch.Tensor, num_layers: int, thr: float,
+                 kernel: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """prob, dec, seg (S, 3), counts.  The exact-size segment list needs S on the host: ONE blocking read of the total per
+    call, after everything is enqueued (use vad_pipeline_padded to avoid it).  Batches of more than 65 535 rows are split."""
+    B = wav.shape[0]
+    if B <= _MAX_PIPELINE_ROWS:
+        prob, dec, seg, counts, seg_off = _pipeline_launch(wav, lens, packed, num_layers, thr, kernel)
+        total = int(seg_off[B].item()) if B > 0 else 0
+        return prob, dec, seg[:total].clone(), counts
+    outs = []
+    for b0 in range(0, B, _MAX_PIPELINE_ROWS):
+        sl = slice(b0, min(B, b0 + _MAX_PIPELINE_ROWS))
+        outs.append((b0,) + _pipeline_launch(wav[sl], None if lens is None else lens[sl], packed, num_layers, thr, kernel))
+    segs = []
+    for b0, _, _, seg, _, seg_off in outs:
+        s = seg[: int(seg_off[-1].item())].clone()
+        s[:, 0] += b0
+        segs.append(s)
+    return (torch.cat([o[1] for o in outs]), torch.cat([o[2] for o in outs]), torch.cat(segs), torch.cat([o[4] for o in outs]))
 
 
 @vad_pipeline.register_fake

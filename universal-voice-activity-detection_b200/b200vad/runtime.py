@@ -191,3 +191,79 @@ def gather_segments(seg: torch.Tensor, row_base: int = 0, group=None) -> torch.T
     bufs = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(bufs, padded, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+class SegmentGatherer:
+    """Segment-list gather that stays OFF the compute stream ("end of corpus or every k batches, on a side stream").
+
+    ``push(seg, seg_off, row_base)`` takes the padded output of ``torch.ops.b200vad.vad_pipeline_padded`` (nothing synchronises:
+    it records an event on the current stream and returns).  The previous push is completed at that moment, while the GPU is
+    already running the batch just enqueued: on a side stream the valid rows are compacted, the counts of all ranks exchanged
+    with one ``all_gather_into_tensor`` and the triples with one fixed-shape ``all_gather_into_tensor`` padded to the largest
+    count.  The only host reads are the 8-byte total of a batch that has already finished and the world-size counts, both on
+    the side stream.  ``drain()`` completes what is pending and returns the list of gathered (S, 3) int32 tensors (global
+    utterance ids in column 0), one per push, identical on every rank.  Single-process use (no process group) skips the
+    collectives.  NCCL on CUDA tensors; the CPU test runs the same code over gloo with ``device="cpu"``."""
+
+    def __init__(self, device=None, group=None):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.cuda = self.device.type == "cuda"
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.pending = None
+        self.results = []
+
+    def push(self, seg: torch.Tensor, seg_off: torch.Tensor, row_base: int = 0):
+        ev = None
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        prev, self.pending = self.pending, (seg, seg_off, int(row_base), ev)
+        if prev is not None:
+            self._complete(prev)
+
+    def _complete(self, item):
+        seg, seg_off, row_base, ev = item
+        ctx = torch.cuda.stream(self.side) if self.cuda else _NullCtx()
+        with ctx:
+            if self.cuda:
+                self.side.wait_event(ev)
+            n = int(seg_off[-1].item())                       # this batch has finished; the compute stream is not touched
+            local = seg[:n].clone()
+            local[:, 0] += row_base
+            if self.world == 1:
+                self.results.append(local)
+                return
+            cnt = torch.tensor([n], dtype=torch.int64, device=seg.device)
+            counts = torch.empty(self.world, dtype=torch.int64, device=seg.device)
+            self.dist.all_gather_into_tensor(counts, cnt, group=self.group)
+            counts = counts.tolist()
+            m = max(max(counts), 1)
+            padded = torch.zeros((m, 3), dtype=torch.int32, device=seg.device)
+            padded[:n] = local
+            out = torch.empty((self.world * m, 3), dtype=torch.int32, device=seg.device)
+            self.dist.all_gather_into_tensor(out, padded, group=self.group)
+            self.results.append(torch.cat([out[r * m: r * m + c] for r, c in enumerate(counts)], dim=0))
+            if self.cuda:
+                seg.record_stream(self.side)
+                seg_off.record_stream(self.side)
+
+    def drain(self):
+        if self.pending is not None:
+            prev, self.pending = self.pending, None
+            self._complete(prev)
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        res, self.results = self.results, []
+        return res
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

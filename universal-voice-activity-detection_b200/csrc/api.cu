@@ -421,6 +421,14 @@ int b200vad_set_lstm_fused(int on) {
     return B200VAD_OK;
 }
 int b200vad_lstm_fused_clusters(void) { return lstm_fused_clusters(); }
+int b200vad_set_lstm_fused_debug(int flags, int lag) {
+    lstm_fused_set_debug(flags, lag);
+    return B200VAD_OK;
+}
+int b200vad_lstm_fused_read_debug(long long* host, int n) {
+    B200VAD_CHECK_ARG(host && n != 0, "null buffer");
+    return lstm_fused_read_debug(host, n);
+}
 int b200vad_set_lstm_tile(int sequences_per_cta) {
     int rc = lstm_tc_set_tile(sequences_per_cta);
     if (rc) set_error("b200vad_set_lstm_tile: must be 0 (automatic), 16 or 64");

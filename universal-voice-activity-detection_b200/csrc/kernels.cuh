@@ -62,6 +62,8 @@ int pack_whh(const float* w, __half* out, cudaStream_t stream, __half* out_lo = 
 // fused projection + recurrence on 4-CTA clusters (lstm_fused.cu); D <= 256
 int lstm_fused_supported(int D);
 int lstm_fused_clusters();
+void lstm_fused_set_debug(int flags, int lag);
+int lstm_fused_read_debug(long long* host, int n);
 int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int D, const __half* wih_hi,
                       const __half* wih_lo, int ldw, const __half* whh_hi, const __half* whh_lo, const float* bias, int terms,
                       __half* y_a, __half* y_b, int y_scaled, cudaStream_t st);

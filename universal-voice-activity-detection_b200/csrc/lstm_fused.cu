@@ -45,18 +45,21 @@ using namespace tc;
 
 constexpr int FC = 4;                       // CTAs per cluster
 constexpr int FU = kHidden / FC;            // hidden units per CTA (32)
-constexpr int FPN = 16;                     // sequences per part (MMA N)
-constexpr int FMAXP = 8;                    // parts per work item (128 sequences per cluster)
-constexpr int FWG = 4;                      // pointwise warpgroups; warpgroup w owns parts w and w + 4
-constexpr int F_THREADS = (FWG * 4 + 2) * 32;   // 16 pointwise warps + TMA producer warp + MMA warp = 576
-constexpr int F_BOX = FPN * 128;            // one x box / one h k-block: 16 rows x 128 bytes = 2 KB
-constexpr int F_HTILE = FC * F_BOX;         // h operand tile of a part: 4 k-blocks = 8 KB
-constexpr int F_EXCH = 4 * FPN * FU * 4;    // gate transposition buffer of a warpgroup: [gate][sequence][unit] fp32 = 8 KB
-constexpr int F_ACC_COL = 0;                // TMEM columns [0, 128): accumulators, part p at 16 p
+constexpr int FPN = 32;                     // sequences per part (MMA N); one pointwise warpgroup per part
+constexpr int FMAXP = 4;                    // parts per work item (128 sequences per cluster)
+constexpr int F_PW_WARPS = 4 * FMAXP;       // pointwise warps: warp w owns TMEM lane quarter w & 3 (8 units x 4 gates) of part w >> 2
+constexpr int F_W_PROD = F_PW_WARPS;        // TMA producer warp (16)
+constexpr int F_W_MMA = F_W_PROD + 1;       // recurrent-product issuer (+ TMEM owner)
+constexpr int F_W_MMAX = F_W_PROD + 2;      // input-product issuer
+constexpr int F_THREADS = (F_W_PROD + 3) * 32;                          // 19 warps = 608 threads
+constexpr int F_BOX = FPN * 128;            // one x box / one h k-block: 32 rows x 128 bytes = 4 KB
+constexpr int F_HTILE = FC * F_BOX;         // h operand tile of a part: 4 k-blocks = 16 KB
+constexpr int F_SCRATCH = 32 * 16 * 4;      // per pointwise warp: gate transposition scratch [lane 32][16 columns] fp32 = 2 KB (then the h chunk staging)
+constexpr int F_ACC_COL = 0;                // TMEM columns [0, 128): accumulators, part p at 32 p
 constexpr int F_WHH_COL = FMAXP * FPN;      // [128, 256): W_hh, k-step j at 128 + 8 j
-constexpr int F_WIH_COL = F_WHH_COL + 128;  // [256, 256 + Dp): W_ih plane a then plane b
+constexpr int F_WIH_COL = F_WHH_COL + 128;  // [256, 256 + 16 nk): W_ih plane a then plane b
 constexpr int F_MAX_STAGES = 16;
-constexpr int F_SMEM_FIXED = FMAXP * F_HTILE + FWG * F_EXCH;   // 96 KB
+constexpr int F_SMEM_FIXED = FMAXP * F_HTILE + F_PW_WARPS * F_SCRATCH;   // 96 KB
 constexpr int F_SMEM_MAX = 232448;          // 227 KB per CTA
 
 struct FusedParams {
@@ -68,7 +71,7 @@ struct FusedParams {
     __half* y_a;             // layer output planes [B][T][256]
     __half* y_b;
     int B, T;
-    int nk;                  // k-steps of 16 of the input projection (D rounded up to 16) / 16
+    int nk;                  // k-steps of 16 of the input projection: ceil(D / 16)
     int kblocks;             // 64-wide k blocks per x plane (TMA boxes per plane)
     int ldw;                 // row pitch of wih planes (elements)
     int terms;               // 2: planes are the scaled (x1, x2) split, plane b of W_ih is W';  3: (hi, lo) planes, plane b is W_lo
@@ -76,12 +79,22 @@ struct FusedParams {
     int items_per_dir;       // work items per direction; parts are spread evenly over them
     int stages;              // x ring depth
     int lag;                 // x-MMAs of a part are issued `lag` part slots after its h-MMAs
-    int flags;               // debug (B200VAD_FUSED_DEBUG): 1 = skip the h exchange (timing probe, wrong results)
+    int prefetch_steps;      // L2 prefetch distance of the x tiles, in time steps (0 = off)
+    int flags;               // timing probes (wrong results): 1 no h exchange, 2 no y store, 4 no cell math, 8 no recurrent MMAs, 16 no input MMAs, 32 wait-time table
 };
 
-#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag(bar, parity, tag)
-__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag) {
-    if (mbar_try_wait(bar, parity)) return;
+// wait-time probe (flags & 32, tools/fused_ablate.py): per (CTA, warp, wait tag) cycles spent in non-immediate waits and their count
+constexpr int F_DBG_TAGS = 8, F_DBG_WARPS = 19, F_DBG_MAX_CTAS = 148;
+__device__ long long g_fused_dbg[F_DBG_MAX_CTAS * F_DBG_WARPS * F_DBG_TAGS * 2];
+
+// timeline probe (flags & 64): clock64 stamps of one part (part 0 of CTA 0's first item) over F_TRACE_STEPS steps
+constexpr int F_TRACE_S0 = 100, F_TRACE_STEPS = 8;
+__device__ long long g_fused_trace[F_TRACE_STEPS * 16];
+
+#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag(bar, parity, tag, wacc)
+__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc) {
+    if (!wacc && mbar_try_wait(bar, parity)) return;
+    if (wacc && mbar_test_wait(bar, parity)) return;          // probe mode: count every wait that is not already satisfied
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {   // ~2 s
@@ -90,16 +103,33 @@ __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int
             __trap();
         }
     }
+    if (wacc) { wacc[2 * tag] += clock64() - t0; wacc[2 * tag + 1] += 1; }
 }
 
+// The MMA-issuing thread is the serial resource of the kernel (one tcgen05.mma of N = 32 occupies the tensor pipe for 16
+// cycles): descriptors are formed by ONE add on the low word of a per-slot base (the swizzled K-major tile layout makes the
+// start-address field additive), the loops are fully unrolled (NK, TERMS are template parameters), and no divisions.
+constexpr uint32_t F_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t fdesc(uint32_t lo) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(F_DESC_HI));
+    return d;
+}
+__device__ __forceinline__ uint32_t fdesc_lo(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
+
+// NK > 0: k-steps of the input projection known at compile time (5: 80 mel bins, 4: 60 SincNet channels, 16: 256 LSTM outputs);
+// NK = 0: run-time p.nk / p.terms (any D <= 256; slower issue loop)
+template <int NK, int TERMS>
 __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(F_THREADS, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, FusedParams p) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* const smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    const uint32_t h_off = 0;                                  // [part 8][k-block 4][16 rows][128 B]
-    const uint32_t e_off = FMAXP * F_HTILE;                    // [warpgroup 4][gate 4][sequence 16][unit 32] fp32
-    const uint32_t x_off = e_off + FWG * F_EXCH;               // [stage][plane 2][k-block][16 rows][128 B]
+    const uint32_t h_off = 0;                                  // [part 4][k-block 4][32 rows][128 B]
+    const uint32_t c_off = FMAXP * F_HTILE;                    // scratch [pointwise warp 16][2 KB]
+    const uint32_t x_off = c_off + F_PW_WARPS * F_SCRATCH;     // [stage][plane 2][k-block][32 rows][128 B]
+    const int nk = NK > 0 ? NK : p.nk;
+    const int terms = NK > 0 ? TERMS : p.terms;
     const uint32_t stage_bytes = 2u * p.kblocks * F_BOX;
     const uint32_t bar_base = smem_base + x_off + p.stages * stage_bytes;
     auto bar_x_full = [&](int s) { return bar_base + 8 * s; };
@@ -109,6 +139,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     auto bar_h_ready = [&](int q) { return bar_base + 384 + 8 * q; };
     auto bar_h_free = [&](int q) { return bar_base + 448 + 8 * q; };
     const uint32_t tmem_slot = bar_base + 512;
+    auto bar_x_done = [&](int q) { return bar_base + 560 + 8 * q; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -126,18 +157,28 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             mbar_init(bar_acc_free(q), 4);
             mbar_init(bar_h_ready(q), 1);
             mbar_init(bar_h_free(q), FC);
+            mbar_init(bar_x_done(q), 1);
         }
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc<512>(tmem_slot);
+    if (warp == F_W_MMA) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     cluster_sync_all();                                       // every CTA's barriers exist before any remote arrive / copy
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    // wait-time probe: lane 0 of every warp accumulates straight into its row of the global table (probe mode only)
+    long long* const wacc = ((p.flags & 32) && lane == 0 && blockIdx.x < F_DBG_MAX_CTAS)
+                                ? &g_fused_dbg[((size_t)blockIdx.x * F_DBG_WARPS + warp) * (2 * F_DBG_TAGS)] : nullptr;
+    if (wacc) {
+        for (int i = 0; i < 2 * F_DBG_TAGS; ++i) wacc[i] = 0;
+        wacc[0] = -clock64();
+    }
+    long long* const trace = ((p.flags & 64) && blockIdx.x == 0 && lane == 0) ? g_fused_trace : nullptr;
     // persistent role state (phases carry over from item to item)
-    uint32_t xcount = 0;                                      // producer / MMA thread: x ring uses so far
+    int xst = 0;                                              // producer / MMA thread: next x ring stage ...
+    uint32_t xph = 0;                                         // ... and its phase
     uint32_t ph_a = 0, ph_b = 0;                              // per-part phase bits (meaning depends on the role)
     int loaded_dir = -1;
 
@@ -147,13 +188,15 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int part0 = ii * base_parts + min(ii, rem_parts);
         const int seq0 = part0 * FPN;
         if (nparts == 0) continue;                            // (uniform over the cluster)
-        const int total = T * nparts;
 
         // ---------------- weights of this direction -> tensor memory (pointwise warps; only when the direction changes)
         if (warp < 16 && loaded_dir != dir) {
+            constexpr int FWG = 4;
             const int wg = warp >> 2, g = warp & 3;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16);
-            const int grow = dir * kGates + g * kHidden + (int)rank * FU + lane;          // packed weight row of this TMEM lane
+            // TMEM lane 32 g + l holds gate (l & 3) of unit 8 g + (l >> 2) of this CTA: the four gates of a cell sit in four
+            // adjacent lanes of ONE warp, so the pointwise warps transpose gates <-> sequences without leaving the warp
+            const int grow = dir * kGates + (lane & 3) * kHidden + (int)rank * FU + 8 * g + (lane >> 2);   // packed weight row of this TMEM lane
             // W_hh: k-step j holds plane (j >> 1) & 1 of units 32 (j >> 2) + 16 (j & 1) .. + 15
             for (int j = wg; j < 16; j += FWG) {
                 const int u0 = 32 * (j >> 2) + 16 * (j & 1), plane = (j >> 1) & 1;
@@ -179,8 +222,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 tmem_st8(lane_addr + F_WHH_COL + 8 * j, r);
             }
             // W_ih: plane a = W_hi, plane b = W_lo (terms 3) or W' (terms 2); k-step j of plane pl at F_WIH_COL + pl * 8 nk + 8 j
-            for (int j = wg; j < 2 * p.nk; j += FWG) {
-                const int pl = j >= p.nk, kj = pl ? j - p.nk : j;
+            for (int j = wg; j < 2 * nk; j += FWG) {
+                const int pl = j >= nk, kj = pl ? j - nk : j;
                 const uint4* hp = reinterpret_cast<const uint4*>(p.wih_hi + (size_t)grow * p.ldw + 16 * kj);
                 const uint4* lp = reinterpret_cast<const uint4*>(p.wih_lo + (size_t)grow * p.ldw + 16 * kj);
                 uint32_t r[8];
@@ -192,7 +235,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     for (int e = 0; e < 4; ++e) {
                         if (!pl) {
                             r[4 * i + e] = hw[e];
-                        } else if (p.terms == 3) {
+                        } else if (terms == 3) {
                             r[4 * i + e] = lw[e];
                         } else {
                             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
@@ -211,81 +254,97 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         __syncthreads();
         tc_fence_after();
 
-        if (warp == 16) {
+        if (warp == F_W_PROD) {
             // ===================== TMA producer: x tiles of (step, part) in issue order, multicast to the cluster =====================
             if (elect_one()) {
                 const int nboxes = 2 * p.kblocks;
-                for (int k = 0; k < total; ++k) {
-                    const int s = k / nparts, q = k - s * nparts;
+                // The x planes stream from HBM (a layer's input does not fit the L2): the ring is only 3-6 stages deep, so the
+                // tiles are pulled into the L2 `pf` steps ahead (cp.async.bulk.prefetch.tensor, no shared memory needed) and
+                // the ring's own loads hit the L2.
+                const int pf = p.prefetch_steps;
+                for (int s = 0; s < min(pf, T); ++s) {
                     const int t = dir == 0 ? s : T - 1 - s;
-                    const int st = (int)(xcount % (uint32_t)p.stages);
-                    const uint32_t ph = (xcount / (uint32_t)p.stages) & 1u;
-                    FUSED_WAIT(bar_x_empty(st), ph ^ 1u, 1);                  // all 4 CTAs' MMAs are done with this stage
-                    mbar_expect_tx(bar_x_full(st), stage_bytes);
-                    const uint32_t dst = smem_base + x_off + st * stage_bytes;
-                    for (int bi = (int)rank; bi < nboxes; bi += FC) {
-                        const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                        tma_load_3d_mc(dst + bi * F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + q * FPN, bar_x_full(st), (uint16_t)0xF);
+                    for (int q = 0; q < nparts; ++q)
+                        for (int bi = (int)rank; bi < nboxes; bi += FC) {
+                            const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
+                            tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, t, seq0 + q * FPN);
+                        }
+                }
+                for (int s = 0; s < T; ++s) {
+                    const int t = dir == 0 ? s : T - 1 - s;
+                    const int sp = s + pf, tp = dir == 0 ? sp : T - 1 - sp;
+                    for (int q = 0; q < nparts; ++q) {
+                        if (pf > 0 && sp < T)
+                            for (int bi = (int)rank; bi < nboxes; bi += FC) {
+                                const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
+                                tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, tp, seq0 + q * FPN);
+                            }
+                        FUSED_WAIT(bar_x_empty(xst), xph ^ 1u, 1);                // all 4 CTAs' MMAs are done with this stage
+                        mbar_expect_tx(bar_x_full(xst), stage_bytes);
+                        const uint32_t dst = smem_base + x_off + xst * stage_bytes;
+                        for (int bi = (int)rank; bi < nboxes; bi += FC) {
+                            const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
+                            tma_load_3d_mc(dst + bi * F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + q * FPN, bar_x_full(xst), (uint16_t)0xF);
+                        }
+                        if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                     }
-                    ++xcount;
                 }
             }
-        } else if (warp == 17) {
-            // ===================== MMA issuer =====================
+        } else if (warp == F_W_MMAX) {
+            // ===================== input-product issuer: acc(s, q) = W_ih . x_s, one step ahead of the recurrence =====================
+            // Two threads feed the tensor pipe: tcgen05.mma issue blocks at the pipe's pace and tcgen05.commit drains it, so a
+            // single issuer leaves the pipe idle during every barrier wait; with the input products on their own thread the
+            // recurrent-product thread is free the moment a part's h tile is complete (the critical path of the cluster).
             if (elect_one()) {
                 constexpr uint32_t idesc = idesc_f16(128, FPN);
-                const int lag = min(p.lag, nparts - 1);
-                // ph_a: h_ready phase bits, ph_b: acc_free phase bits
-                auto issue_x = [&](int k) {
-                    const int s = k / nparts, q = k - s * nparts;
-                    if (s > 0) {                                                   // the pointwise warps have read acc(s - 1, q)
-                        FUSED_WAIT(bar_acc_free(q), (ph_b >> q) & 1u, 2);
-                        ph_b ^= 1u << q;
-                    }
-                    const int st = (int)(xcount % (uint32_t)p.stages);
-                    const uint32_t ph = (xcount / (uint32_t)p.stages) & 1u;
-                    FUSED_WAIT(bar_x_full(st), ph, 3);
-                    tc_fence_after();
-                    const uint32_t xa = smem_base + x_off + st * stage_bytes, xb = xa + p.kblocks * F_BOX;
-                    const uint32_t d = tmem_base + F_ACC_COL + q * FPN;
-                    const uint32_t wa0 = tmem_base + F_WIH_COL, wb0 = wa0 + 8 * p.nk;
-                    for (int j = 0; j < p.nk; ++j) {
-                        const uint32_t off = (j >> 2) * F_BOX + (j & 3) * 32;
-                        const uint64_t da = smem_desc_sw128(xa + off), db = smem_desc_sw128(xb + off);
-                        if (p.terms == 3) {
-                            mma_f16_ts(d, wa0 + 8 * j, db, idesc, j != 0);         // x_lo . W_hi (small terms first)
-                            mma_f16_ts(d, wb0 + 8 * j, da, idesc, 1);              // x_hi . W_lo
-                        } else {
-                            mma_f16_ts(d, wb0 + 8 * j, db, idesc, j != 0);         // x2 . W'
+                const uint32_t wa0 = tmem_base + F_WIH_COL, wb0 = wa0 + 8 * nk;
+                const uint32_t plane_lo = (uint32_t)(p.kblocks * F_BOX) >> 4;
+                // ph_b: acc_free phase bits
+                for (int s = 0; s < T; ++s) {
+                    for (int q = 0; q < nparts; ++q) {
+                        const bool trx = trace && q == 0 && item == cluster_id && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                        if (trx) trace[(s - F_TRACE_S0) * 16 + 9] = clock64();
+                        if (s > 0) {                                               // the pointwise warps have read acc(s - 1, q)
+                            FUSED_WAIT(bar_acc_free(q), (ph_b >> q) & 1u, 2);
+                            ph_b ^= 1u << q;
                         }
-                        mma_f16_ts(d, wa0 + 8 * j, da, idesc, 1);                  // x1 . W_hi
-                    }
-                    mma_commit_mc(bar_x_empty(st), (uint16_t)0xF);
-                    ++xcount;
-                    if (s == 0) {                                                  // h_{-1} = 0: no recurrent product at the first step
-                        mma_commit(bar_acc_ready(q));
-                        if (T > 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);
-                    }
-                };
-                for (int k = 0; k < nparts; ++k) issue_x(k);
-                for (int j = 0; j < total; ++j) {
-                    const int s = j / nparts, q = j - s * nparts;
-                    if (s > 0) {
-                        FUSED_WAIT(bar_h_ready(q), (ph_a >> q) & 1u, 4);           // h_{s-1} of this part: all four slices landed
-                        ph_a ^= 1u << q;
+                        if (trx) trace[(s - F_TRACE_S0) * 16 + 11] = clock64();
+                        FUSED_WAIT(bar_x_full(xst), xph, 3);
                         tc_fence_after();
-                        const uint32_t hb = smem_base + h_off + q * F_HTILE;
+                        if (trx) trace[(s - F_TRACE_S0) * 16 + 13] = clock64();
+                        const uint32_t xa = fdesc_lo(smem_base + x_off + xst * stage_bytes), xb = xa + plane_lo;
                         const uint32_t d = tmem_base + F_ACC_COL + q * FPN;
+                        if (NK > 0) {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const uint64_t dh = smem_desc_sw128(hb + (jj >> 2) * F_BOX + (jj & 3) * 32);
-                            mma_f16_ts(d, tmem_base + F_WHH_COL + 8 * jj, dh, idesc, 1);
+                            for (int j = 0; j < (NK > 0 ? NK : 1); ++j) {
+                                if ((p.flags & 16) && j > 0) break;
+                                const uint32_t off = (uint32_t)((j >> 2) * (F_BOX >> 4) + (j & 3) * 2);
+                                if (TERMS == 3) {
+                                    mma_f16_ts(d, wa0 + 8 * j, fdesc(xb + off), idesc, j != 0);   // x_lo . W_hi (small terms first)
+                                    mma_f16_ts(d, wb0 + 8 * j, fdesc(xa + off), idesc, 1);        // x_hi . W_lo
+                                } else {
+                                    mma_f16_ts(d, wb0 + 8 * j, fdesc(xb + off), idesc, j != 0);   // x2 . W'
+                                }
+                                mma_f16_ts(d, wa0 + 8 * j, fdesc(xa + off), idesc, 1);            // x1 . W_hi
+                            }
+                        } else {
+                            for (int j = 0; j < ((p.flags & 16) ? 1 : nk); ++j) {
+                                const uint32_t off = (uint32_t)((j >> 2) * (F_BOX >> 4) + (j & 3) * 2);
+                                if (terms == 3) {
+                                    mma_f16_ts(d, wa0 + 8 * j, fdesc(xb + off), idesc, j != 0);
+                                    mma_f16_ts(d, wb0 + 8 * j, fdesc(xa + off), idesc, 1);
+                                } else {
+                                    mma_f16_ts(d, wb0 + 8 * j, fdesc(xb + off), idesc, j != 0);
+                                }
+                                mma_f16_ts(d, wa0 + 8 * j, fdesc(xa + off), idesc, 1);
+                            }
                         }
-                        mma_commit(bar_acc_ready(q));
-                        if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA may now overwrite this part's h tile
+                        if (trx) trace[(s - F_TRACE_S0) * 16 + 14] = clock64();
+                        mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
+                        mma_commit(bar_x_done(q));
+                        if (++xst == p.stages) { xst = 0; xph ^= 1u; }
+                        if (trx) trace[(s - F_TRACE_S0) * 16 + 15] = clock64();
                     }
-                    const int k = j - lag + nparts;
-                    if (j >= lag && k < total) issue_x(k);
                 }
                 // the accumulators of the last step must be read before the next item overwrites them
                 for (int q = 0; q < nparts; ++q) {
@@ -293,115 +352,176 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     ph_b ^= 1u << q;
                 }
             }
-        } else {
-            // ===================== pointwise warpgroups =====================
-            const int wg = warp >> 2, g = warp & 3;                               // g: gate read from TMEM == warp index in the warpgroup
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16);
-            const float bias = __ldg(p.bias + dir * kGates + g * kHidden + (int)rank * FU + lane);
-            // after the transposition: 4 units (quad q4) of one sequence n
-            const int n = g + 4 * (lane >> 3), q4 = lane & 7;
-            float* const exw = reinterpret_cast<float*>(smem_gen + e_off + wg * F_EXCH) + g * (FPN * FU) + lane;          // + 32 * sequence
-            const float4* const exr = reinterpret_cast<const float4*>(smem_gen + e_off + wg * F_EXCH) + n * (FU / 4) + q4;   // + gate * 128
-            const bool tid0 = (threadIdx.x & 127) == 0;
+        } else if (warp == F_W_MMA) {
+            // ===================== recurrent-product issuer: acc(s, q) += W_hh . h_{s-1} =====================
+            if (elect_one()) {
+                constexpr uint32_t idesc = idesc_f16(128, FPN);
+                // ph_a: h_ready phase bits, ph_b: x_done phase bits
+                // h_ready(q) = this thread's arming arrival + the 16 KB of h_s that the 16 pointwise warps of the cluster store
+                // into this CTA's tile (st.async credits the bytes); armed before the step whose pointwise pass produces them
+                if (T > 1 && !(p.flags & 1))
+                    for (int q = 0; q < nparts; ++q) mbar_expect_tx(bar_h_ready(q), FC * F_BOX);
+                for (int s = 0; s < T; ++s) {
+                    for (int q = 0; q < nparts; ++q) {
+                        const bool trh = trace && q == 0 && item == cluster_id && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                        FUSED_WAIT(bar_x_done(q), (ph_b >> q) & 1u, 2);            // acc(s, q) holds the complete input product
+                        ph_b ^= 1u << q;
+                        if (s > 0) {
+                            FUSED_WAIT(bar_h_ready(q), (ph_a >> q) & 1u, 4);       // h_{s-1} of this part: all four slices landed
+                            ph_a ^= 1u << q;
+                            if (s < T - 1 && !(p.flags & 1)) mbar_expect_tx(bar_h_ready(q), FC * F_BOX);   // arm for h_s
+                            fence_proxy_async();                                   // st.async data -> tensor-core (async proxy) reads
+                            tc_fence_after();
+                            if (trh) trace[(s - F_TRACE_S0) * 16 + 0] = clock64();
+                            const uint32_t hb = fdesc_lo(smem_base + h_off + q * F_HTILE);
+                            const uint32_t d = tmem_base + F_ACC_COL + q * FPN;
+                            if (!(p.flags & 8)) {
+#pragma unroll
+                                for (int jj = 0; jj < 16; ++jj)
+                                    mma_f16_ts(d, tmem_base + F_WHH_COL + 8 * jj, fdesc(hb + (uint32_t)((jj >> 2) * (F_BOX >> 4) + (jj & 3) * 2)), idesc, 1);
+                            }
+                        }
+                        mma_commit(bar_acc_ready(q));                              // (s = 0: h_{-1} = 0, the input product alone)
+                        if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA may now overwrite this part's h tile
+                        if (trh) trace[(s - F_TRACE_S0) * 16 + 1] = clock64();
+                    }
+                }
+            }
+        } else if ((warp >> 2) < nparts) {
+            // ===================== pointwise warps: warp (q, g) = part q, units 8 g .. 8 g + 7 of this CTA =====================
+            // lane l reads the accumulator row of gate l & 3 of unit 8 g + (l >> 2) for the part's 32 sequences, turns it into
+            // exponentials, and the four lanes of a unit transpose (gate x sequence) through a warp-private scratch, after
+            // which lane l owns all four gates of 8 cells: unit 8 g + (l >> 2), sequences 16 hf + 4 (l & 3) + i.  No other warp
+            // is involved until the h_s slice is complete.
+            const int q = warp >> 2, g = warp & 3;
+            const int uu = lane >> 2, jj = lane & 3;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16) + F_ACC_COL + q * FPN;
+            const float bias = __ldg(p.bias + dir * kGates + jj * kHidden + (int)rank * FU + 8 * g + uu);
+            unsigned char* const scr = smem_gen + c_off + warp * F_SCRATCH;
+            // scratch address of (row, 16-byte chunk c): conflict-free for the row-wise stores and the gate-wise loads
+            auto scr_at = [&](int row, int c) -> unsigned char* {
+                return scr + (((row * 64) + ((c ^ ((row >> 1) & 3)) << 4)) ^ (((row >> 2) & 1) << 6));
+            };
             const float s1 = 1.f - kPlaneScale;
             const float L2E2 = 2.f * kLog2e;
-            float cst[2][4];
+            float cst[8];
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 8; ++b) cst[b] = 0.f;
+            // h planes of (sequence row, unit 8 g + uu): 2-byte elements of chunk g (h1) / 4 + g (h2) of the 128-byte swizzled row
+            const uint32_t hoff = (uint32_t)uu * 2;
+            uint32_t cta_delta[FC];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) cst[a][b] = 0.f;
-            // own slice of the h operand tile: row n, chunk (q4 >> 1) for h1 and 4 + (q4 >> 1) for h2, 8-byte half (q4 & 1)
-            const uint32_t hrow = (uint32_t)rank * F_BOX + n * 128 + ((q4 & 1) << 3);
-            const uint32_t hc1 = (uint32_t)(((q4 >> 1) ^ (n & 7)) << 4), hc2 = (uint32_t)(((4 + (q4 >> 1)) ^ (n & 7)) << 4);
-            // ph_a: acc_ready phase bits, ph_b: h_free phase bits
+            for (uint32_t d = 0; d < FC; ++d) cta_delta[d] = mapa_shared(smem_base, d) - smem_base;
+            // ph_a: acc_ready phase bit, ph_b: h_free phase bit
             for (int s = 0; s < T; ++s) {
                 const int t = dir == 0 ? s : T - 1 - s;
+                const bool exchange = s + 1 < T;
+                FUSED_WAIT(bar_acc_ready(q), ph_a & 1u, 6);
+                ph_a ^= 1u;
+                tc_fence_after();
+                const bool tr_on = trace && warp == 0 && item == cluster_id && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 2] = clock64();
+                float z[32];
+                tmem_ld32(lane_addr, z);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_free(q));                       // the next step's input product may overwrite the accumulator
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 3] = clock64();
 #pragma unroll
-                for (int pi = 0; pi < 2; ++pi) {
-                    const int q = wg + FWG * pi;
-                    if (q >= nparts) break;
-                    FUSED_WAIT(bar_acc_ready(q), (ph_a >> q) & 1u, 6);
-                    ph_a ^= 1u << q;
-                    tc_fence_after();
-                    float z[16];
-                    tmem_ld16(lane_addr + F_ACC_COL + q * FPN, z);
-                    tmem_ld_wait();
-                    tc_fence_before();
+                for (int j = 0; j < 32; ++j) z[j] = fast_ex2(fminf(z[j] + bias, 29.f));
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 4] = clock64();
+                float ev[4][8];                                                    // [gate][cell]: cell 4 hf + i = sequence 16 hf + 4 jj + i
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<float4*>(scr_at(lane, c)) = make_float4(z[16 * hf + 4 * c], z[16 * hf + 4 * c + 1], z[16 * hf + 4 * c + 2], z[16 * hf + 4 * c + 3]);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acc_free(q));
-                    // 2^(pre-activation) of this thread's gate row for the 16 sequences -> [gate][sequence][unit]
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) exw[j * FU] = fast_ex2(fminf(z[j] + bias, 29.f));
-                    named_bar_sync(1 + wg, 128);
-                    const float4 vi = exr[0], vf = exr[FPN * FU / 4], vg = exr[2 * FPN * FU / 4], vo = exr[3 * FPN * FU / 4];
-                    const float ei[4] = {vi.x, vi.y, vi.z, vi.w}, ef[4] = {vf.x, vf.y, vf.z, vf.w};
-                    const float eg[4] = {vg.x, vg.y, vg.z, vg.w}, eo[4] = {vo.x, vo.y, vo.z, vo.w};
-                    float hv[4];
-                    const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), k2 = pack2(L2E2, L2E2);
-#pragma unroll
-                    for (int jp = 0; jp < 2; ++jp) {
-                        const f32x2 pei = pack2(ei[2 * jp], ei[2 * jp + 1]), pef = pack2(ef[2 * jp], ef[2 * jp + 1]);
-                        const f32x2 peg = pack2(eg[2 * jp], eg[2 * jp + 1]), peo = pack2(eo[2 * jp], eo[2 * jp + 1]);
-                        // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(eg + 1)) with one reciprocal (lstm_tc.cu)
-                        const f32x2 di = add2(pei, one), df = add2(pef, one), dg = add2(peg, one);
-                        const f32x2 dig = mul2(di, dg);
-                        const f32x2 den = mul2(df, dig);
-                        const f32x2 cn = mul2(fma2(pack2(cst[pi][2 * jp], cst[pi][2 * jp + 1]), dig, mul2(add2(peg, mone), df)), rcp2(den));
-                        unpack2(cn, cst[pi][2 * jp], cst[pi][2 * jp + 1]);
-                        const f32x2 ec = ex2_clamped2(mul2(cn, k2));
-                        const f32x2 h2v = mul2(add2(ec, mone), rcp2(mul2(add2(peo, one), add2(ec, one))));
-                        unpack2(h2v, hv[2 * jp], hv[2 * jp + 1]);
+                    for (int b = 0; b < 4; ++b) {
+                        const float4 v = *reinterpret_cast<const float4*>(scr_at((lane & ~3) + b, jj));
+                        ev[b][4 * hf] = v.x; ev[b][4 * hf + 1] = v.y; ev[b][4 * hf + 2] = v.z; ev[b][4 * hf + 3] = v.w;
                     }
-                    // recurrent operand planes: always the scaled split (h1 . W_hi + h2 . W')
-                    __half a1[4], a2[4];
+                    __syncwarp();
+                }
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 5] = clock64();
+                float hv[8];
+                const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), k2 = pack2(L2E2, L2E2);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split_scaled_f16(hv[e], s1, a1[e], a2[e]);
-                    uint2 w1, w2;
-                    w1.x = (uint32_t)__half_as_ushort(a1[0]) | ((uint32_t)__half_as_ushort(a1[1]) << 16);
-                    w1.y = (uint32_t)__half_as_ushort(a1[2]) | ((uint32_t)__half_as_ushort(a1[3]) << 16);
-                    w2.x = (uint32_t)__half_as_ushort(a2[0]) | ((uint32_t)__half_as_ushort(a2[1]) << 16);
-                    w2.y = (uint32_t)__half_as_ushort(a2[2]) | ((uint32_t)__half_as_ushort(a2[3]) << 16);
-                    const bool exchange = s + 1 < T;
-                    if (exchange) {
-                        // the peers' MMAs of this step have finished reading their copy of this part's tile, and therefore
-                        // (their h_ready of the previous step completed) last step's copies out of our slice have landed
-                        FUSED_WAIT(bar_h_free(q), (ph_b >> q) & 1u, 7);
-                        ph_b ^= 1u << q;
-                        unsigned char* const hp = smem_gen + h_off + q * F_HTILE + hrow;
-                        *reinterpret_cast<uint2*>(hp + hc1) = w1;
-                        *reinterpret_cast<uint2*>(hp + hc2) = w2;
-                        fence_proxy_async();
-                    }
-                    // layer output planes (B, T, 256): scaled split (next layer's 2-MMA projection) or hi / lo (head)
-                    const int b = seq0 + q * FPN + n;
-                    if (b < p.B) {
-                        if (!p.y_scaled) {
+                for (int jp = 0; jp < 4; ++jp) {
+                    if (p.flags & 4) { hv[2 * jp] = ev[0][2 * jp] * 1e-3f; hv[2 * jp + 1] = ev[3][2 * jp + 1] * 1e-3f; continue; }
+                    const f32x2 pei = pack2(ev[0][2 * jp], ev[0][2 * jp + 1]), pef = pack2(ev[1][2 * jp], ev[1][2 * jp + 1]);
+                    const f32x2 peg = pack2(ev[2][2 * jp], ev[2][2 * jp + 1]), peo = pack2(ev[3][2 * jp], ev[3][2 * jp + 1]);
+                    // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(eg + 1)) with one reciprocal (lstm_tc.cu)
+                    const f32x2 di = add2(pei, one), df = add2(pef, one), dg = add2(peg, one);
+                    const f32x2 dig = mul2(di, dg);
+                    const f32x2 den = mul2(df, dig);
+                    const f32x2 cn = mul2(fma2(pack2(cst[2 * jp], cst[2 * jp + 1]), dig, mul2(add2(peg, mone), df)), rcp2(den));
+                    unpack2(cn, cst[2 * jp], cst[2 * jp + 1]);
+                    const f32x2 ec = ex2_clamped2(mul2(cn, k2));
+                    const f32x2 h2v = mul2(add2(ec, mone), rcp2(mul2(add2(peo, one), add2(ec, one))));
+                    unpack2(h2v, hv[2 * jp], hv[2 * jp + 1]);
+                }
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 10] = clock64();
+                // h_s planes (scaled split: h1 . W_hi + h2 . W') -> warp-private staging [plane][row 32][16 B] (the scratch is free
+                // again), so that lane = sequence row holds this warp's 16-byte chunk (8 units) of both planes
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) split_f16(hv[e], a1[e], a2[e]);
-                            w1.x = (uint32_t)__half_as_ushort(a1[0]) | ((uint32_t)__half_as_ushort(a1[1]) << 16);
-                            w1.y = (uint32_t)__half_as_ushort(a1[2]) | ((uint32_t)__half_as_ushort(a1[3]) << 16);
-                            w2.x = (uint32_t)__half_as_ushort(a2[0]) | ((uint32_t)__half_as_ushort(a2[1]) << 16);
-                            w2.y = (uint32_t)__half_as_ushort(a2[2]) | ((uint32_t)__half_as_ushort(a2[3]) << 16);
+                for (int c = 0; c < 8; ++c) {
+                    const int row = 16 * (c >> 2) + 4 * jj + (c & 3);
+                    __half a1, a2;
+                    split_scaled_f16(hv[c], s1, a1, a2);
+                    *reinterpret_cast<__half*>(scr + row * 16 + hoff) = a1;
+                    *reinterpret_cast<__half*>(scr + 512 + row * 16 + hoff) = a2;
+                }
+                __syncwarp();
+                const uint4 v1 = *reinterpret_cast<const uint4*>(scr + lane * 16);
+                const uint4 v2 = *reinterpret_cast<const uint4*>(scr + 512 + lane * 16);
+                if (exchange) {
+                    // every CTA's recurrent MMAs of this step have finished reading the part's tile (it still holds h_{s-1})
+                    if (lane == 0) FUSED_WAIT(bar_h_free(q), ph_b & 1u, 7);
+                    ph_b ^= 1u;
+                    __syncwarp();
+                    if (p.flags & 1) {
+                        if (lane == 0 && g == 0) mbar_arrive(bar_h_ready(q));
+                    } else {
+                        // k-block `rank` of the part's operand tile in all four CTAs: row = lane, chunks g (h1) and 4 + g (h2)
+                        const uint32_t dst = smem_base + h_off + q * F_HTILE + rank * F_BOX + lane * 128;
+                        const uint32_t o1 = (uint32_t)((g ^ (lane & 7)) << 4), o2 = (uint32_t)(((4 + g) ^ (lane & 7)) << 4);
+#pragma unroll
+                        for (int d = 0; d < FC; ++d) {
+                            st_async_v4(dst + o1 + cta_delta[d], v1, bar_h_ready(q) + cta_delta[d]);
+                            st_async_v4(dst + o2 + cta_delta[d], v2, bar_h_ready(q) + cta_delta[d]);
                         }
-                        const size_t yo = ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 4 * q4;
-                        *reinterpret_cast<uint2*>(p.y_a + yo) = w1;
-                        *reinterpret_cast<uint2*>(p.y_b + yo) = w2;
                     }
-                    named_bar_sync(1 + wg, 128);                                   // slice complete (and the exchange buffer is free again)
-                    if (exchange && tid0) {
-                        const uint32_t src = smem_base + h_off + q * F_HTILE + rank * F_BOX;
-                        if (p.flags & 1) {
-                            mbar_arrive(bar_h_ready(q));
-                        } else {
-                            mbar_expect_tx(bar_h_ready(q), (FC - 1) * F_BOX);      // own arrival + the three peers' slices
+                }
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 12] = clock64();
+                // layer output planes (B, T, 256)
+                if (!(p.flags & 2)) {
+                    if (p.y_scaled) {
+                        const int b = seq0 + q * FPN + lane;
+                        if (b < p.B) {
+                            const size_t yo = ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 8 * g;
+                            *reinterpret_cast<uint4*>(p.y_a + yo) = v1;
+                            *reinterpret_cast<uint4*>(p.y_b + yo) = v2;
+                        }
+                    } else {
+                        // last layer: plain hi / lo planes for the head's three-term product
 #pragma unroll
-                            for (uint32_t d = 1; d < FC; ++d) {
-                                const uint32_t peer = (rank + d) & (FC - 1);
-                                dsmem_bulk_copy(mapa_shared(src, peer), src, F_BOX, mapa_shared(bar_h_ready(q), peer));
+                        for (int c = 0; c < 8; ++c) {
+                            const int b = seq0 + q * FPN + 16 * (c >> 2) + 4 * jj + (c & 3);
+                            if (b < p.B) {
+                                __half a1, a2;
+                                split_f16(hv[c], a1, a2);
+                                const size_t yo = ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 8 * g + uu;
+                                p.y_a[yo] = a1;
+                                p.y_b[yo] = a2;
                             }
                         }
                     }
                 }
+                __syncwarp();                                                      // the staging reads are done before the next step's scratch writes
+                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 6] = clock64();
             }
         }
         // item boundary: every role of every CTA is done with this item's tiles and barriers
@@ -409,14 +529,35 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         cluster_sync_all();
         tc_fence_after();
     }
+    if (wacc) wacc[0] += clock64();
     tc_fence_before();
     cluster_sync_all();                                       // no CTA exits while a peer may still signal or copy into it
-    if (warp == 17) tmem_dealloc<512>(tmem_base);
+    if (warp == F_W_MMA) tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------- launcher
+static int g_fused_debug = -1, g_fused_lag = -1;
+// timing probes (wrong results): 1 no h exchange, 2 no y store, 4 no cell math, 8 no recurrent MMAs, 16 no input MMAs
+void lstm_fused_set_debug(int flags, int lag) { g_fused_debug = flags; if (lag >= 0) g_fused_lag = lag; }
+int lstm_fused_read_debug(long long* host, int n) {
+    if (n < 0) {                                             // the timeline table (flag 64)
+        B200VAD_CUDA(cudaMemcpyFromSymbol(host, g_fused_trace, sizeof(long long) * std::min(-n, F_TRACE_STEPS * 16)));
+        return B200VAD_OK;
+    }
+    const size_t bytes = sizeof(long long) * (size_t)std::min<long long>(n, (long long)F_DBG_MAX_CTAS * F_DBG_WARPS * F_DBG_TAGS * 2);
+    B200VAD_CUDA(cudaMemcpyFromSymbol(host, g_fused_dbg, bytes));
+    return B200VAD_OK;
+}
 static int g_fused_clusters[64];
 static std::once_flag g_fused_once[64];
+
+typedef void (*FusedKern)(CUtensorMap, CUtensorMap, FusedParams);
+static FusedKern fused_pick(int nk, int terms) {
+    if (nk == 16) return terms == 2 ? lstm_fused_kernel<16, 2> : lstm_fused_kernel<16, 3>;
+    if (nk == 5) return terms == 2 ? lstm_fused_kernel<5, 2> : lstm_fused_kernel<5, 3>;
+    if (nk == 4) return terms == 2 ? lstm_fused_kernel<4, 2> : lstm_fused_kernel<4, 3>;
+    return lstm_fused_kernel<0, 0>;
+}
 
 static int fused_smem_bytes(int kblocks, int* stages_out) {
     const int stage = 2 * kblocks * F_BOX;
@@ -427,11 +568,12 @@ static int fused_smem_bytes(int kblocks, int* stages_out) {
 }
 
 // resident clusters of the kernel on this device (cudaOccupancyMaxActiveClusters); cached per device
-static int fused_max_clusters(int smem) {
+static int fused_max_clusters() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     std::call_once(g_fused_once[dev], [&] {
+        const void* fn = reinterpret_cast<const void*>(lstm_fused_kernel<16, 2>);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(FC * 64);
         cfg.blockDim = dim3(F_THREADS);
@@ -441,23 +583,22 @@ static int fused_max_clusters(int smem) {
         at.val.clusterDim.x = FC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         int n = 0;
-        cudaFuncSetAttribute(reinterpret_cast<const void*>(lstm_fused_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_MAX - 1024);
-        if (cudaOccupancyMaxActiveClusters(&n, reinterpret_cast<const void*>(lstm_fused_kernel), &cfg) != cudaSuccess || n <= 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (set_max_dynamic_smem(fn, F_SMEM_MAX - 1024) != B200VAD_OK ||
+            cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             n = std::max(1, sms / FC - 4);
         }
         const char* e = getenv("B200VAD_FUSED_CLUSTERS");
         if (e && atoi(e) > 0) n = atoi(e);
         g_fused_clusters[dev] = n;
     });
-    (void)smem;
     return g_fused_clusters[dev];
 }
 
 int lstm_fused_supported(int D) { return D >= 1 && D <= 256; }
-int lstm_fused_clusters() { int st; return fused_max_clusters(fused_smem_bytes(4, &st)); }
+int lstm_fused_clusters() { return fused_max_clusters(); }
 
 // One bidirectional LSTM layer.  x_a / x_b: input planes (B, T, lda) fp16 (terms 2: scaled split; terms 3: hi / lo);
 // weights as packed by api.cu (gate-scaled): wih planes [1024][ldw], whh planes [2][512][128], bias [1024];
@@ -476,21 +617,23 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     int stages = 0;
     const int smem = fused_smem_bytes(p.kblocks, &stages);
     p.stages = stages;
-    static int dbg = -1, lag_env = -1;
-    if (dbg < 0) { const char* e = getenv("B200VAD_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; }
-    if (lag_env < 0) { const char* e = getenv("B200VAD_FUSED_LAG"); lag_env = e ? atoi(e) : 3; }
-    p.flags = dbg; p.lag = lag_env;
-    const int nc = fused_max_clusters(smem);
-    // work items: parts of 16 sequences, spread evenly over items_per_dir items per direction (<= 8 parts each); choose the
-    // count that minimises waves x step cost (a step costs ~ max(parts, 3) part slots: below ~3 parts the per-part
-    // MMA -> pointwise -> exchange chain is the critical path)
+    if (g_fused_debug < 0) { const char* e = getenv("B200VAD_FUSED_DEBUG"); g_fused_debug = e ? atoi(e) : 0; }
+    if (g_fused_lag < 0) { const char* e = getenv("B200VAD_FUSED_LAG"); g_fused_lag = e ? atoi(e) : 2; }
+    p.flags = g_fused_debug; p.lag = g_fused_lag;
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("B200VAD_FUSED_PREFETCH"); pf_env = e ? atoi(e) : 4; }
+    p.prefetch_steps = pf_env;
+    const int nc = fused_max_clusters();
+    // work items: parts of 32 sequences, spread evenly over items_per_dir items per direction (<= 4 parts each); choose the
+    // count that minimises waves x step cost (a step costs ~ max(parts, 2) part slots: with fewer parts in flight the
+    // per-part MMA -> pointwise -> exchange chain is the critical path)
     const int P = (B + FPN - 1) / FPN;
     int best_ipd = (P + FMAXP - 1) / FMAXP;
     double best_cost = 1e30;
     for (int ipd = (P + FMAXP - 1) / FMAXP; ipd <= P; ++ipd) {
         const int maxp = (P + ipd - 1) / ipd;
         const int waves = (2 * ipd + nc - 1) / nc;
-        const double cost = waves * std::max<double>(maxp, 3.0);
+        const double cost = waves * std::max<double>(maxp, 2.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_ipd = ipd; }
         if (maxp == 1) break;
     }
@@ -502,9 +645,10 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, FPN,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(lstm_fused_kernel), smem))) return rc;
+    const FusedKern kern = fused_pick(p.nk, terms);
+    if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem))) return rc;
     prof_begin(0, st);
-    lstm_fused_kernel<<<grid, F_THREADS, smem, st>>>(tm_a, tm_b, p);
+    kern<<<grid, F_THREADS, smem, st>>>(tm_a, tm_b, p);
     prof_end(0, st);
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;

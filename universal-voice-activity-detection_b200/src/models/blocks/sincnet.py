@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 import b200vad
-from .._base import PackedWeights
+from .._base import PackedOwner, PackedWeights
 
 
 class ParamSincFB(nn.Module):
@@ -37,7 +37,7 @@ class Encoder(nn.Module):
         self.filterbank = filterbank
 
 
-class SincNet(nn.Module):
+class SincNet(PackedOwner, nn.Module):
     def __init__(self, sample_rate: int = 16000, stride: int = 1):
         super().__init__()
         if sample_rate != 16000:
@@ -66,7 +66,8 @@ class SincNet(nn.Module):
             raise NotImplementedError("kernels are built for stride=10 (PyanNet.SINCNET_DEFAULTS)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("b200vad implements inference only; call .eval() / torch.no_grad()")
-        blob = self._packed.get(self, waveforms.device, lambda: b200vad.pack_sincnet(self.state_dict(), waveforms.device, prefix=""))
+        blob = self._packed.get(self, waveforms.device, lambda: b200vad.pack_sincnet(self.state_dict(), waveforms.device, prefix=""),
+                                always=self.repack_always)
         return torch.ops.b200vad.sincnet(waveforms[:, 0, :], blob)
 
     def forward(self, waveforms: torch.Tensor) -> torch.Tensor:

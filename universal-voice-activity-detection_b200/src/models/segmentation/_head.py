@@ -5,10 +5,10 @@ import torch.nn as nn
 
 import b200vad
 from src.utils.helper import merge_dict, pairwise
-from .._base import Base, PackedWeights
+from .._base import Base, PackedOwner, PackedWeights
 
 
-class HeadMixin:
+class HeadMixin(PackedOwner):
     LSTM_DEFAULTS = {"hidden_size": 128, "num_layers": 4, "bidirectional": True, "monolithic": True, "dropout": 0.5}
     LINEAR_DEFAULTS = {"hidden_size": 128, "num_layers": 2}
 
@@ -52,6 +52,10 @@ class HeadMixin:
                                       "Linear(128) x 2 (PyanNet2.py:60-67)")
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("b200vad implements inference only; call .eval() / torch.no_grad()")
+        if self.training and l["num_layers"] > 1 and l.get("dropout", 0.0) > 0:
+            # the reference applies inter-layer dropout in train mode even under no_grad (nn.LSTM dropout / self.dropout,
+            # PyanNet2.py:95-120,176-181); the kernels never do
+            raise NotImplementedError("b200vad runs the eval-mode forward (no inter-layer LSTM dropout); call .eval()")
 
     def _head_forward(self, feats: torch.Tensor) -> torch.Tensor:
         """(B, T, D) float32 CUDA -> (B, T, 1) probabilities through torch.ops.b200vad.lstm_head."""
@@ -60,7 +64,7 @@ class HeadMixin:
         num_layers = self.hparams.lstm["num_layers"]
         blob = self._packed.get(self, feats.device, lambda: b200vad.pack_model(
             {k: v for k, v in sd_owner.state_dict().items() if not k.startswith("sincnet.")}, feats.device,
-            self.encoding_dim, num_layers, monolithic=self.hparams.lstm["monolithic"]))
+            self.encoding_dim, num_layers, monolithic=self.hparams.lstm["monolithic"]), always=self.repack_always)
         return torch.ops.b200vad.lstm_head(feats.float(), blob, num_layers).unsqueeze(-1)
 
 

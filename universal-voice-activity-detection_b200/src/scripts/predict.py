@@ -15,7 +15,7 @@ from b200vad.host import (merge_intervals_with_buffer, recording_offsets, segmen
 
 
 def get_segments(test_preds: torch.Tensor, durations: Optional[Sequence[float]] = None, frame_shift: float = 0.02,
-                 buffer: float = 0, split: bool = False, sincnet: bool = False) -> List[list]:
+                 buffer: float = 0, split: bool = False, sincnet: bool = False, row_duration: Optional[float] = None) -> List[list]:
     """test_preds: (rows, frames, 1) or (rows, frames) decisions / probabilities on the GPU (values >= 0.5
     count as speech, predict.py:473).  With ``durations`` the flat stream is re-sliced per recording as
     predict.py:447-458 does; otherwise every row is one recording.  Returns, per recording, the
@@ -26,7 +26,13 @@ def get_segments(test_preds: torch.Tensor, durations: Optional[Sequence[float]] 
     if durations is None:
         seg, _ = torch.ops.b200vad.segments(dec.contiguous(), None, min_run)
         R = dec.shape[0]
-        durs = [dec.shape[1] * frame_shift] * R
+        if row_duration is not None:
+            durs = [float(row_duration)] * R
+        elif sincnet:
+            # SincNet frames are 270 samples apart with a 991-sample receptive field (receptive_field.py:165-219), not frame_shift
+            durs = [((dec.shape[1] - 1) * 270 + 991) / 16000.0] * R
+        else:
+            durs = [dec.shape[1] * frame_shift] * R
     else:
         offs = recording_offsets(durations, dec.numel(), frame_shift, sincnet=sincnet)
         seg, _ = torch.ops.b200vad.segments(dec.reshape(-1).contiguous(),
@@ -119,4 +125,5 @@ def predict_vad(model, waveforms: torch.Tensor, frame_shift: float = 0.01, max_r
         inputs = fb.extract_batch(w, 16000) if fb is not None else w
         preds.append(model.predict_step({"inputs": inputs}, 0))
     test_preds = torch.cat(preds)
-    return test_preds, get_segments(test_preds, None, frame_shift, sincnet=model.model_name == "PyanNet")
+    return test_preds, get_segments(test_preds, None, frame_shift, sincnet=model.model_name == "PyanNet",
+                                    row_duration=waveforms.shape[1] / 16000.0)
