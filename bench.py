@@ -9,12 +9,18 @@ Workload (BASELINE.json configs[1]): a batch of 4096 x 8 s synthetic 16 kHz utte
   e2e   : the same metric through the host-facing C ABI (b200vad_session_submit_host / _wait):
           waveforms in PINNED HOST memory, H2D copy of every step's input and D2H of its results
           inside the timed region; two steps are in flight so the copies overlap the compute.
-  roofline : the dominant kernel (LSTM recurrence), timed live with CUDA events on its own stream
-          inside the timed region (b200vad_profile_*), algorithmic FLOPs / measured duration.
+  roofline : the dominant kernel (the fused LSTM layer kernel: input projection + recurrence), timed live with
+          CUDA events on its own stream inside the timed region (b200vad_profile_*).  SURVEY 8(d) bounds the
+          LSTM by the TENSOR pipe: frac = algorithmic FLOPs per launch / measured duration / sustained bf16 peak;
+          path_frac = the same for the whole model over the whole step; traffic from the committed ncu capture.
+  pyannet  : the SincNet path (PyanNet through the drop-in VadModel) on the same 4096 x 8 s batch.
+  modes    : BASELINE configs 1 / 3 / 5 and a sharded corpus run (config 4) at this build (N = 1 only).
   cpu_baseline : the oracle (CPU restatement of the reference path) on a bounded sample, rank 0, N=1.
-`--impl reference` times the reference's CPU implementation of the path (the oracle port) instead.
-Multi-GPU: `torchrun --nproc-per-node N bench.py --gpus N ...`; utterances are sharded across ranks
-(no data-path collective), segment lists are gathered with NCCL inside the step; scaling = weak.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port) instead, on the same
+`config.workload` (a bounded sample of its rows per step).
+Multi-GPU: `torchrun --nproc-per-node N bench.py --gpus N ...`; utterances are sharded across ranks (no data-path
+collective); segment lists are gathered with NCCL on a side stream, one step behind the compute (b200vad.SegmentGatherer),
+and drained inside the timed region; scaling = weak.
 """
 
 from __future__ import annotations
@@ -37,16 +43,17 @@ ROWS, SECONDS = 4096, 8.0
 N_SAMPLES = int(SECONDS * 16000)
 T_FRAMES = (N_SAMPLES + 80) // 160
 # Per-kernel algorithmic work per FRAME (10 ms of one utterance; 3 276 800 frames per launch at 4096 x 8 s), DESIGN.md
-# section 4.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture
-# (profiles/r01_ncu_full_summary_v10.md; average over the launches of a kind), bytes per launch at 4096 x 8 s.  `executed_over_algorithmic`: the split-precision
-# products execute 3 (layer-0 projection, head) / 2 (layer 1-3 projections; recurrence: two h planes) fp16 MMAs per algorithmic one.
+# section 4.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch of an `ncu --set full` capture at the named
+# workload (profiles/r02_ncu_full_summary.md; average over the launches of a kind).  `executed_over_algorithmic`: the
+# split-precision products execute 3 (layer-0 input product, head) / 2 (everything else) fp16 MMAs per algorithmic one.
+LSTM_FLOP = [2 * 2 * 512 * (80 + 128)] + [2 * 2 * 512 * (256 + 128)] * 3          # per frame and layer, both directions
+LSTM_EXEC = [2 * 2 * 512 * (3 * 80 + 2 * 128)] + [2 * 2 * 512 * 2 * (256 + 128)] * 3
 KERNELS = {
-    0: {"name": "lstm_tc_kernel (LSTM recurrence, 4 launches/step)", "bound": "hbm", "tensor": True,
-        # per layer: xg read 2 x 512 x 4 B + y planes written 2 x 128 x (2 + 2) B
-        "bytes_per_frame": 4096 + 1024, "flop_per_frame": 2 * 2 * 512 * 128, "executed_over_algorithmic": 2.0, "traffic": 16.76e9},
-    1: {"name": "gemm_xg_pair_kernel (input projections, 4 launches/step)", "bound": "hbm", "tensor": True,
-        # per layer (1-3): x planes read 256 x 4 B + xg written 1024 x 4 B; layer 0 reads 80 x 4 B.  Bound by the xg write
-        # stream (and, at 1.3 GHz under the power cap, 81 % of the sustained tensor peak: profiles/r01_ncu_full_summary_v8.md)
+    0: {"name": "lstm_fused_kernel (input projection + recurrence per layer, 4 launches/step)", "bound": "tensor", "tensor": True,
+        # per layer: x planes read 2 x 2 B x D (320 B layer 0, 1024 B layers 1-3) + y planes written 1024 B; no xg tensor
+        "bytes_per_frame": ((320 + 1024) + 3 * (1024 + 1024)) / 4.0, "flop_per_frame": sum(LSTM_FLOP) / 4.0,
+        "executed_over_algorithmic": sum(LSTM_EXEC) / float(sum(LSTM_FLOP)), "traffic": None},
+    1: {"name": "gemm_xg_pair_kernel (legacy input projections, b200vad_set_lstm_fused(0) only)", "bound": "hbm", "tensor": True,
         "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
         "executed_over_algorithmic": (3 * 80 + 2 * 3 * 256) / (80 + 3 * 256.0), "traffic": (14.76e9 + 3 * 16.76e9) / 4},
     2: {"name": "head_fused_kernel (head linears + classifier + sigmoid, 1 launch/step)", "bound": "hbm", "tensor": True,
@@ -57,6 +64,11 @@ KERNELS = {
         "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": 3.12e9},
 }
 MODEL_FLOP_PER_FRAME = 2.884e6
+ALGORITHMIC_BYTES_PER_AUDIO_S = 64.4e3      # 64 000 (waveform f32) + 400 (probabilities)
+# DRAM traffic of one step at the named workload, summed over all launches of the ncu --set full capture (None until captured)
+STEP_TRAFFIC_BYTES = None
+WORKLOAD = (f"{ROWS} x {SECONDS:.0f} s synthetic 16 kHz utterances per GPU: fbank + PyanNet2 (4xBiLSTM128, random-init seed 42) "
+            "forward + threshold/median(49) + segments")
 
 
 def load_peaks():
@@ -149,13 +161,98 @@ def run_reference(args, out):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{ROWS} x {SECONDS:.0f} s utterances, 16 kHz, fbank + PyanNet2 forward + median + segments",
-                       "sample": f"{sample_rows} x {SECONDS:.0f} s per step"},
+            "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "samples_per_row": N_SAMPLES, "frames_per_row": T_FRAMES,
+                       "sample": f"{sample_rows} of the {ROWS} rows per step (CPU arm: bounded sample of the same workload)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample_rows} x {SECONDS:.0f} s utterances per step, torch CPU threads={threads}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     out.emit(json.dumps(line))
     return 0
+
+
+def other_paths(torch, b200vad, VadModel, dev, blob, wav_dev, rows):
+    """The other named paths at this build, on the GPU the bench line ran on (CUDA events; parity for each lives in tests/):
+    `pyannet`: the SincNet front-end + LSTM head (PyanNet through the drop-in VadModel) on the bench batch;
+    `modes`: BASELINE configs 1 (60 s clip as 12 reference windows through the drop-in modules), 3 (1 h long-form, reference
+    window semantics), 5 (256 streams x 5 s ring x 10 ms hop, per-push latency) and 4 (sharded corpus: here 50 h on this GPU)."""
+    from b200vad import corpus
+    from src.features import Fbank, FbankConfig
+    from src.scripts.predict import get_segments
+
+    def timed(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    # ---- PyanNet (north_star's SincNet front-end) on the same batch
+    torch.manual_seed(42)
+    pm = VadModel("PyanNet", {}).eval().to(dev)
+    with torch.no_grad():
+        ms_all = timed(lambda: pm.predict_step({"inputs": wav_dev}, 0), 5, 3)
+        ms_front = timed(lambda: pm.model.sincnet.frames_time_major(wav_dev.unsqueeze(1)), 5, 2)
+    hours = rows * SECONDS / 3600.0
+    ts = int(b200vad.lib().b200vad_sincnet_num_frames(N_SAMPLES))
+    out["pyannet"] = {"value": hours / (ms_all / 1e3), "unit": UNIT, "ms_per_step": ms_all, "frontend_ms": ms_front,
+                      "workload": f"{rows} x {SECONDS:.0f} s through VadModel('PyanNet').predict_step: SincNet (sinc conv 251/10 + 2 x conv5, "
+                                  f"MaxPool3 + InstanceNorm + LeakyReLU) -> 4 x BiLSTM(128) -> head -> median(49); {ts} frames per row",
+                      "roofline": {"bound": "tensor", "frontend_flop_per_audio_s": 96.3e6, "head_flop_per_audio_s": 168.5e6,
+                                   "achieved_tflops": (96.3e6 + 168.5e6) * rows * SECONDS / (ms_all / 1e3) / 1e12,
+                                   "note": "algorithmic FLOPs (SURVEY 8d) over the whole PyanNet step"}}
+    del pm
+    modes = {}
+    # ---- config 1
+    torch.manual_seed(42)
+    model = VadModel("PyanNet2", {"encoding_dim": 80}).eval().to(dev)
+    clip = b200vad.synth.meeting_batch(1, 960000, seed=42)[0].to(dev)
+    fb = Fbank(FbankConfig(device="cuda"))
+
+    def config1():
+        with torch.no_grad():
+            dec = model.predict_step({"inputs": fb.extract_batch(clip.view(12, 80000), 16000)}, 0)
+        return get_segments(dec, [60.0], 0.01)
+    modes["config1_60s_clip_ms"] = timed(config1, 10, 2)
+    # ---- config 3
+    g = torch.Generator(device=dev).manual_seed(1)
+    wav = 0.05 * torch.randn(3600 * 16000, device=dev, generator=g)
+    lf = b200vad.LongFormVad(blob, 4, hop=None)
+    modes["config3_one_hour_720_windows_ms"] = timed(lambda: lf(wav), 3, 1)
+    lf2 = b200vad.LongFormVad(blob, 4, hop=40000)
+    modes["config3_one_hour_overlap_1439_windows_ms"] = timed(lambda: lf2(wav), 3, 1)
+    del wav, lf, lf2
+    # ---- config 5
+    sv = b200vad.StreamingVad(blob, 4, num_streams=256, window=80000, hop=160)
+    gen = torch.Generator().manual_seed(0)
+    chunks = [(0.1 * torch.randn(256, 160, generator=gen)).pin_memory() for _ in range(16)]
+    dms = []
+    for i in range(330):
+        _, _, ms = sv.push(chunks[i % 16])
+        if i >= 30:
+            dms.append(ms)
+    sv.close()
+    dms.sort()
+    modes["config5_streaming_256x5s_push_ms_p50"] = dms[len(dms) // 2]
+    modes["config5_streaming_256x5s_push_ms_p99"] = dms[min(len(dms) - 1, int(0.99 * len(dms)))]
+    # ---- config 4 (one rank's share of a sharded corpus: waveforms synthesised on the device per batch, segment gather at the end)
+    corpus_hours = 50.0
+    U = int(round(corpus_hours * 3600 / SECONDS))
+    corpus.run_corpus(blob, 4096, N_SAMPLES, 0, 1, 4096)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    seg, _ = corpus.run_corpus(blob, U, N_SAMPLES, 0, 1, 4096)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    modes["corpus_audio_h_s"] = corpus_hours / dt
+    modes["corpus_note"] = f"{corpus_hours:g} h = {U} x 8 s utterances on this GPU incl. on-device synthesis and the final segment gather ({int(seg.shape[0])} segments)"
+    out["modes"] = modes
+    return out
 
 
 class _OnlyJsonOnStdout:
@@ -181,6 +278,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS, help="utterances per GPU per step (default = the named workload)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-modes", action="store_true", help="skip the PyanNet arm and the configs 1 / 3 / 4 / 5 timings")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, jout)
@@ -223,11 +321,13 @@ def main():
         host_mem = "pinned write-combined (b200vad_host_alloc)"
     hours_step_global = rows * world * SECONDS / 3600.0
 
+    # segment lists: fixed-capacity device output (no host sync in the step), gathered across ranks one step behind the
+    # compute on a side stream and drained inside the timed region
+    gatherer = b200vad.SegmentGatherer(device=dev)
+
     def device_step():
-        prob, dec, seg, counts = torch.ops.b200vad.vad_pipeline(wav_dev, None, blob, 4, 0.5, 49)
-        if world > 1:
-            seg = b200vad.gather_segments(seg, row_base=lo)
-        return seg
+        prob, dec, seg, counts, seg_off = torch.ops.b200vad.vad_pipeline_padded(wav_dev, None, blob, 4, 0.5, 49)
+        gatherer.push(seg, seg_off, row_base=lo)
 
     def barrier():
         if world > 1:
@@ -237,6 +337,7 @@ def main():
     # ---------------- device-resident arm
     for _ in range(warmup):
         device_step()
+    gatherer.drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -248,9 +349,11 @@ def main():
     e0.record()
     for _ in range(steps):
         device_step()
+    gathered = gatherer.drain()                 # completes the pending gathers; the compute stream waits for the side stream
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    nseg_gathered = int(gathered[-1].shape[0]) if gathered else 0
     launches = L.b200vad_launch_count() - launches0
     prof = {}
     for kind in KERNELS:
@@ -275,7 +378,10 @@ def main():
         res = sess.wait(slot, outs[slot])
         seg = res["seg"]
         if world > 1:
-            seg = b200vad.gather_segments(seg.to(dev), row_base=lo)
+            # host segment list of this step -> device -> side-stream gather (completed one step later / at the drain)
+            sd = seg.to(dev, non_blocking=True)
+            off = torch.tensor([0, sd.shape[0]], dtype=torch.int64, device=dev)
+            gatherer.push(sd, off, row_base=lo)
         return seg
 
     def e2e_run(k):
@@ -285,6 +391,7 @@ def main():
             if i >= 1:
                 nseg = e2e_finish((i - 1) & 1).shape[0]
         nseg = e2e_finish((k - 1) & 1).shape[0]
+        gatherer.drain()
         return nseg
 
     e2e_run(2)
@@ -320,6 +427,33 @@ def main():
     d2h = (hi - lo) * T_FRAMES + nseg * 12 + 8
     sess.close()
 
+    # ---------------- copy-only H2D probe (what bounds e2e with float32 host waveforms): all ranks copy at the same time
+    probe_dst = torch.empty_like(wav_dev)
+    for _ in range(2):
+        probe_dst.copy_(wav_host, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(5):
+        probe_dst.copy_(wav_host, non_blocking=True)
+    e1.record()
+    barrier()
+    h2d_gbs = 5 * h2d / (e0.elapsed_time(e1) / 1e3) / 1e9
+    t = torch.tensor([h2d_gbs, h2d_gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmin = t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_min, h2d_sum = tmin[0].item(), t[1].item()
+    else:
+        h2d_min = h2d_sum = h2d_gbs
+    del probe_dst
+    h2d_floor_ms = h2d / (h2d_min * 1e9) * 1e3            # the slowest rank's copy time of one step's input
+
+    # ---------------- the SincNet path (PyanNet) and the other BASELINE configs at this build (single GPU only)
+    extra = {}
+    if world == 1 and not args.skip_modes:
+        extra = other_paths(torch, b200vad, VadModel, dev, blob, wav_dev, rows)
+
     if rank == 0:
         peaks = load_peaks()
         frames_per_launch = T_FRAMES * (hi - lo)
@@ -343,37 +477,49 @@ def main():
         dom = max(prof, key=lambda k: prof[k][0])
         dspec, (tms, n) = KERNELS[dom], prof[dom]
         dent = kernels[dspec["name"]]
+        whole_tf = MODEL_FLOP_PER_FRAME * frames_per_launch / (ms_per_step / 1e3) / 1e12
+        alg_bytes_step = ALGORITHMIC_BYTES_PER_AUDIO_S * (hi - lo) * SECONDS
         if dspec["bound"] == "hbm":
             roof = {"kernel": dspec["name"], "bound": "hbm", "achieved": dent["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": dent["hbm_frac"], "traffic": dent["traffic"],
                     "peak_source": f"{peaks['src']} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"}
         else:
+            # the LSTM is bounded by the tensor pipe; achieved counts ALGORITHMIC FLOPs (2 * 512 * (D + 128) per
+            # frame, layer and direction), the split-precision products execute 2-3 fp16 MMAs per algorithmic one (executed_frac)
             roof = {"kernel": dspec["name"], "bound": "tensor", "achieved": dent["tflops"], "peak": peaks["tf_sustained"],
                     "unit": "TFLOP/s", "frac": dent["tflops"] / peaks["tf_sustained"], "traffic": dent["traffic"],
                     "executed_frac": dent["tensor_frac"],
-                    "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); `achieved` counts ALGORITHMIC "
-                                   "FLOPs, the split-precision products execute 2-3 fp16 MMAs per algorithmic one (executed_frac)"}
+                    "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json bf16_tflops_sustained)"}
         roof.update({"launches": int(n), "avg_launch_ms": tms / max(n, 1), "share_of_step": dent["share_of_step"],
-                     "algorithmic_per_launch": "bytes (or FLOPs) per frame below x 3 276 800 frames per launch (DESIGN.md section 4)",
+                     "algorithmic_per_launch": "FLOPs (bytes) per frame below x 3 276 800 frames per launch (DESIGN.md section 4)",
+                     "path_frac": whole_tf / peaks["tf_sustained"], "path_tflops": whole_tf,
+                     "path_note": "whole model (2.884 MFLOP per frame, SURVEY 8d) over the whole step vs the sustained tensor peak",
+                     "step_traffic_bytes": STEP_TRAFFIC_BYTES if rows == ROWS else None,
+                     "algorithmic_bytes_per_step": alg_bytes_step,
+                     "traffic_over_algorithmic": (STEP_TRAFFIC_BYTES / alg_bytes_step) if (STEP_TRAFFIC_BYTES and rows == ROWS) else None,
                      "kernels": kernels})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (fbank, activations, cell state in f32)", "data": "synthetic",
-            "config": {"workload": f"{rows} x {SECONDS:.0f} s synthetic 16 kHz utterances per GPU: fbank + PyanNet2 (4xBiLSTM128, random-init seed 42) "
-                                   "forward + threshold/median(49) + segments", "rows_per_gpu": rows, "samples_per_row": N_SAMPLES,
+            "config": {"workload": WORKLOAD if rows == ROWS else WORKLOAD.replace(str(ROWS), str(rows), 1), "rows_per_gpu": rows, "samples_per_row": N_SAMPLES,
                        "frames_per_row": T_FRAMES, "parallelism": f"utterance-sharded x{world}",
                        "l2": f"inputs ({rows * N_SAMPLES * 4 / 1e9:.2f} GB waveforms + GBs of intermediates per step) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "host_numa_node": numa, "host_memory": host_mem,
+                    "h2d_ceiling_gbs": {"per_gpu_min": h2d_min, "aggregate": h2d_sum,
+                                        "note": "copy-only H2D of the same pinned batch, all ranks at once, CUDA events"},
+                    "h2d_floor_ms_per_step": h2d_floor_ms, "e2e_over_h2d_floor": h2d_floor_ms / e2e_ms,
                     "pcm16_input": {"value": hours_step_global / (pcm_ms / 1e3), "ms_per_step": pcm_ms, "h2d_bytes_per_step": h2d // 2,
                                     "note": "same API fed int16 PCM host waveforms (b200vad_session_submit_host_i16); informational"},
                     "api": "b200vad_session_submit_host / b200vad_session_wait, 2 steps in flight (pinned host waveforms -> host decisions + segments)"},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "whole_model_tflops": MODEL_FLOP_PER_FRAME * T_FRAMES * (hi - lo) / (ms_per_step / 1e3) / 1e12,
+            "whole_model_tflops": whole_tf,
+            "segments_gathered_per_step": nseg_gathered,
             "clocks": clocks,
         }
+        line.update(extra)
         if world == 1 and not args.skip_cpu_baseline:
             threads = os.cpu_count() or 1
             v, dt = cpu_reference(512, 1, 1, threads)

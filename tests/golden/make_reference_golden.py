@@ -154,11 +154,12 @@ def state_hash(sd):
     return h.hexdigest()
 
 
-def spread(vm, x):
-    """Rescale the classifier so that the logits on x have zero mean and unit spread."""
+def spread(vm, x, sigma=1.0):
+    """Rescale the classifier so that the logits on x have zero mean and standard deviation sigma (1: the original fixtures;
+    2 and 4: what a trained detector looks like, p from ~1e-4 to ~1 - 1e-4)."""
     p = vm(x).double()
     z = torch.log(p / (1 - p))
-    scale = (1.0 / z.std().clamp_min(1e-9)).float()
+    scale = (float(sigma) / z.std().clamp_min(1e-9)).float()
     cls = vm.model.classifier
     cls.bias.copy_((cls.bias - z.mean().float()) * scale)
     cls.weight.mul_(scale)
@@ -222,6 +223,33 @@ def main():
         finally:
             torch.Tensor.to = orig_to
 
+    # trained-model logit spreads: the same model and inputs with the classifier rescaled to sigma = 2 and 4
+    for sg in (2, 4):
+        with torch.no_grad():
+            spread(vm, feats, sg)
+            out[f"d80_s{sg}_cls_w"] = vm.model.classifier.weight.numpy().copy()
+            out[f"d80_s{sg}_cls_b"] = vm.model.classifier.bias.numpy().copy()
+            out[f"d80_s{sg}_prob"] = vm(feats).numpy()
+            torch.Tensor.to = to_cpu_for_cuda
+            try:
+                out[f"d80_s{sg}_predict"] = vm.predict_step({"inputs": feats, "is_voice": labels}, 0).numpy()
+            finally:
+                torch.Tensor.to = orig_to
+    # BASELINE config 2's row shape (8 s = 800 frames x 80 mel bins), one row, sigma = 2 classifier: the reference's own output
+    g2 = torch.Generator().manual_seed(321)
+    feats8 = torch.randn(1, 800, 80, generator=g2) * 3 - 5
+    with torch.no_grad():
+        spread(vm, feats8, 2)
+        out["cfg2_cls_w"] = vm.model.classifier.weight.numpy().copy()
+        out["cfg2_cls_b"] = vm.model.classifier.bias.numpy().copy()
+        out["cfg2_feats"] = feats8.numpy()
+        out["cfg2_prob"] = vm(feats8).numpy()
+        torch.Tensor.to = to_cpu_for_cuda
+        try:
+            out["cfg2_predict"] = vm.predict_step({"inputs": feats8, "is_voice": torch.zeros(1, 800)}, 0).numpy()
+        finally:
+            torch.Tensor.to = orig_to
+
     # ---- a2: a small PyanNet2 with every weight stored (independent of the RNG stream): monolithic and layer-wise LSTMs
     for tag, mono in (("tiny_mono", True), ("tiny_split", False)):
         torch.manual_seed(7)
@@ -269,6 +297,12 @@ def main():
             out["d768_predict"] = vm768.predict_step({"inputs": x768, "is_voice": torch.zeros(2, 60)}, 0).numpy()
         finally:
             torch.Tensor.to = orig_to
+    for sg in (2, 4):
+        with torch.no_grad():
+            spread(vm768, x768, sg)
+            out[f"d768_s{sg}_cls_w"] = vm768.model.classifier.weight.numpy().copy()
+            out[f"d768_s{sg}_cls_b"] = vm768.model.classifier.bias.numpy().copy()
+            out[f"d768_s{sg}_prob"] = vm768(x768).numpy()
 
     # ---- a7: median_filter on its own (helper.py:66-97), both windows, ties / NaN / short rows
     prob = torch.sigmoid(torch.cumsum(torch.randn(5, 400, generator=g), 1) * 0.3)

@@ -52,15 +52,15 @@ def main():
         lib.b200vad_set_lstm_fused_debug(flags | 32, 3)
         torch.ops.b200vad.lstm_head(x, blob, 4)
         torch.cuda.synchronize()
-        n = 148 * 19 * 16
+        n = 148 * 25 * 16
         buf = (C.c_longlong * n)()
         lib.b200vad_lstm_fused_read_debug(buf, n)
-        roles = {"prod": {1: "x_empty"},
-                 "pw": {6: "acc_ready", 7: "h_free"}, "mmah": {2: "x_done", 4: "h_ready"}, "mmax": {2: "acc_free", 3: "x_full", 5: "drain"}}
+        roles = {"prod": {1: "x_empty"}, "pw": {6: "acc_ready"}, "mmah": {2: "x_done", 4: "h_ready"},
+                 "mmax": {2: "acc_free", 3: "x_full", 5: "drain"}, "send": {1: "slice", 7: "h_free"}}
         print(f"--- wait sites, {label} (last layer launch; cycles per kernel, non-immediate waits)")
         for cta in (0, 1, 5):
-            for warp, role in ((0, "pw"), (5, "pw"), (10, "pw"), (15, "pw"), (16, "prod"), (17, "mmah"), (18, "mmax")):
-                base = (cta * 19 + warp) * 16
+            for warp, role in ((0, "pw"), (5, "pw"), (10, "pw"), (15, "pw"), (16, "prod"), (17, "mmah"), (18, "mmah"), (19, "mmax"), (20, "mmax"), (21, "send"), (24, "send")):
+                base = (cta * 25 + warp) * 16
                 tot = buf[base]
                 names = roles[role]
                 parts = [f"{names.get(t, t)} {buf[base + 2 * t] / max(tot, 1) * 100:5.1f}% (n={buf[base + 2 * t + 1]})" for t in range(1, 8) if buf[base + 2 * t + 1]]
@@ -75,8 +75,8 @@ def main():
         torch.cuda.synchronize()
         buf = (C.c_longlong * 128)()
         lib.b200vad_lstm_fused_read_debug(buf, -128)
-        names = ["mma:h_ready", "mma:issued", "pw:acc_rdy", "pw:tmem_ld", "pw:ex2", "pw:xchg", "pw:done", "snd:slice", "snd:sent",
-                 "x:start", "pw:math", "x:accfree", "pw:slice", "x:xfull", "x:issued", "x:commit"]
+        names = ["mma:h_ready", "mma:issued", "pw:acc_rdy", "pw:tmem_ld", "pw:ex2", "pw:xchg", "-", "snd:slice", "snd:sent",
+                 "x:start", "pw:math", "-", "pw:done", "x:xfull", "-", "x:commit"]
         print(f"--- timeline of one part, {label} (cycles after the MMA thread saw h_ready; last column = step period)")
         print("      " + " ".join(f"{n:>12s}" for n in names))
         prev = None
@@ -89,23 +89,37 @@ def main():
         print("(x:* = the input product of the SAME step and part, issued by the MMA thread one round earlier: negative offsets)")
         lib.b200vad_set_lstm_fused_debug(0, lag_default)
 
+    def mma_threads(label):
+        """stamps of the two MMA-issuing threads of CTA 0 over two consecutive steps (flag 128)"""
+        lib.b200vad_set_lstm_fused(1)
+        lib.b200vad_set_lstm_fused_debug(64 | 128, 2)
+        torch.ops.b200vad.lstm_head(x, blob, 4)
+        torch.cuda.synchronize()
+        buf = (C.c_longlong * 256)()
+        lib.b200vad_lstm_fused_read_debug(buf, -256)
+        base = 128
+        t0 = buf[base]
+        print(f"--- MMA threads of CTA 0, {label}: cycles since the recurrent issuer reached (step 100, part 0)")
+        for st in range(2):
+            for q in range(8):
+                h = [buf[base + st * 32 + q * 4 + i] - t0 for i in range(4)]
+                xx = [buf[base + 64 + st * 32 + q * 4 + i] - t0 for i in range(4)]
+                print(f"step {100 + st} part {q}: H start {h[0]:6d} x_done {h[1]:6d} h_ready {h[2]:6d} committed {h[3]:6d} | "
+                      f"X start {xx[0]:6d} acc_free {xx[1]:6d} x_full {xx[2]:6d} committed {xx[3]:6d}", flush=True)
+        lib.b200vad_set_lstm_fused_debug(0, 2)
+
     lag_default = int(os.environ.get("LAG", "2"))
+    mma_threads("product path")
     timeline(0, "product path")
     timeline(8 | 16, "no MMAs")
     waits(0, "product path")
-    waits(1 | 2 | 4 | 8 | 16, "all work off")
+    waits(4 | 8 | 16, "no cell math, no MMAs")
     run(0, 2, "legacy (projection + recurrence)", fused=0)
     run(0, 2, "fused, product path")
-    for lag in (1, 3):
-        run(0, lag, f"fused, lag {lag}")
-    run(1, 2, "no h exchange")
-    run(2, 2, "no y store")
     run(4, 2, "no cell math")
     run(8, 2, "no recurrent MMAs")
     run(16, 2, "no input MMAs")
-    run(1 | 2, 2, "no exchange, no y store")
-    run(1 | 2 | 4, 2, "no exchange, no y store, no cell math")
-    run(1 | 2 | 4 | 8 | 16, 2, "all off (barrier chain only)")
+    run(4 | 8 | 16, 2, "no cell math, no MMAs")
     run(8 | 16, 2, "no MMAs at all")
     lib.b200vad_set_lstm_fused_debug(0, 3)
 

@@ -36,15 +36,20 @@ def run_corpus(packed: torch.Tensor, num_utts: int, num_samples: int, rank: int 
     dev = packed.device
     lo, hi = shard_range(num_utts, rank, world)
     buf = torch.empty((min(batch_rows, max(hi - lo, 1)), num_samples), dtype=torch.float32, device=dev)
-    segs, frames = [], 0
+    pend, frames = [], 0
     for b0 in range(lo, hi, batch_rows):
         rows = min(batch_rows, hi - b0)
         wav = synth_corpus(b0, rows, num_samples, seed, dev, out=buf)
-        prob, dec, seg, counts = torch.ops.b200vad.vad_pipeline(wav, None, packed, num_layers, thr, kernel)
-        seg = seg.clone()
-        seg[:, 0] += b0
-        segs.append(seg)
+        # fixed-capacity segment output: nothing synchronises inside the loop (the batches queue back to back on the stream)
+        prob, dec, seg, counts, seg_off = torch.ops.b200vad.vad_pipeline_padded(wav, None, packed, num_layers, thr, kernel)
+        pend.append((b0, seg, seg_off))
         frames += dec.numel()
+    segs = []
+    totals = torch.stack([o[-1] for _, _, o in pend]).tolist() if pend else []       # ONE host read for the whole shard
+    for (b0, seg, _), n in zip(pend, totals):
+        sl = seg[: int(n)].clone()
+        sl[:, 0] += b0
+        segs.append(sl)
     local = torch.cat(segs) if segs else torch.empty((0, 3), dtype=torch.int32, device=dev)
     if gather and world > 1:
         return gather_segments(local, row_base=0), frames

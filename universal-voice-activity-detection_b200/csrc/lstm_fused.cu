@@ -5,31 +5,39 @@
 //
 // The two-kernel layer (gemm_xg_pair_kernel -> xg in HBM -> lstm_tc_kernel) moved 8 KB of fp32 xg per frame and layer
 // (107 of the 140 GB a 4096 x 8 s step moved) and had room for only ONE fp16 plane of W_hh in tensor memory.  Here a
-// CLUSTER OF 4 CTAs owns a block of sequences of one direction and splits the HIDDEN UNITS: CTA r computes the four
+// CLUSTER OF 4 CTAs owns up to 128 sequences of one direction and splits the HIDDEN UNITS: CTA r computes the four
 // gates of units [32 r, 32 r + 32) = 128 gate rows = one MMA M tile.  Per CTA, tensor memory (512 columns) holds
 //   * W_hh rows of its units as TWO fp16 planes (W_hi, W' -- the scaled split below): 128 columns,
 //   * W_ih rows of its units as two planes (W_hi + W_lo or W_hi + W'):                <= 256 columns (D <= 256),
 //   * the gate accumulators of up to 8 parts of 16 sequences:                           128 columns,
-// so all weights of the layer stay resident for all T steps and nothing but x_t (fp16 planes, 1 KB per sequence-step) is
-// read from HBM and nothing but h_t (the layer output planes) is written.
-// Per step and part (16 sequences) the single MMA-issuing thread of a CTA issues
-//   x-MMAs:  acc  = W_ih . x_t        (A = weights in TMEM, B = the TMA-loaded x tile; issued one step AHEAD, as soon as the
-//                                      pointwise warps have read the previous step's accumulator),
-//   h-MMAs:  acc += W_hh . h_{t-1}    (B = the h operand tile in shared memory) once the cluster has exchanged h_{t-1},
-// the pointwise warps turn the accumulator into h_t for the CTA's 32 units, write it into the CTA's own slice of the h
-// operand tile and to HBM, and one thread sends that 2 KB slice to the three peers with cp.async.bulk over distributed
-// shared memory (the peers' mbarriers count the bytes).  x tiles are TMA-multicast: each CTA fetches a quarter of a tile
-// for the whole cluster.  8 parts per cluster are in flight, so the exchange of one part hides behind the MMAs of the others.
+// so all weights of the layer stay resident for all T steps; the only HBM traffic is x_t in (fp16 planes) and h_t out
+// (the layer output planes, which the next layer and the head read anyway).
+//
+// Roles of a CTA (20 warps):
+//   * TMA producer: x tiles of (step, part), multicast to the cluster (each CTA fetches a quarter of every tile);
+//   * input-product issuer:     acc(s, q)  = W_ih . x_s      (tcgen05.mma, A = weights in TMEM), one step ahead;
+//   * recurrent-product issuer: acc(s, q) += W_hh . h_{s-1}  as soon as the part's h tile is complete -- the critical path.
+//     Two issuing threads because tcgen05.mma issue blocks at the tensor pipe's pace and a commit drains it: one thread
+//     alone left the pipe idle during every barrier wait;
+//   * 16 pointwise warps: warp (pg, g) serves parts pg and pg + 4 alternately (while one part's h travels, the other is
+//     computed) and owns TMEM lane quarter g.  Lane 32 g + l of the accumulator is gate (l & 3) of unit 8 g + (l >> 2):
+//     the four gates of a cell sit in four adjacent lanes of ONE warp, so the (gate x sequence) transposition runs through a
+//     warp-private 2 KB scratch with __syncwarp only -- no cross-warp barrier anywhere in the per-step chain;
+//   * h exchange over distributed shared memory: the pointwise warps write h_s (fp16 planes, operand layout) into the CTA's
+//     own 2 KB staging slice of the part; the exchange-sender thread copies it with cp.async.bulk into k-block `rank` of the
+//     part's operand tile in all four CTAs (the destination mbarriers count the bytes).  The MMA K index is free as long as
+//     A and B agree: K block r (64 slots = one 128-byte swizzled row) is [h1 of units 32r..32r+31 | h2 of the same units],
+//     exactly what CTA r produces, so a CTA's contribution is ONE contiguous box.  (Tried and slower: per-lane st.async
+//     stores -- the ~20 B/clk DSMEM port back-pressures the pointwise warps; an exchange through the output planes in L2
+//     with a multicast TMA load -- the release after the global stores costs ~2500 cycles per pass.)
 //
 // Precision (DESIGN.md "Precision"): every product is split-precision with fp32 accumulation.  Activations travel as the
 // scaled split x1 = fp16((1 - s) x), x2 = fp16(x - x1), s = 2^-6, weights as W_hi = fp16(W), W' = fp16(W_hi + W_lo / s):
 // x1 . W_hi + x2 . W' = x . W to ~2^-18 with TWO fp16 MMAs.  The recurrent product uses the same split for h, so W_hh has
 // the accuracy of two planes (the single-plane W_hh of lstm_tc.cu was the dominant error of the old path: 1.3e-3 on p at
-// logit spread 2).  Layer 0 may take (hi, lo) planes and three MMAs (x_lo.W_hi + x_hi.W_lo + x_hi.W_hi).
-//
-// K ordering of the recurrent product: the MMA K index is free as long as A and B agree.  K block r (64 slots = one
-// 128-byte swizzled row) is [h1 of units 32r..32r+31 | h2 of the same units], i.e. exactly what CTA r produces, so a
-// CTA's contribution to a part's operand tile is ONE contiguous 2 KB region (16 sequences x 128 bytes).
+// logit spread 2).  Layer 0 may take (hi, lo) planes and three MMAs (x_lo.W_hi + x_hi.W_lo + x_hi.W_hi).  The output
+// planes are always the scaled split (they ARE the recurrent operand); a consumer that treats them as (hi, lo) in a
+// three-term product (the head, or a terms = 3 layer) loses only the x2 . W_lo term, 2^-17 relative.
 //
 // Algorithmic work per (sequence, frame, direction): FLOPs 2 * 512 * (D + 128); HBM bytes 2 * 2 * D8 (x planes read,
 // shared by both directions through L2) + 512 (y planes written).
@@ -45,21 +53,25 @@ using namespace tc;
 
 constexpr int FC = 4;                       // CTAs per cluster
 constexpr int FU = kHidden / FC;            // hidden units per CTA (32)
-constexpr int FPN = 32;                     // sequences per part (MMA N); one pointwise warpgroup per part
-constexpr int FMAXP = 4;                    // parts per work item (128 sequences per cluster)
-constexpr int F_PW_WARPS = 4 * FMAXP;       // pointwise warps: warp w owns TMEM lane quarter w & 3 (8 units x 4 gates) of part w >> 2
-constexpr int F_W_PROD = F_PW_WARPS;        // TMA producer warp (16)
-constexpr int F_W_MMA = F_W_PROD + 1;       // recurrent-product issuer (+ TMEM owner)
-constexpr int F_W_MMAX = F_W_PROD + 2;      // input-product issuer
-constexpr int F_THREADS = (F_W_PROD + 3) * 32;                          // 19 warps = 608 threads
-constexpr int F_BOX = FPN * 128;            // one x box / one h k-block: 32 rows x 128 bytes = 4 KB
-constexpr int F_HTILE = FC * F_BOX;         // h operand tile of a part: 4 k-blocks = 16 KB
-constexpr int F_SCRATCH = 32 * 16 * 4;      // per pointwise warp: gate transposition scratch [lane 32][16 columns] fp32 = 2 KB (then the h chunk staging)
-constexpr int F_ACC_COL = 0;                // TMEM columns [0, 128): accumulators, part p at 32 p
+constexpr int FPN = 16;                     // sequences per part (MMA N)
+constexpr int FMAXP = 8;                    // parts per work item (128 sequences per cluster)
+constexpr int F_PW_WARPS = 16;              // pointwise warps: warp w owns TMEM lane quarter w & 3 of parts (w >> 2) and (w >> 2) + 4
+constexpr int F_W_PROD = F_PW_WARPS;        // TMA producer of the x tiles
+constexpr int F_W_MMA = F_W_PROD + 1;       // 2 recurrent-product issuers (even / odd parts; the first also owns the TMEM allocation)
+constexpr int F_W_MMAX = F_W_PROD + 3;      // 2 input-product issuers (even / odd parts)
+constexpr int F_W_SEND = F_W_PROD + 5;      // 4 exchange senders (own staging slice -> k-block `rank` of all four CTAs' operand tiles):
+                                            // sender k serves parts k and k + 4, like the pointwise warps (4 k .. 4 k + 3)
+constexpr int F_THREADS = (F_W_PROD + 9) * 32;   // 25 warps = 800 threads
+constexpr int F_BOX = FPN * 128;            // one h k-block of a part: 16 rows x 128 bytes = 2 KB
+constexpr int F_XBOX = 2 * F_BOX;           // one x TMA box: the 32 rows of a PAIR of parts (the input products run on pairs, MMA N = 32)
+constexpr int F_HTILE = FC * F_BOX;         // h operand tile of a part: 4 k-blocks (one per source CTA) = 8 KB
+constexpr int F_STAGING = 2 * FMAXP * F_BOX; // own h slices [step parity][part][16 rows][128 B] (source of the exchange copies): 32 KB
+constexpr int F_SCRATCH = 32 * 16 * 4;      // per pointwise warp: gate transposition scratch [lane 32][16 columns] fp32 = 2 KB (then the y chunk staging)
+constexpr int F_ACC_COL = 0;                // TMEM columns [0, 128): accumulators, part p at 16 p
 constexpr int F_WHH_COL = FMAXP * FPN;      // [128, 256): W_hh, k-step j at 128 + 8 j
 constexpr int F_WIH_COL = F_WHH_COL + 128;  // [256, 256 + 16 nk): W_ih plane a then plane b
 constexpr int F_MAX_STAGES = 16;
-constexpr int F_SMEM_FIXED = FMAXP * F_HTILE + F_PW_WARPS * F_SCRATCH;   // 96 KB
+constexpr int F_SMEM_FIXED = FMAXP * F_HTILE + F_STAGING + F_PW_WARPS * F_SCRATCH;   // 128 KB
 constexpr int F_SMEM_MAX = 232448;          // 227 KB per CTA
 
 struct FusedParams {
@@ -75,28 +87,28 @@ struct FusedParams {
     int kblocks;             // 64-wide k blocks per x plane (TMA boxes per plane)
     int ldw;                 // row pitch of wih planes (elements)
     int terms;               // 2: planes are the scaled (x1, x2) split, plane b of W_ih is W';  3: (hi, lo) planes, plane b is W_lo
-    int y_scaled;            // 1: y planes use the scaled split (feeds a 2-MMA product), 0: plain hi / lo (feeds the head)
     int items_per_dir;       // work items per direction; parts are spread evenly over them
     int stages;              // x ring depth
-    int lag;                 // x-MMAs of a part are issued `lag` part slots after its h-MMAs
     int prefetch_steps;      // L2 prefetch distance of the x tiles, in time steps (0 = off)
-    int flags;               // timing probes (wrong results): 1 no h exchange, 2 no y store, 4 no cell math, 8 no recurrent MMAs, 16 no input MMAs, 32 wait-time table
+    int flags;               // timing probes (wrong results): 2 no y store, 4 no cell math, 8 no recurrent MMAs, 16 no input MMAs, 32 wait-time table, 64 timeline
 };
 
 // wait-time probe (flags & 32, tools/fused_ablate.py): per (CTA, warp, wait tag) cycles spent in non-immediate waits and their count
-constexpr int F_DBG_TAGS = 8, F_DBG_WARPS = 19, F_DBG_MAX_CTAS = 148;
+constexpr int F_DBG_TAGS = 8, F_DBG_WARPS = 25, F_DBG_MAX_CTAS = 148;
 __device__ long long g_fused_dbg[F_DBG_MAX_CTAS * F_DBG_WARPS * F_DBG_TAGS * 2];
 
 // timeline probe (flags & 64): clock64 stamps of one part (part 0 of CTA 0's first item) over F_TRACE_STEPS steps
 constexpr int F_TRACE_S0 = 100, F_TRACE_STEPS = 8;
-__device__ long long g_fused_trace[F_TRACE_STEPS * 16];
+__device__ long long g_fused_trace[F_TRACE_STEPS * 16 + 128];   // + per-part stamps of the two MMA threads over two steps (flag 128)
 
-#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag(bar, parity, tag, wacc)
+#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc)
+#define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc)
+template <bool CLUSTER_ACQUIRE>
 __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc) {
-    if (!wacc && mbar_try_wait(bar, parity)) return;
-    if (wacc && mbar_test_wait(bar, parity)) return;          // probe mode: count every wait that is not already satisfied
+    if (!wacc && (CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) return;
+    if (wacc && !CLUSTER_ACQUIRE && mbar_test_wait(bar, parity)) return;   // probe mode: count every wait that is not already satisfied
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
         if (clock64() - t0 > 4000000000LL) {   // ~2 s
             printf("b200vad lstm_fused: wait timed out (block %d thread %d tag %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, tag, bar,
                    parity);
@@ -106,8 +118,8 @@ __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int
     if (wacc) { wacc[2 * tag] += clock64() - t0; wacc[2 * tag + 1] += 1; }
 }
 
-// The MMA-issuing thread is the serial resource of the kernel (one tcgen05.mma of N = 32 occupies the tensor pipe for 16
-// cycles): descriptors are formed by ONE add on the low word of a per-slot base (the swizzled K-major tile layout makes the
+// The MMA-issuing threads are serial resources (one tcgen05.mma of N = 16 occupies the tensor pipe for 8 cycles):
+// descriptors are formed by ONE add on the low word of a per-slot base (the swizzled K-major tile layout makes the
 // start-address field additive), the loops are fully unrolled (NK, TERMS are template parameters), and no divisions.
 constexpr uint32_t F_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, descriptor version 1, SWIZZLE_128B
 __device__ __forceinline__ uint64_t fdesc(uint32_t lo) {
@@ -119,18 +131,19 @@ __device__ __forceinline__ uint32_t fdesc_lo(uint32_t smem_addr) { return (smem_
 
 // NK > 0: k-steps of the input projection known at compile time (5: 80 mel bins, 4: 60 SincNet channels, 16: 256 LSTM outputs);
 // NK = 0: run-time p.nk / p.terms (any D <= 256; slower issue loop)
-template <int NK, int TERMS>
+template <int NK, int TERMS, bool PROBE>
 __global__ void __cluster_dims__(FC, 1, 1) __launch_bounds__(F_THREADS, 1)
 lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, FusedParams p) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* const smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    const uint32_t h_off = 0;                                  // [part 4][k-block 4][32 rows][128 B]
-    const uint32_t c_off = FMAXP * F_HTILE;                    // scratch [pointwise warp 16][2 KB]
-    const uint32_t x_off = c_off + F_PW_WARPS * F_SCRATCH;     // [stage][plane 2][k-block][32 rows][128 B]
+    const uint32_t h_off = 0;                                  // [part 8][k-block 4][16 rows][128 B]
+    const uint32_t g_off = FMAXP * F_HTILE;                    // staging [step parity 2][part 8][16 rows][128 B]
+    const uint32_t c_off = g_off + F_STAGING;                  // scratch [pointwise warp 16][2 KB]
+    const uint32_t x_off = c_off + F_PW_WARPS * F_SCRATCH;     // [stage][plane 2][k-block][16 rows][128 B]
     const int nk = NK > 0 ? NK : p.nk;
     const int terms = NK > 0 ? TERMS : p.terms;
-    const uint32_t stage_bytes = 2u * p.kblocks * F_BOX;
+    const uint32_t stage_bytes = 2u * p.kblocks * F_XBOX;     // one stage = the x tile of a pair of parts
     const uint32_t bar_base = smem_base + x_off + p.stages * stage_bytes;
     auto bar_x_full = [&](int s) { return bar_base + 8 * s; };
     auto bar_x_empty = [&](int s) { return bar_base + 128 + 8 * s; };
@@ -139,7 +152,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     auto bar_h_ready = [&](int q) { return bar_base + 384 + 8 * q; };
     auto bar_h_free = [&](int q) { return bar_base + 448 + 8 * q; };
     const uint32_t tmem_slot = bar_base + 512;
-    auto bar_x_done = [&](int q) { return bar_base + 560 + 8 * q; };
+    auto bar_slice = [&](int q) { return bar_base + 528 + 8 * q; };
+    auto bar_x_done = [&](int pp) { return bar_base + 592 + 8 * pp; };   // per pair of parts
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -157,27 +171,28 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             mbar_init(bar_acc_free(q), 4);
             mbar_init(bar_h_ready(q), 1);
             mbar_init(bar_h_free(q), FC);
+            mbar_init(bar_slice(q), 4);
             mbar_init(bar_x_done(q), 1);
         }
         mbar_fence_init();
     }
     if (warp == F_W_MMA) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
-    cluster_sync_all();                                       // every CTA's barriers exist before any remote arrive / copy
+    cluster_sync_all();                                       // every CTA's barriers exist before any remote arrive / multicast
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     // wait-time probe: lane 0 of every warp accumulates straight into its row of the global table (probe mode only)
-    long long* const wacc = ((p.flags & 32) && lane == 0 && blockIdx.x < F_DBG_MAX_CTAS)
+    long long* const wacc = (PROBE && (p.flags & 32) && lane == 0 && blockIdx.x < F_DBG_MAX_CTAS)
                                 ? &g_fused_dbg[((size_t)blockIdx.x * F_DBG_WARPS + warp) * (2 * F_DBG_TAGS)] : nullptr;
     if (wacc) {
         for (int i = 0; i < 2 * F_DBG_TAGS; ++i) wacc[i] = 0;
         wacc[0] = -clock64();
     }
-    long long* const trace = ((p.flags & 64) && blockIdx.x == 0 && lane == 0) ? g_fused_trace : nullptr;
+    long long* const trace = (PROBE && (p.flags & 64) && blockIdx.x == 0 && lane == 0) ? g_fused_trace : nullptr;
     // persistent role state (phases carry over from item to item)
-    int xst = 0;                                              // producer / MMA thread: next x ring stage ...
+    int xst = 0;                                              // producer / input-product issuer: next x ring stage ...
     uint32_t xph = 0;                                         // ... and its phase
     uint32_t ph_a = 0, ph_b = 0;                              // per-part phase bits (meaning depends on the role)
     int loaded_dir = -1;
@@ -188,17 +203,16 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int part0 = ii * base_parts + min(ii, rem_parts);
         const int seq0 = part0 * FPN;
         if (nparts == 0) continue;                            // (uniform over the cluster)
+        const bool tr_item = trace && item == cluster_id;
 
         // ---------------- weights of this direction -> tensor memory (pointwise warps; only when the direction changes)
-        if (warp < 16 && loaded_dir != dir) {
-            constexpr int FWG = 4;
+        if (warp < F_PW_WARPS && loaded_dir != dir) {
             const int wg = warp >> 2, g = warp & 3;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16);
-            // TMEM lane 32 g + l holds gate (l & 3) of unit 8 g + (l >> 2) of this CTA: the four gates of a cell sit in four
-            // adjacent lanes of ONE warp, so the pointwise warps transpose gates <-> sequences without leaving the warp
+            // TMEM lane 32 g + l holds gate (l & 3) of unit 8 g + (l >> 2) of this CTA
             const int grow = dir * kGates + (lane & 3) * kHidden + (int)rank * FU + 8 * g + (lane >> 2);   // packed weight row of this TMEM lane
-            // W_hh: k-step j holds plane (j >> 1) & 1 of units 32 (j >> 2) + 16 (j & 1) .. + 15
-            for (int j = wg; j < 16; j += FWG) {
+            // W_hh: k-step j holds plane (j >> 1) & 1 of units 32 (j >> 2) + 16 (j & 1) .. + 15  (K block j >> 2 = source CTA)
+            for (int j = wg; j < 16; j += 4) {
                 const int u0 = 32 * (j >> 2) + 16 * (j & 1), plane = (j >> 1) & 1;
                 const uint4* hp = reinterpret_cast<const uint4*>(p.whh_hi + (size_t)grow * kHidden + u0);
                 const uint4* lp = reinterpret_cast<const uint4*>(p.whh_lo + (size_t)grow * kHidden + u0);
@@ -222,7 +236,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 tmem_st8(lane_addr + F_WHH_COL + 8 * j, r);
             }
             // W_ih: plane a = W_hi, plane b = W_lo (terms 3) or W' (terms 2); k-step j of plane pl at F_WIH_COL + pl * 8 nk + 8 j
-            for (int j = wg; j < 2 * nk; j += FWG) {
+            for (int j = wg; j < 2 * nk; j += 4) {
                 const int pl = j >= nk, kj = pl ? j - nk : j;
                 const uint4* hp = reinterpret_cast<const uint4*>(p.wih_hi + (size_t)grow * p.ldw + 16 * kj);
                 const uint4* lp = reinterpret_cast<const uint4*>(p.wih_lo + (size_t)grow * p.ldw + 16 * kj);
@@ -258,67 +272,80 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             // ===================== TMA producer: x tiles of (step, part) in issue order, multicast to the cluster =====================
             if (elect_one()) {
                 const int nboxes = 2 * p.kblocks;
-                // The x planes stream from HBM (a layer's input does not fit the L2): the ring is only 3-6 stages deep, so the
-                // tiles are pulled into the L2 `pf` steps ahead (cp.async.bulk.prefetch.tensor, no shared memory needed) and
-                // the ring's own loads hit the L2.
-                const int pf = p.prefetch_steps;
+                const int pf = p.prefetch_steps;                                  // optional L2 prefetch distance (steps)
+                const int npairs = (nparts + 1) >> 1;
                 for (int s = 0; s < min(pf, T); ++s) {
                     const int t = dir == 0 ? s : T - 1 - s;
-                    for (int q = 0; q < nparts; ++q)
+                    for (int pp = 0; pp < npairs; ++pp)
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                            tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, t, seq0 + q * FPN);
+                            tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN);
                         }
                 }
                 for (int s = 0; s < T; ++s) {
                     const int t = dir == 0 ? s : T - 1 - s;
                     const int sp = s + pf, tp = dir == 0 ? sp : T - 1 - sp;
-                    for (int q = 0; q < nparts; ++q) {
+                    for (int pp = 0; pp < npairs; ++pp) {
                         if (pf > 0 && sp < T)
                             for (int bi = (int)rank; bi < nboxes; bi += FC) {
                                 const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                                tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, tp, seq0 + q * FPN);
+                                tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, tp, seq0 + pp * 2 * FPN);
                             }
                         FUSED_WAIT(bar_x_empty(xst), xph ^ 1u, 1);                // all 4 CTAs' MMAs are done with this stage
                         mbar_expect_tx(bar_x_full(xst), stage_bytes);
                         const uint32_t dst = smem_base + x_off + xst * stage_bytes;
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                            tma_load_3d_mc(dst + bi * F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + q * FPN, bar_x_full(xst), (uint16_t)0xF);
+                            tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst), (uint16_t)0xF);
                         }
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                     }
                 }
             }
-        } else if (warp == F_W_MMAX) {
-            // ===================== input-product issuer: acc(s, q) = W_ih . x_s, one step ahead of the recurrence =====================
-            // Two threads feed the tensor pipe: tcgen05.mma issue blocks at the pipe's pace and tcgen05.commit drains it, so a
-            // single issuer leaves the pipe idle during every barrier wait; with the input products on their own thread the
-            // recurrent-product thread is free the moment a part's h tile is complete (the critical path of the cluster).
+        } else if (warp == F_W_MMAX || warp == F_W_MMAX + 1) {
+            // ===================== input-product issuers: acc(s, q) = W_ih . x_s, up to one step ahead of the recurrence =====================
+            // (a thread spends ~2/3 of a part slot in barrier waits and commits, not in MMAs: parts are split by parity over two
+            // issuers per product so that the tensor pipe always has the other thread's MMAs queued)
             if (elect_one()) {
-                constexpr uint32_t idesc = idesc_f16(128, FPN);
+                const int me = warp - F_W_MMAX;
+                constexpr uint32_t idesc = idesc_f16(128, 2 * FPN);                 // a pair of parts per MMA: N = 32
                 const uint32_t wa0 = tmem_base + F_WIH_COL, wb0 = wa0 + 8 * nk;
-                const uint32_t plane_lo = (uint32_t)(p.kblocks * F_BOX) >> 4;
-                // ph_b: acc_free phase bits
+                const uint32_t plane_lo = (uint32_t)(p.kblocks * F_XBOX) >> 4;
+                const int npairs = (nparts + 1) >> 1;
+                // ph_b: acc_free phase bits (per part)
                 for (int s = 0; s < T; ++s) {
-                    for (int q = 0; q < nparts; ++q) {
-                        const bool trx = trace && q == 0 && item == cluster_id && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
-                        if (trx) trace[(s - F_TRACE_S0) * 16 + 9] = clock64();
-                        if (s > 0) {                                               // the pointwise warps have read acc(s - 1, q)
-                            FUSED_WAIT(bar_acc_free(q), (ph_b >> q) & 1u, 2);
-                            ph_b ^= 1u << q;
+                    for (int pp = 0; pp < npairs; ++pp) {
+                        if ((pp & 1) != me) {                                      // the other issuer's slot of the x ring
+                            if (++xst == p.stages) { xst = 0; xph ^= 1u; }
+                            continue;
                         }
-                        if (trx) trace[(s - F_TRACE_S0) * 16 + 11] = clock64();
+                        const bool trx = tr_item && pp == 0 && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                        if (trx) trace[(s - F_TRACE_S0) * 16 + 9] = clock64();
+                        long long* const t3 = (PROBE && (p.flags & 128) && tr_item && (s == F_TRACE_S0 || s == F_TRACE_S0 + 1))
+                                                  ? g_fused_trace + F_TRACE_STEPS * 16 + 64 + (s - F_TRACE_S0) * 32 + pp * 8 : nullptr;
+                        if (t3) t3[0] = clock64();
+                        if (s > 0) {                                               // the pointwise warps have read acc(s - 1, .) of both parts
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int q = 2 * pp + h;
+                                if (q < nparts) {
+                                    FUSED_WAIT(bar_acc_free(q), (ph_b >> q) & 1u, 2);
+                                    ph_b ^= 1u << q;
+                                }
+                            }
+                        }
+                        if (t3) t3[1] = clock64();
                         FUSED_WAIT(bar_x_full(xst), xph, 3);
                         tc_fence_after();
+                        if (t3) t3[2] = clock64();
                         if (trx) trace[(s - F_TRACE_S0) * 16 + 13] = clock64();
                         const uint32_t xa = fdesc_lo(smem_base + x_off + xst * stage_bytes), xb = xa + plane_lo;
-                        const uint32_t d = tmem_base + F_ACC_COL + q * FPN;
+                        const uint32_t d = tmem_base + F_ACC_COL + pp * 2 * FPN;
                         if (NK > 0) {
 #pragma unroll
                             for (int j = 0; j < (NK > 0 ? NK : 1); ++j) {
-                                if ((p.flags & 16) && j > 0) break;
-                                const uint32_t off = (uint32_t)((j >> 2) * (F_BOX >> 4) + (j & 3) * 2);
+                                if ((PROBE && (p.flags & 16)) && j > 0) break;
+                                const uint32_t off = (uint32_t)((j >> 2) * (F_XBOX >> 4) + (j & 3) * 2);
                                 if (TERMS == 3) {
                                     mma_f16_ts(d, wa0 + 8 * j, fdesc(xb + off), idesc, j != 0);   // x_lo . W_hi (small terms first)
                                     mma_f16_ts(d, wb0 + 8 * j, fdesc(xa + off), idesc, 1);        // x_hi . W_lo
@@ -328,8 +355,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 mma_f16_ts(d, wa0 + 8 * j, fdesc(xa + off), idesc, 1);            // x1 . W_hi
                             }
                         } else {
-                            for (int j = 0; j < ((p.flags & 16) ? 1 : nk); ++j) {
-                                const uint32_t off = (uint32_t)((j >> 2) * (F_BOX >> 4) + (j & 3) * 2);
+                            for (int j = 0; j < ((PROBE && (p.flags & 16)) ? 1 : nk); ++j) {
+                                const uint32_t off = (uint32_t)((j >> 2) * (F_XBOX >> 4) + (j & 3) * 2);
                                 if (terms == 3) {
                                     mma_f16_ts(d, wa0 + 8 * j, fdesc(xb + off), idesc, j != 0);
                                     mma_f16_ts(d, wb0 + 8 * j, fdesc(xa + off), idesc, 1);
@@ -339,63 +366,104 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 mma_f16_ts(d, wa0 + 8 * j, fdesc(xa + off), idesc, 1);
                             }
                         }
-                        if (trx) trace[(s - F_TRACE_S0) * 16 + 14] = clock64();
                         mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
-                        mma_commit(bar_x_done(q));
+                        mma_commit(bar_x_done(pp));
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
+                        if (t3) t3[3] = clock64();
                         if (trx) trace[(s - F_TRACE_S0) * 16 + 15] = clock64();
                     }
                 }
                 // the accumulators of the last step must be read before the next item overwrites them
                 for (int q = 0; q < nparts; ++q) {
+                    if (((q >> 1) & 1) != me) continue;
                     FUSED_WAIT(bar_acc_free(q), (ph_b >> q) & 1u, 5);
                     ph_b ^= 1u << q;
                 }
             }
-        } else if (warp == F_W_MMA) {
-            // ===================== recurrent-product issuer: acc(s, q) += W_hh . h_{s-1} =====================
+        } else if (warp == F_W_MMA || warp == F_W_MMA + 1) {
+            // ===================== recurrent-product issuers: acc(s, q) += W_hh . h_{s-1} =====================
             if (elect_one()) {
+                const int me = warp - F_W_MMA;
                 constexpr uint32_t idesc = idesc_f16(128, FPN);
                 // ph_a: h_ready phase bits, ph_b: x_done phase bits
-                // h_ready(q) = this thread's arming arrival + the 16 KB of h_s that the 16 pointwise warps of the cluster store
-                // into this CTA's tile (st.async credits the bytes); armed before the step whose pointwise pass produces them
-                if (T > 1 && !(p.flags & 1))
-                    for (int q = 0; q < nparts; ++q) mbar_expect_tx(bar_h_ready(q), FC * F_BOX);
+                // h_ready(q) = this thread's arming arrival + the 8 KB of h_s that the four CTAs' senders store into this CTA's
+                // tile (st.async credits the bytes); armed before the step whose pointwise pass produces them
+                if (T > 1)
+                    for (int q = me; q < nparts; q += 2) mbar_expect_tx(bar_h_ready(q), F_HTILE);
                 for (int s = 0; s < T; ++s) {
-                    for (int q = 0; q < nparts; ++q) {
-                        const bool trh = trace && q == 0 && item == cluster_id && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
-                        FUSED_WAIT(bar_x_done(q), (ph_b >> q) & 1u, 2);            // acc(s, q) holds the complete input product
-                        ph_b ^= 1u << q;
+                    for (int q = me; q < nparts; q += 2) {
+                        const bool trh = tr_item && q == 0 && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                        long long* const t2 = (PROBE && (p.flags & 128) && tr_item && (s == F_TRACE_S0 || s == F_TRACE_S0 + 1))
+                                                  ? g_fused_trace + F_TRACE_STEPS * 16 + (s - F_TRACE_S0) * 32 + q * 4 : nullptr;
+                        if (t2) t2[0] = clock64();
+                        FUSED_WAIT(bar_x_done(q >> 1), (ph_b >> (q >> 1)) & 1u, 2);   // acc(s, q) holds the complete input product of its pair
+                        ph_b ^= 1u << (q >> 1);
+                        if (t2) t2[1] = clock64();
                         if (s > 0) {
                             FUSED_WAIT(bar_h_ready(q), (ph_a >> q) & 1u, 4);       // h_{s-1} of this part: all four slices landed
                             ph_a ^= 1u << q;
-                            if (s < T - 1 && !(p.flags & 1)) mbar_expect_tx(bar_h_ready(q), FC * F_BOX);   // arm for h_s
+                            if (s < T - 1) mbar_expect_tx(bar_h_ready(q), F_HTILE);   // arm for h_s
                             fence_proxy_async();                                   // st.async data -> tensor-core (async proxy) reads
                             tc_fence_after();
+                            if (t2) t2[2] = clock64();
                             if (trh) trace[(s - F_TRACE_S0) * 16 + 0] = clock64();
                             const uint32_t hb = fdesc_lo(smem_base + h_off + q * F_HTILE);
                             const uint32_t d = tmem_base + F_ACC_COL + q * FPN;
-                            if (!(p.flags & 8)) {
+                            if (!(PROBE && (p.flags & 8))) {
 #pragma unroll
                                 for (int jj = 0; jj < 16; ++jj)
                                     mma_f16_ts(d, tmem_base + F_WHH_COL + 8 * jj, fdesc(hb + (uint32_t)((jj >> 2) * (F_BOX >> 4) + (jj & 3) * 2)), idesc, 1);
                             }
                         }
                         mma_commit(bar_acc_ready(q));                              // (s = 0: h_{-1} = 0, the input product alone)
-                        if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA may now overwrite this part's h tile
+                        if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA's copy of this part's h tile may be overwritten
+                        if (t2) t2[3] = clock64();
                         if (trh) trace[(s - F_TRACE_S0) * 16 + 1] = clock64();
                     }
                 }
             }
+        } else if (warp >= F_W_SEND) {
+            // ===================== exchange senders: own 2 KB slice of a part's h_s -> k-block `rank` of all four CTAs' operand tiles =====================
+            // A whole warp per sender: the slice is copied with 16-byte st.async stores (SM-to-SM, a few hundred cycles; the
+            // bytes are credited to the destination's h_ready barrier).  cp.async.bulk took ~3000 cycles per copy through the TMA
+            // unit, and the same stores issued by the pointwise warps stalled them on the ~20 B/clk DSMEM port.
+            uint32_t cta_delta[FC];
+#pragma unroll
+            for (uint32_t d = 0; d < FC; ++d) cta_delta[d] = mapa_shared(smem_base, d) - smem_base;
+            // ph_a: slice phase bits, ph_b: h_free phase bits
+            for (int s = 0; s + 1 < T; ++s) {
+                for (int q = warp - F_W_SEND; q < nparts; q += 4) {
+                    const bool trl = tr_item && q == 0 && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                    if (lane == 0) {
+                        FUSED_WAIT(bar_slice(q), (ph_a >> q) & 1u, 1);            // the part's four pointwise warps have written h_s
+                        if (trl) trace[(s - F_TRACE_S0) * 16 + 7] = clock64();
+                        // every CTA's recurrent MMAs of step s have finished reading the part's tile (it still holds h_{s-1})
+                        FUSED_WAIT(bar_h_free(q), (ph_b >> q) & 1u, 7);
+                    }
+                    ph_a ^= 1u << q;
+                    ph_b ^= 1u << q;
+                    __syncwarp();
+                    const uint32_t src = smem_base + g_off + ((s & 1) * FMAXP + q) * F_BOX + lane * 16;
+                    const uint32_t dst = smem_base + h_off + q * F_HTILE + rank * F_BOX + lane * 16;
+                    const uint32_t bar = bar_h_ready(q);
+#pragma unroll
+                    for (int c = 0; c < F_BOX / 512; ++c) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + c * 512));
+#pragma unroll
+                        for (int d = 0; d < FC; ++d) st_async_v4(dst + c * 512 + cta_delta[d], v, bar + cta_delta[d]);
+                    }
+                    if (trl) trace[(s - F_TRACE_S0) * 16 + 8] = clock64();
+                }
+            }
         } else if ((warp >> 2) < nparts) {
-            // ===================== pointwise warps: warp (q, g) = part q, units 8 g .. 8 g + 7 of this CTA =====================
-            // lane l reads the accumulator row of gate l & 3 of unit 8 g + (l >> 2) for the part's 32 sequences, turns it into
-            // exponentials, and the four lanes of a unit transpose (gate x sequence) through a warp-private scratch, after
-            // which lane l owns all four gates of 8 cells: unit 8 g + (l >> 2), sequences 16 hf + 4 (l & 3) + i.  No other warp
-            // is involved until the h_s slice is complete.
-            const int q = warp >> 2, g = warp & 3;
+            // ===================== pointwise warps: warp (pg, g) = parts pg and pg + 4, units 8 g .. 8 g + 7 of this CTA =====================
+            // lane l reads the accumulator row of gate l & 3 of unit 8 g + (l >> 2) for the part's 16 sequences, turns it into
+            // exponentials, and the four lanes of a unit transpose (gate x sequence) through the warp-private scratch, after
+            // which lane l owns all four gates of 4 cells: unit 8 g + (l >> 2), sequences 4 (l & 3) + i.
+            const int pg = warp >> 2, g = warp & 3;
             const int uu = lane >> 2, jj = lane & 3;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16) + F_ACC_COL + q * FPN;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16) + F_ACC_COL;
             const float bias = __ldg(p.bias + dir * kGates + jj * kHidden + (int)rank * FU + 8 * g + uu);
             unsigned char* const scr = smem_gen + c_off + warp * F_SCRATCH;
             // scratch address of (row, 16-byte chunk c): conflict-free for the row-wise stores and the gate-wise loads
@@ -404,124 +472,89 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             };
             const float s1 = 1.f - kPlaneScale;
             const float L2E2 = 2.f * kLog2e;
-            float cst[8];
+            float cst[2][4];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) cst[b] = 0.f;
-            // h planes of (sequence row, unit 8 g + uu): 2-byte elements of chunk g (h1) / 4 + g (h2) of the 128-byte swizzled row
-            const uint32_t hoff = (uint32_t)uu * 2;
-            uint32_t cta_delta[FC];
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (uint32_t d = 0; d < FC; ++d) cta_delta[d] = mapa_shared(smem_base, d) - smem_base;
-            // ph_a: acc_ready phase bit, ph_b: h_free phase bit
+                for (int b = 0; b < 4; ++b) cst[a][b] = 0.f;
+            // after the staging pass: lane = (sequence row lane & 15, plane lane >> 4), the 16-byte chunk of this warp's 8 units
+            const int yrow = lane & 15;
+            __half* const yplane = (lane >> 4) ? p.y_b : p.y_a;
+            // ph_a: acc_ready phase bits (bit pi)
             for (int s = 0; s < T; ++s) {
                 const int t = dir == 0 ? s : T - 1 - s;
                 const bool exchange = s + 1 < T;
-                FUSED_WAIT(bar_acc_ready(q), ph_a & 1u, 6);
-                ph_a ^= 1u;
-                tc_fence_after();
-                const bool tr_on = trace && warp == 0 && item == cluster_id && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 2] = clock64();
-                float z[32];
-                tmem_ld32(lane_addr, z);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_free(q));                       // the next step's input product may overwrite the accumulator
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 3] = clock64();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) z[j] = fast_ex2(fminf(z[j] + bias, 29.f));
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 4] = clock64();
-                float ev[4][8];                                                    // [gate][cell]: cell 4 hf + i = sequence 16 hf + 4 jj + i
+                for (int pi = 0; pi < 2; ++pi) {
+                    const int q = pg + 4 * pi;
+                    if (q >= nparts) break;
+                    FUSED_WAIT(bar_acc_ready(q), (ph_a >> pi) & 1u, 6);
+                    ph_a ^= 1u << pi;
+                    tc_fence_after();
+                    const bool tr_on = tr_item && warp == 0 && pi == 0 && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
+                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 2] = clock64();
+                    float z[16];
+                    tmem_ld16(lane_addr + q * FPN, z);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_free(q));                   // the next step's input product may overwrite the accumulator
+                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 3] = clock64();
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
+                    for (int j = 0; j < 16; ++j) z[j] = fast_ex2(fminf(z[j] + bias, 29.f));
+                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 4] = clock64();
+                    float ev[4][4];                                                // [gate][cell i]: sequence 4 jj + i
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<float4*>(scr_at(lane, c)) = make_float4(z[16 * hf + 4 * c], z[16 * hf + 4 * c + 1], z[16 * hf + 4 * c + 2], z[16 * hf + 4 * c + 3]);
+                        *reinterpret_cast<float4*>(scr_at(lane, c)) = make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]);
                     __syncwarp();
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const float4 v = *reinterpret_cast<const float4*>(scr_at((lane & ~3) + b, jj));
-                        ev[b][4 * hf] = v.x; ev[b][4 * hf + 1] = v.y; ev[b][4 * hf + 2] = v.z; ev[b][4 * hf + 3] = v.w;
+                        ev[b][0] = v.x; ev[b][1] = v.y; ev[b][2] = v.z; ev[b][3] = v.w;
                     }
                     __syncwarp();
-                }
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 5] = clock64();
-                float hv[8];
-                const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), k2 = pack2(L2E2, L2E2);
+                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 5] = clock64();
+                    float hv[4];
+                    const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), k2 = pack2(L2E2, L2E2);
 #pragma unroll
-                for (int jp = 0; jp < 4; ++jp) {
-                    if (p.flags & 4) { hv[2 * jp] = ev[0][2 * jp] * 1e-3f; hv[2 * jp + 1] = ev[3][2 * jp + 1] * 1e-3f; continue; }
-                    const f32x2 pei = pack2(ev[0][2 * jp], ev[0][2 * jp + 1]), pef = pack2(ev[1][2 * jp], ev[1][2 * jp + 1]);
-                    const f32x2 peg = pack2(ev[2][2 * jp], ev[2][2 * jp + 1]), peo = pack2(ev[3][2 * jp], ev[3][2 * jp + 1]);
-                    // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(eg + 1)) with one reciprocal (lstm_tc.cu)
-                    const f32x2 di = add2(pei, one), df = add2(pef, one), dg = add2(peg, one);
-                    const f32x2 dig = mul2(di, dg);
-                    const f32x2 den = mul2(df, dig);
-                    const f32x2 cn = mul2(fma2(pack2(cst[2 * jp], cst[2 * jp + 1]), dig, mul2(add2(peg, mone), df)), rcp2(den));
-                    unpack2(cn, cst[2 * jp], cst[2 * jp + 1]);
-                    const f32x2 ec = ex2_clamped2(mul2(cn, k2));
-                    const f32x2 h2v = mul2(add2(ec, mone), rcp2(mul2(add2(peo, one), add2(ec, one))));
-                    unpack2(h2v, hv[2 * jp], hv[2 * jp + 1]);
-                }
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 10] = clock64();
-                // h_s planes (scaled split: h1 . W_hi + h2 . W') -> warp-private staging [plane][row 32][16 B] (the scratch is free
-                // again), so that lane = sequence row holds this warp's 16-byte chunk (8 units) of both planes
+                    for (int jp = 0; jp < 2; ++jp) {
+                        if (PROBE && (p.flags & 4)) { hv[2 * jp] = ev[0][2 * jp] * 1e-3f; hv[2 * jp + 1] = ev[3][2 * jp + 1] * 1e-3f; continue; }
+                        const f32x2 pei = pack2(ev[0][2 * jp], ev[0][2 * jp + 1]), pef = pack2(ev[1][2 * jp], ev[1][2 * jp + 1]);
+                        const f32x2 peg = pack2(ev[2][2 * jp], ev[2][2 * jp + 1]), peo = pack2(ev[3][2 * jp], ev[3][2 * jp + 1]);
+                        // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(eg + 1)) with one reciprocal (lstm_tc.cu)
+                        const f32x2 di = add2(pei, one), df = add2(pef, one), dg = add2(peg, one);
+                        const f32x2 dig = mul2(di, dg);
+                        const f32x2 den = mul2(df, dig);
+                        const f32x2 cn = mul2(fma2(pack2(cst[pi][2 * jp], cst[pi][2 * jp + 1]), dig, mul2(add2(peg, mone), df)), rcp2(den));
+                        unpack2(cn, cst[pi][2 * jp], cst[pi][2 * jp + 1]);
+                        const f32x2 ec = ex2_clamped2(mul2(cn, k2));
+                        const f32x2 h2v = mul2(add2(ec, mone), rcp2(mul2(add2(peo, one), add2(ec, one))));
+                        unpack2(h2v, hv[2 * jp], hv[2 * jp + 1]);
+                    }
+                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 10] = clock64();
+                    // h_s planes (scaled split: h1 . W_hi + h2 . W') -> the CTA's staging slice of (step parity, part), in operand
+                    // layout: row = sequence, 2-byte element uu of chunk g (h1) / 4 + g (h2) of the 128-byte swizzled row.  The slice
+                    // of this parity was last read by the copies of step s - 2, which landed before any CTA could start step s.
+                    unsigned char* const stg = smem_gen + g_off + ((s & 1) * FMAXP + q) * F_BOX;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int row = 16 * (c >> 2) + 4 * jj + (c & 3);
-                    __half a1, a2;
-                    split_scaled_f16(hv[c], s1, a1, a2);
-                    *reinterpret_cast<__half*>(scr + row * 16 + hoff) = a1;
-                    *reinterpret_cast<__half*>(scr + 512 + row * 16 + hoff) = a2;
-                }
-                __syncwarp();
-                const uint4 v1 = *reinterpret_cast<const uint4*>(scr + lane * 16);
-                const uint4 v2 = *reinterpret_cast<const uint4*>(scr + 512 + lane * 16);
-                if (exchange) {
-                    // every CTA's recurrent MMAs of this step have finished reading the part's tile (it still holds h_{s-1})
-                    if (lane == 0) FUSED_WAIT(bar_h_free(q), ph_b & 1u, 7);
-                    ph_b ^= 1u;
+                    for (int c = 0; c < 4; ++c) {
+                        const int row = 4 * jj + c;
+                        __half a1, a2;
+                        split_scaled_f16(hv[c], s1, a1, a2);
+                        unsigned char* const rp = stg + row * 128 + uu * 2;
+                        *reinterpret_cast<__half*>(rp + ((g ^ (row & 7)) << 4)) = a1;
+                        *reinterpret_cast<__half*>(rp + (((4 + g) ^ (row & 7)) << 4)) = a2;
+                    }
                     __syncwarp();
-                    if (p.flags & 1) {
-                        if (lane == 0 && g == 0) mbar_arrive(bar_h_ready(q));
-                    } else {
-                        // k-block `rank` of the part's operand tile in all four CTAs: row = lane, chunks g (h1) and 4 + g (h2)
-                        const uint32_t dst = smem_base + h_off + q * F_HTILE + rank * F_BOX + lane * 128;
-                        const uint32_t o1 = (uint32_t)((g ^ (lane & 7)) << 4), o2 = (uint32_t)(((4 + g) ^ (lane & 7)) << 4);
-#pragma unroll
-                        for (int d = 0; d < FC; ++d) {
-                            st_async_v4(dst + o1 + cta_delta[d], v1, bar_h_ready(q) + cta_delta[d]);
-                            st_async_v4(dst + o2 + cta_delta[d], v2, bar_h_ready(q) + cta_delta[d]);
-                        }
-                    }
+                    if (exchange && lane == 0) mbar_arrive(bar_slice(q));          // (release: the sender warp reads the slice with plain loads)
+                    // layer output planes (B, T, 256) = the same chunks: lane = (row, plane), this warp's 16 bytes (8 units)
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + yrow * 128 + ((((lane >> 4) * 4 + g) ^ (yrow & 7)) << 4));
+                    const int b = seq0 + q * FPN + yrow;
+                    if (b < p.B && !(PROBE && (p.flags & 2)))
+                        *reinterpret_cast<uint4*>(yplane + ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 8 * g) = v;
+                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 12] = clock64();
                 }
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 12] = clock64();
-                // layer output planes (B, T, 256)
-                if (!(p.flags & 2)) {
-                    if (p.y_scaled) {
-                        const int b = seq0 + q * FPN + lane;
-                        if (b < p.B) {
-                            const size_t yo = ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 8 * g;
-                            *reinterpret_cast<uint4*>(p.y_a + yo) = v1;
-                            *reinterpret_cast<uint4*>(p.y_b + yo) = v2;
-                        }
-                    } else {
-                        // last layer: plain hi / lo planes for the head's three-term product
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int b = seq0 + q * FPN + 16 * (c >> 2) + 4 * jj + (c & 3);
-                            if (b < p.B) {
-                                __half a1, a2;
-                                split_f16(hv[c], a1, a2);
-                                const size_t yo = ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 8 * g + uu;
-                                p.y_a[yo] = a1;
-                                p.y_b[yo] = a2;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();                                                      // the staging reads are done before the next step's scratch writes
-                if (tr_on) trace[(s - F_TRACE_S0) * 16 + 6] = clock64();
             }
         }
         // item boundary: every role of every CTA is done with this item's tiles and barriers
@@ -531,7 +564,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     if (wacc) wacc[0] += clock64();
     tc_fence_before();
-    cluster_sync_all();                                       // no CTA exits while a peer may still signal or copy into it
+    cluster_sync_all();                                       // no CTA exits while a peer may still signal or multicast into it
     if (warp == F_W_MMA) tmem_dealloc<512>(tmem_base);
 }
 
@@ -541,7 +574,7 @@ static int g_fused_debug = -1, g_fused_lag = -1;
 void lstm_fused_set_debug(int flags, int lag) { g_fused_debug = flags; if (lag >= 0) g_fused_lag = lag; }
 int lstm_fused_read_debug(long long* host, int n) {
     if (n < 0) {                                             // the timeline table (flag 64)
-        B200VAD_CUDA(cudaMemcpyFromSymbol(host, g_fused_trace, sizeof(long long) * std::min(-n, F_TRACE_STEPS * 16)));
+        B200VAD_CUDA(cudaMemcpyFromSymbol(host, g_fused_trace, sizeof(long long) * std::min(-n, F_TRACE_STEPS * 16 + 128)));
         return B200VAD_OK;
     }
     const size_t bytes = sizeof(long long) * (size_t)std::min<long long>(n, (long long)F_DBG_MAX_CTAS * F_DBG_WARPS * F_DBG_TAGS * 2);
@@ -552,15 +585,19 @@ static int g_fused_clusters[64];
 static std::once_flag g_fused_once[64];
 
 typedef void (*FusedKern)(CUtensorMap, CUtensorMap, FusedParams);
-static FusedKern fused_pick(int nk, int terms) {
-    if (nk == 16) return terms == 2 ? lstm_fused_kernel<16, 2> : lstm_fused_kernel<16, 3>;
-    if (nk == 5) return terms == 2 ? lstm_fused_kernel<5, 2> : lstm_fused_kernel<5, 3>;
-    if (nk == 4) return terms == 2 ? lstm_fused_kernel<4, 2> : lstm_fused_kernel<4, 3>;
-    return lstm_fused_kernel<0, 0>;
+static FusedKern fused_pick(int nk, int terms, int probe) {
+    if (probe) {                                             // timing / ablation build of the bench shapes (tools/fused_ablate.py)
+        if (nk == 16 && terms == 2) return lstm_fused_kernel<16, 2, true>;
+        if (nk == 5 && terms == 3) return lstm_fused_kernel<5, 3, true>;
+    }
+    if (nk == 16) return terms == 2 ? lstm_fused_kernel<16, 2, false> : lstm_fused_kernel<16, 3, false>;
+    if (nk == 5) return terms == 2 ? lstm_fused_kernel<5, 2, false> : lstm_fused_kernel<5, 3, false>;
+    if (nk == 4) return terms == 2 ? lstm_fused_kernel<4, 2, false> : lstm_fused_kernel<4, 3, false>;
+    return lstm_fused_kernel<0, 0, false>;
 }
 
 static int fused_smem_bytes(int kblocks, int* stages_out) {
-    const int stage = 2 * kblocks * F_BOX;
+    const int stage = 2 * kblocks * F_XBOX;
     int stages = (F_SMEM_MAX - 1024 - F_SMEM_FIXED - 1024) / stage;
     if (stages > F_MAX_STAGES) stages = F_MAX_STAGES;
     *stages_out = stages;
@@ -573,7 +610,7 @@ static int fused_max_clusters() {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     std::call_once(g_fused_once[dev], [&] {
-        const void* fn = reinterpret_cast<const void*>(lstm_fused_kernel<16, 2>);
+        const void* fn = reinterpret_cast<const void*>(lstm_fused_kernel<16, 2, false>);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(FC * 64);
         cfg.blockDim = dim3(F_THREADS);
@@ -613,19 +650,20 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     }
     FusedParams p;
     p.wih_hi = wih_hi; p.wih_lo = wih_lo; p.whh_hi = whh_hi; p.whh_lo = whh_lo; p.bias = bias; p.y_a = y_a; p.y_b = y_b;
-    p.B = B; p.T = T; p.nk = (D + 15) / 16; p.kblocks = (D + 63) / 64; p.ldw = ldw; p.terms = terms; p.y_scaled = y_scaled;
+    p.B = B; p.T = T; p.nk = (D + 15) / 16; p.kblocks = (D + 63) / 64; p.ldw = ldw; p.terms = terms;
+    (void)y_scaled;                                          // the output planes are always the scaled split (see the header)
     int stages = 0;
     const int smem = fused_smem_bytes(p.kblocks, &stages);
     p.stages = stages;
     if (g_fused_debug < 0) { const char* e = getenv("B200VAD_FUSED_DEBUG"); g_fused_debug = e ? atoi(e) : 0; }
     if (g_fused_lag < 0) { const char* e = getenv("B200VAD_FUSED_LAG"); g_fused_lag = e ? atoi(e) : 2; }
-    p.flags = g_fused_debug; p.lag = g_fused_lag;
+    p.flags = g_fused_debug;
     static int pf_env = -1;
-    if (pf_env < 0) { const char* e = getenv("B200VAD_FUSED_PREFETCH"); pf_env = e ? atoi(e) : 4; }
+    if (pf_env < 0) { const char* e = getenv("B200VAD_FUSED_PREFETCH"); pf_env = e ? atoi(e) : 0; }
     p.prefetch_steps = pf_env;
     const int nc = fused_max_clusters();
-    // work items: parts of 32 sequences, spread evenly over items_per_dir items per direction (<= 4 parts each); choose the
-    // count that minimises waves x step cost (a step costs ~ max(parts, 2) part slots: with fewer parts in flight the
+    // work items: parts of 16 sequences, spread evenly over items_per_dir items per direction (<= 8 parts each); choose the
+    // count that minimises waves x step cost (a step costs ~ max(parts, 4) part slots: with fewer parts in flight the
     // per-part MMA -> pointwise -> exchange chain is the critical path)
     const int P = (B + FPN - 1) / FPN;
     int best_ipd = (P + FMAXP - 1) / FMAXP;
@@ -633,7 +671,7 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     for (int ipd = (P + FMAXP - 1) / FMAXP; ipd <= P; ++ipd) {
         const int maxp = (P + ipd - 1) / ipd;
         const int waves = (2 * ipd + nc - 1) / nc;
-        const double cost = waves * std::max<double>(maxp, 2.0);
+        const double cost = waves * std::max<double>(maxp, 4.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_ipd = ipd; }
         if (maxp == 1) break;
     }
@@ -641,11 +679,11 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     const int grid = FC * std::min(nc, 2 * best_ipd);
     CUtensorMap tm_a, tm_b;
     int rc;
-    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, FPN,
+    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, 2 * FPN,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, FPN,
+    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, 2 * FPN,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    const FusedKern kern = fused_pick(p.nk, terms);
+    const FusedKern kern = fused_pick(p.nk, terms, p.flags != 0);
     if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem))) return rc;
     prof_begin(0, st);
     kern<<<grid, F_THREADS, smem, st>>>(tm_a, tm_b, p);

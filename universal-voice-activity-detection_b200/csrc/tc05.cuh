@@ -44,6 +44,21 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// acquire at cluster scope: orders this thread's later accesses (including TMA issues) after writes that other CTAs of the
+// cluster released before arriving on the barrier
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// generic-proxy writes (any state space) before, async-proxy accesses after
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Bounded wait: a protocol bug must abort the kernel instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
