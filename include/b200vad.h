@@ -79,6 +79,9 @@ B200VAD_API int b200vad_set_lstm_fused_debug(int flags, int lag);
 /* with flag 32 set, the last fused launch leaves per (CTA, warp, wait site) cycle totals / counts of its mbarrier waits in a
  * device table; this copies the first n int64 values [cta 148][warp 18][site 8][cycles, count] to host (synchronises) */
 B200VAD_API int b200vad_lstm_fused_read_debug(long long* host, int n);
+/* the fused kernel's waits are bounded (a protocol bug traps instead of hanging the GPU); the first wait that timed out leaves
+ * {1, block, thread, wait site, barrier address, parity, grid size} in page-locked host memory, readable after the fault */
+B200VAD_API int b200vad_lstm_fused_last_timeout(int* out7);
 /* Split-precision linear layer on the tcgen05 GEMM: c[M,N] = a[M,K] . w[N,K]^T + bias, fp32 in / out, operands
  * split into fp16 (hi, lo) planes in `ws` (K % 8 == 0, N % 128 == 0; weights must fit in shared memory). */
 B200VAD_API int b200vad_linear_split_f32(const float* a, int64_t M, int K, const float* w, int N, const float* bias, int use_w_lo,

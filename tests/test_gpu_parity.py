@@ -204,9 +204,16 @@ def test_segments_sincnet_time_base(dev):
     from src.scripts.predict import get_segments
     g = torch.Generator().manual_seed(5)
     d = (torch.sigmoid(torch.cumsum(torch.randn(6, 293, generator=g), 1)) > 0.5).to(torch.uint8)
+    # without explicit durations a row's duration is what its frame count covers: 270-sample frames, 991-sample receptive field
+    dur = ((293 - 1) * 270 + 991) / 16000.0
     got = get_segments(d.to(dev), None, 0.02, sincnet=True)
     for i in range(6):
-        want = oracle.merge_intervals_with_buffer(oracle.rle_segments_sincnet(d[i].tolist(), 293 * 0.02), 293 * 0.02, 0)
+        want = oracle.merge_intervals_with_buffer(oracle.rle_segments_sincnet(d[i].tolist(), dur), dur, 0)
+        assert [list(x) for x in got[i]] == [list(x) for x in want], i
+    # an explicit per-row duration (what predict_vad passes: samples / 16000)
+    got = get_segments(d.to(dev), None, 0.02, sincnet=True, row_duration=5.0)
+    for i in range(6):
+        want = oracle.merge_intervals_with_buffer(oracle.rle_segments_sincnet(d[i].tolist(), 5.0), 5.0, 0)
         assert [list(x) for x in got[i]] == [list(x) for x in want], i
 
 

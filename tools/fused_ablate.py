@@ -52,15 +52,15 @@ def main():
         lib.b200vad_set_lstm_fused_debug(flags | 32, 3)
         torch.ops.b200vad.lstm_head(x, blob, 4)
         torch.cuda.synchronize()
-        n = 148 * 25 * 16
+        n = 148 * 26 * 16
         buf = (C.c_longlong * n)()
         lib.b200vad_lstm_fused_read_debug(buf, n)
         roles = {"prod": {1: "x_empty"}, "pw": {6: "acc_ready"}, "mmah": {2: "x_done", 4: "h_ready"},
-                 "mmax": {2: "acc_free", 3: "x_full", 5: "drain"}, "send": {1: "slice", 7: "h_free"}}
+                 "mmax": {2: "acc_free", 3: "x_full", 5: "drain"}, "pub": {1: "slice"}, "load": {1: "y_done", 7: "h_free"}}
         print(f"--- wait sites, {label} (last layer launch; cycles per kernel, non-immediate waits)")
         for cta in (0, 1, 5):
-            for warp, role in ((0, "pw"), (5, "pw"), (10, "pw"), (15, "pw"), (16, "prod"), (17, "mmah"), (18, "mmah"), (19, "mmax"), (20, "mmax"), (21, "send"), (24, "send")):
-                base = (cta * 25 + warp) * 16
+            for warp, role in ((0, "pw"), (5, "pw"), (10, "pw"), (15, "pw"), (16, "prod"), (17, "mmah"), (18, "mmah"), (19, "mmax"), (20, "mmax"), (21, "pub"), (24, "pub"), (25, "load")):
+                base = (cta * 26 + warp) * 16
                 tot = buf[base]
                 names = roles[role]
                 parts = [f"{names.get(t, t)} {buf[base + 2 * t] / max(tot, 1) * 100:5.1f}% (n={buf[base + 2 * t + 1]})" for t in range(1, 8) if buf[base + 2 * t + 1]]
@@ -75,8 +75,8 @@ def main():
         torch.cuda.synchronize()
         buf = (C.c_longlong * 128)()
         lib.b200vad_lstm_fused_read_debug(buf, -128)
-        names = ["mma:h_ready", "mma:issued", "pw:acc_rdy", "pw:tmem_ld", "pw:ex2", "pw:xchg", "-", "snd:slice", "snd:sent",
-                 "x:start", "pw:math", "-", "pw:done", "x:xfull", "-", "x:commit"]
+        names = ["mma:h_ready", "mma:issued", "pw:acc_rdy", "pw:tmem_ld", "pw:ex2", "pw:xchg", "ld:y_done", "pub:slice", "pub:done",
+                 "x:start", "pw:math", "ld:issued", "pw:done", "x:xfull", "-", "x:commit"]
         print(f"--- timeline of one part, {label} (cycles after the MMA thread saw h_ready; last column = step period)")
         print("      " + " ".join(f"{n:>12s}" for n in names))
         prev = None

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "b200vad_lstm_fused_clusters": (c_int, []),
     "b200vad_set_lstm_fused_debug": (c_int, [c_int, c_int]),
     "b200vad_lstm_fused_read_debug": (c_int, [c_void_p, c_int]),
+    "b200vad_lstm_fused_last_timeout": (c_int, [c_void_p]),
     "b200vad_set_projection_terms": (c_int, [c_int]),
     "b200vad_set_projection_kernel": (c_int, [c_int]),
     "b200vad_set_head_fused": (c_int, [c_int]),
@@ -105,7 +106,16 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().b200vad_last_error()
-        raise B200VadError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+        extra = ""
+        try:   # a bounded wait of the fused LSTM kernel that timed out leaves its last words in page-locked host memory
+            rec = (C.c_int * 7)()
+            lib().b200vad_lstm_fused_last_timeout(rec)
+            if rec[0]:
+                extra = (f" [lstm_fused wait timed out: block {rec[1]} thread {rec[2]} (warp {rec[2] // 32}) site {rec[3]} "
+                         f"barrier 0x{rec[4] & 0xffffffff:x} parity {rec[5]} grid {rec[6]}]")
+        except Exception:  # noqa: BLE001
+            pass
+        raise B200VadError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}{extra}")
 
 
 _inited = set()

@@ -425,6 +425,10 @@ int b200vad_set_lstm_fused_debug(int flags, int lag) {
     lstm_fused_set_debug(flags, lag);
     return B200VAD_OK;
 }
+int b200vad_lstm_fused_last_timeout(int* out7) {
+    B200VAD_CHECK_ARG(out7, "null buffer");
+    return lstm_fused_last_timeout(out7);
+}
 int b200vad_lstm_fused_read_debug(long long* host, int n) {
     B200VAD_CHECK_ARG(host && n != 0, "null buffer");
     return lstm_fused_read_debug(host, n);

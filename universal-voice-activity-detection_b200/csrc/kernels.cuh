@@ -64,6 +64,7 @@ int lstm_fused_supported(int D);
 int lstm_fused_clusters();
 void lstm_fused_set_debug(int flags, int lag);
 int lstm_fused_read_debug(long long* host, int n);
+int lstm_fused_last_timeout(int* out7);
 int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int D, const __half* wih_hi,
                       const __half* wih_lo, int ldw, const __half* whh_hi, const __half* whh_lo, const float* bias, int terms,
                       __half* y_a, __half* y_b, int y_scaled, cudaStream_t st);
