@@ -50,23 +50,29 @@ LSTM_FLOP = [2 * 2 * 512 * (80 + 128)] + [2 * 2 * 512 * (256 + 128)] * 3        
 LSTM_EXEC = [2 * 2 * 512 * (3 * 80 + 2 * 128)] + [2 * 2 * 512 * 2 * (256 + 128)] * 3
 KERNELS = {
     0: {"name": "lstm_fused_kernel (input projection + recurrence per layer, 4 launches/step)", "bound": "tensor", "tensor": True,
-        # per layer: x planes read 2 x 2 B x D (320 B layer 0, 1024 B layers 1-3) + y planes written 1024 B; no xg tensor
+        # per layer: x planes read 2 x 2 B x D (320 B layer 0, 1024 B layers 1-3) + y planes written 1024 B; no xg tensor.
+        # Measured traffic is 1.45x that: the forward and the backward sweep of a layer each read x (they meet only at T/2, and
+        # 3.3 GB of x per layer does not stay in the 126 MB L2); the y planes are written exactly once (3.33 GB per launch).
         "bytes_per_frame": ((320 + 1024) + 3 * (1024 + 1024)) / 4.0, "flop_per_frame": sum(LSTM_FLOP) / 4.0,
-        "executed_over_algorithmic": sum(LSTM_EXEC) / float(sum(LSTM_FLOP)), "traffic": None},
+        "executed_over_algorithmic": sum(LSTM_EXEC) / float(sum(LSTM_FLOP)),
+        "traffic": (5.384654e9 + 10.010359e9 + 10.006204e9 + 10.014153e9) / 4},
     1: {"name": "gemm_xg_pair_kernel (legacy input projections, b200vad_set_lstm_fused(0) only)", "bound": "hbm", "tensor": True,
         "bytes_per_frame": (3 * (1024 + 4096) + (320 + 4096)) / 4.0, "flop_per_frame": 2 * 1024 * (3 * 256 + 80) / 4.0,
         "executed_over_algorithmic": (3 * 80 + 2 * 3 * 256) / (80 + 3 * 256.0), "traffic": (14.76e9 + 3 * 16.76e9) / 4},
     2: {"name": "head_fused_kernel (head linears + classifier + sigmoid, 1 launch/step)", "bound": "hbm", "tensor": True,
         # y planes 1024 B read -> 4 B probability (the hidden activations stay in shared memory)
         "bytes_per_frame": 1024 + 4, "flop_per_frame": 2 * (256 * 128 + 128 * 128),
-        "executed_over_algorithmic": 3.0, "traffic": 3.38e9},
+        "executed_over_algorithmic": 3.0, "traffic": 3.372568e9},
     3: {"name": "fbank_kernel (frame/window/FFT/mel/log, 1 launch/step)", "bound": "hbm", "tensor": False,
-        "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": 3.12e9},
+        "bytes_per_frame": 640 + 320, "flop_per_frame": 55000, "executed_over_algorithmic": 1.0, "traffic": 3.122489e9},
 }
 MODEL_FLOP_PER_FRAME = 2.884e6
 ALGORITHMIC_BYTES_PER_AUDIO_S = 64.4e3      # 64 000 (waveform f32) + 400 (probabilities)
-# DRAM traffic of one step at the named workload, summed over all launches of the ncu --set full capture (None until captured)
-STEP_TRAFFIC_BYTES = None
+# DRAM traffic of one step at the named workload, summed over all 10 launches of the ncu --set full capture
+# (profiles/r02_ncu_full_summary.md): row_sum 2.10 + fbank 3.12 + 4 x lstm_fused 35.42 + head 3.37 + post 0.02 GB.  The 20.9x over
+# the algorithmic bytes is the five inter-kernel tensors (fbank features, four layers' y planes as two fp16 planes each) that
+# leave the chip once and come back 1-2 times; see DESIGN.md section 4 for why they cannot stay in the 126 MB L2.
+STEP_TRAFFIC_BYTES = 44.029487e9
 WORKLOAD = (f"{ROWS} x {SECONDS:.0f} s synthetic 16 kHz utterances per GPU: fbank + PyanNet2 (4xBiLSTM128, random-init seed 42) "
             "forward + threshold/median(49) + segments")
 

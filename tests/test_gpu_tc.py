@@ -60,6 +60,9 @@ def test_tc_model_matches_warp_mma_and_oracle(dev, B, T):
         ref = o(feats).squeeze(-1)
     blob = b200vad.pack_model(o.model.state_dict(), dev, 80, 4)
     L = b200vad.lib()
+    if L.b200vad_set_impl(1) != 0:
+        L.b200vad_set_impl(2)
+        pytest.skip("the warp-MMA cross-validation kernels are built with `make VALIDATE=1` only")
     try:
         b200vad._lib.check(L.b200vad_set_impl(1), "set_impl")
         p1 = torch.ops.b200vad.lstm_head(feats.to(dev), blob, 4).cpu()

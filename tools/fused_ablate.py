@@ -89,10 +89,10 @@ def main():
         print("(x:* = the input product of the SAME step and part, issued by the MMA thread one round earlier: negative offsets)")
         lib.b200vad_set_lstm_fused_debug(0, lag_default)
 
-    def mma_threads(label):
+    def mma_threads(label, extra=0):
         """stamps of the two MMA-issuing threads of CTA 0 over two consecutive steps (flag 128)"""
         lib.b200vad_set_lstm_fused(1)
-        lib.b200vad_set_lstm_fused_debug(64 | 128, 2)
+        lib.b200vad_set_lstm_fused_debug(64 | 128 | extra, 2)
         torch.ops.b200vad.lstm_head(x, blob, 4)
         torch.cuda.synchronize()
         buf = (C.c_longlong * 256)()
@@ -109,13 +109,34 @@ def main():
         lib.b200vad_set_lstm_fused_debug(0, 2)
 
     lag_default = int(os.environ.get("LAG", "2"))
-    mma_threads("product path")
-    timeline(0, "product path")
-    timeline(8 | 16, "no MMAs")
-    waits(0, "product path")
-    waits(4 | 8 | 16, "no cell math, no MMAs")
+    if os.environ.get("RUNS_ONLY") != "1":
+        mma_threads("product path")
+        timeline(0, "product path")
+        timeline(8 | 16, "no MMAs")
+        waits(0, "product path")
+        waits(4 | 8 | 16, "no cell math, no MMAs")
+    if os.environ.get("RUNS_ONLY") == "3":
+        mma_threads("product path")
+        mma_threads("no x loads", 256)
+        return
+    if os.environ.get("RUNS_ONLY") == "2":
+        run(0, 2, "fused, product path, prefetch " + os.environ.get("B200VAD_FUSED_PREFETCH", "0"))
+        return
     run(0, 2, "legacy (projection + recurrence)", fused=0)
     run(0, 2, "fused, product path")
+    run(64, 2, "probe build, all work")
+    run(64 | 1, 2, "probe build, HALF the exchange bytes (DSMEM port probe)")
+    run(64 | 1 | 8 | 16, 2, "probe build, half exchange, no MMAs")
+    run(64 | 256, 2, "probe build, no x loads")
+    run(64 | 256 | 1, 2, "probe build, no x loads, half exchange")
+    run(64 | 256 | 16, 2, "probe build, no x loads, no input MMAs")
+    run(64 | 256 | 8 | 16, 2, "probe build, no x loads, no MMAs")
+    run(64 | 256 | 8 | 16 | 1, 2, "probe build, no x loads, no MMAs, half exchange")
+    if os.environ.get("RUNS_ONLY") == "1":
+        timeline(0, "product path")
+        timeline(256, "no x loads")
+        timeline(256 | 8 | 16, "no x loads, no MMAs")
+        return
     run(4, 2, "no cell math")
     run(8, 2, "no recurrent MMAs")
     run(16, 2, "no input MMAs")

@@ -381,6 +381,12 @@ int b200vad_profile_collect(int kind, double* total_ms, int* launches) {
 
 int b200vad_set_impl(int impl) {
     B200VAD_CHECK_ARG(impl == 1 || impl == 2, "impl must be 1 (warp-MMA) or 2 (tcgen05)");
+#ifndef B200VAD_VALIDATE
+    if (impl == 1) {
+        set_error("b200vad_set_impl(1): the warp-MMA validation kernels are not in this build (make VALIDATE=1)");
+        return B200VAD_ESTATE;
+    }
+#endif
     g_impl = impl;
     return B200VAD_OK;
 }

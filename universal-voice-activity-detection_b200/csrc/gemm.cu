@@ -12,8 +12,10 @@
 
 namespace b200vad {
 
+// The warp-MMA (mma.sync) GEMM is the cross-validation path of round 1 (b200vad_set_impl(1)); it is compiled only with
+// `make VALIDATE=1` (-DB200VAD_VALIDATE): the product library carries the tcgen05 kernels only.
+#ifdef B200VAD_VALIDATE
 constexpr int GBM = 128, GBK = 32, GPAD = 8, GLD = GBK + GPAD;   // smem row = 40 halves (80 B)
-
 
 template <int BN, int TERMS, typename AT, int VEC>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
             }
         }
 }
+#endif  // B200VAD_VALIDATE
 
 // weights fp32 [N][K] -> fp16 hi / lo [N][Kp], zero padded
 __global__ void split_weights_kernel(const float* __restrict__ w, int N, int K, int Kp, __half* __restrict__ hi,
@@ -209,6 +212,7 @@ int split_weights(const float* w, int N, int K, int Kp, __half* hi, __half* lo, 
     return B200VAD_OK;
 }
 
+#ifdef B200VAD_VALIDATE
 template <int BN, int TERMS, typename AT, int VEC>
 static int launch_one(const GemmArgs& a, cudaStream_t stream) {
     dim3 grid((a.N + BN - 1) / BN, (unsigned)((a.M + GBM - 1) / GBM));
@@ -244,5 +248,12 @@ int gemm_launch(const GemmArgs& a, int a_half, int terms, cudaStream_t stream) {
     if (vec) return wide ? launch_one<128, 1, float, 4>(a, stream) : launch_one<64, 1, float, 4>(a, stream);
     return wide ? launch_one<128, 1, float, 1>(a, stream) : launch_one<64, 1, float, 1>(a, stream);
 }
+
+#else
+int gemm_launch(const GemmArgs&, int, int, cudaStream_t) {
+    set_error("the warp-MMA validation kernels are not in this build (make VALIDATE=1)");
+    return B200VAD_ESTATE;
+}
+#endif
 
 }  // namespace b200vad

@@ -14,6 +14,7 @@
 
 namespace b200vad {
 
+#ifdef B200VAD_VALIDATE   // warp-MMA recurrence: cross-validation path of round 1, `make VALIDATE=1` only
 constexpr int RB = 32;                 // sequences per CTA
 constexpr int RLD = kHidden + 8;       // padded smem row (halves)
 constexpr int RTHREADS = 512;
@@ -144,6 +145,12 @@ int lstm_recurrent_launch(const float* xg, const __half* whh, float* y, int B, i
     B200VAD_LAUNCH_CHECK();
     return B200VAD_OK;
 }
+#else
+int lstm_recurrent_launch(const float*, const __half*, float*, int, int, cudaStream_t) {
+    set_error("the warp-MMA validation kernels are not in this build (make VALIDATE=1)");
+    return B200VAD_ESTATE;
+}
+#endif
 
 // ---------------------------------------------------------------- classifier: sigmoid(wc . z + bc), one warp per row
 __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict__ z, int64_t rows, const float* __restrict__ wc,

@@ -307,6 +307,11 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 tma_prefetch_l2_3d(pl ? &tm_b : &tm_a, kb * 64, tp, seq0 + pp * 2 * FPN);
                             }
                         FUSED_WAIT(bar_x_empty(xst), xph ^ 1u, 1);                // all 4 CTAs' MMAs are done with this stage
+                        if (PROBE && (p.flags & 256)) {                           // timing probe: no x loads (stale tiles)
+                            mbar_arrive(bar_x_full(xst));
+                            if (++xst == p.stages) { xst = 0; xph ^= 1u; }
+                            continue;
+                        }
                         mbar_expect_tx(bar_x_full(xst), stage_bytes);
                         const uint32_t dst = smem_base + x_off + xst * stage_bytes;
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
@@ -404,7 +409,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 // h_ready(q) = this thread's arming arrival + the 8 KB of h_s that the four CTAs' senders store into this CTA's
                 // tile (st.async credits the bytes); armed before the step whose pointwise pass produces them
                 if (T > 1)
-                    for (int q = me; q < nparts; q += 2) mbar_expect_tx(bar_h_ready(q), F_HTILE);
+                    for (int q = me; q < nparts; q += 2) mbar_expect_tx(bar_h_ready(q), (PROBE && (p.flags & 1)) ? F_HTILE / 2 : F_HTILE);
                 for (int s = 0; s < T; ++s) {
                     for (int q = me; q < nparts; q += 2) {
                         const bool trh = tr_item && q == 0 && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
@@ -417,7 +422,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         if (s > 0) {
                             FUSED_WAIT(bar_h_ready(q), (ph_a >> q) & 1u, 4);       // h_{s-1} of this part: all four slices landed
                             ph_a ^= 1u << q;
-                            if (s < T - 1) mbar_expect_tx(bar_h_ready(q), F_HTILE);   // arm for h_s
+                            if (s < T - 1) mbar_expect_tx(bar_h_ready(q), (PROBE && (p.flags & 1)) ? F_HTILE / 2 : F_HTILE);   // arm for h_s
                             fence_proxy_async();                                   // st.async data -> tensor-core (async proxy) reads
                             tc_fence_after();
                             if (t2) t2[2] = clock64();
@@ -463,11 +468,20 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     const uint32_t bar = bar_h_ready(q);
 #pragma unroll
                     for (int c = 0; c < F_BOX / 512; ++c) {
+                        if (PROBE && (p.flags & 1) && c >= F_BOX / 1024) break;   // timing probe: half the exchange bytes
                         uint4 v;
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + c * 512));
+                        // the three peers over DSMEM; the own copy is a plain shared-memory store (it does not take the SM-to-SM port)
 #pragma unroll
-                        for (int d = 0; d < FC; ++d) st_async_v4(dst + c * 512 + cta_delta[d], v, bar + cta_delta[d]);
+                        for (uint32_t d = 1; d < FC; ++d) {
+                            const uint32_t peer = (rank + d) & (FC - 1);
+                            st_async_v4(dst + c * 512 + cta_delta[peer], v, bar + cta_delta[peer]);
+                        }
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * 512), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                     }
+                    fence_proxy_async();                                           // own copy: generic stores before the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_complete_tx(bar, (PROBE && (p.flags & 1)) ? F_BOX / 2 : F_BOX);
                     if (trl) trace[(s - F_TRACE_S0) * 16 + 8] = clock64();
                 }
             }

@@ -327,7 +327,11 @@ int lstm_tc_launch(const float* xg, const __half* whh, __half* y_hi, __half* y_l
     if (parts < 0) { const char* e = getenv("B200VAD_LSTM_PARTS"); parts = (e && atoi(e) == 2) ? 2 : LPARTS_DEFAULT; }
     const int nb_env = g_lstm_tile;
     // 16 sequences per CTA while that still fits one wave of CTAs (latency mode), else 64 (throughput mode)
-    const int sms = 148;
+    int sms = 148, dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        sms = 148;
+    }
     int nb = ((B + 15) / 16) * 2 <= sms ? 16 : 64;
     if (nb_env == 16 || nb_env == 64) nb = nb_env;
     const uint32_t lpn = nb == 16 ? 16 : XBLK / parts;

@@ -290,6 +290,10 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, uint4 v, uint3
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
 }
+// credits `bytes` to the transaction count of an mbarrier of this CTA (the counterpart of expect_tx for data written with plain stores)
+__device__ __forceinline__ void mbar_complete_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
