@@ -379,6 +379,9 @@ def main():
     # step's copies are inside the timed region (pipeline fill and drain included).
     sess = b200vad.HostSession(blob, 4, N_SAMPLES, chunk_rows=hi - lo, device=local)
     outs = [{}, {}]
+    # host-driven loop: the segment lists of all steps are exchanged ONCE, at the drain inside the timed region (a per-step
+    # exchange makes the host wait for the slowest rank every step, and the next H2D cannot be submitted meanwhile)
+    e2e_gatherer = b200vad.SegmentGatherer(device=dev, every=0)
 
     def e2e_finish(slot):
         res = sess.wait(slot, outs[slot])
@@ -387,7 +390,7 @@ def main():
             # host segment list of this step -> device -> side-stream gather (completed one step later / at the drain)
             sd = seg.to(dev, non_blocking=True)
             off = torch.tensor([0, sd.shape[0]], dtype=torch.int64, device=dev)
-            gatherer.push(sd, off, row_base=lo)
+            e2e_gatherer.push(sd, off, row_base=lo)
         return seg
 
     def e2e_run(k):
@@ -397,7 +400,7 @@ def main():
             if i >= 1:
                 nseg = e2e_finish((i - 1) & 1).shape[0]
         nseg = e2e_finish((k - 1) & 1).shape[0]
-        gatherer.drain()
+        e2e_gatherer.drain()
         return nseg
 
     e2e_run(2)
@@ -414,6 +417,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item() / steps
     e2e_value = hours_step_global / (e2e_ms / 1e3)
+    # device timeline of the last two batches of this rank (CUDA events inside the session): where an e2e step goes
+    st = [sess.slot_times(sl) for sl in (0, 1)]
+    slot_ms = {"h2d": round(sum(x[1] - x[0] for x in st) / 2, 3), "h2d_to_compute_gap": round(sum(x[2] - x[1] for x in st) / 2, 3),
+               "compute": round(sum(x[3] - x[2] for x in st) / 2, 3), "d2h": round(sum(x[4] - x[3] for x in st) / 2, 3),
+               "note": "rank 0, mean of the last two batches: H2D copy, wait for the compute stream, device path, D2H of the results"}
     clocks = sampler.stop() if rank == 0 else None
     # informational: the same loop fed 16-bit PCM (half the PCIe bytes, identical results -- tests/test_gpu_edges.py); the
     # headline e2e above keeps the reference's float32 waveforms
@@ -516,6 +524,7 @@ def main():
                     "h2d_ceiling_gbs": {"per_gpu_min": h2d_min, "aggregate": h2d_sum,
                                         "note": "copy-only H2D of the same pinned batch, all ranks at once, CUDA events"},
                     "h2d_floor_ms_per_step": h2d_floor_ms, "e2e_over_h2d_floor": h2d_floor_ms / e2e_ms,
+                    "slot_ms": slot_ms,
                     "pcm16_input": {"value": hours_step_global / (pcm_ms / 1e3), "ms_per_step": pcm_ms, "h2d_bytes_per_step": h2d // 2,
                                     "note": "same API fed int16 PCM host waveforms (b200vad_session_submit_host_i16); informational"},
                     "api": "b200vad_session_submit_host / b200vad_session_wait, 2 steps in flight (pinned host waveforms -> host decisions + segments)"},

@@ -446,24 +446,46 @@ def main():
     import tempfile
     import src.scripts.predict_sincnet as PS
 
-    class _Cut(_Obj):
+    # lhotse's cut objects: a functional stand-in.  ``truncate`` is the package's restatement of lhotse's MonoCut.truncate
+    # (b200vad/manifests.py: parity with lhotse itself unpinned, lhotse is absent); everything the REFERENCE does with the
+    # truncated cuts (:391-467: counters, text folding, first-supervision rewrite, ids, empty-cut drop) runs for real and
+    # the CutSet it would write is captured.
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "universal-voice-activity-detection_b200"))
+    from b200vad import manifests as _mf
+
+    class _Cut:
+        def __init__(self, d):
+            self._d = {k: v for k, v in d.items() if k != "supervisions"}
+            self.id, self.start, self.duration = d["id"], d["start"], d["duration"]
+            self.supervisions = [types.SimpleNamespace(**dict({"text": None}, **x)) for x in d["supervisions"]]
+
+        def to_dict(self):
+            return dict(self._d, id=self.id, start=self.start, duration=self.duration,
+                        supervisions=[{k: v for k, v in vars(x).items()} for x in self.supervisions])
+
         def index_supervisions(self, **k):
             return None
 
-        def truncate(self, **k):
-            return _Cut({"id": self["id"], "start": k.get("offset", 0), "duration": k.get("duration", 0), "supervisions": []})
+        def truncate(self, offset=0.0, duration=None, keep_excessive_supervisions=True, _supervisions_index=None):
+            return _Cut(_mf.truncate_cut(self.to_dict(), offset=offset, duration=duration,
+                                         keep_excessive_supervisions=keep_excessive_supervisions))
 
         def with_id(self, i):
-            self["id"] = i
+            self.id = i
             return self
 
+    captured = {}
+
     class _CutSet:
+        def __init__(self, cuts):
+            self.cuts = cuts
+
         @classmethod
         def from_cuts(cls, cuts):
-            return cls()
+            return cls(list(cuts))
 
         def to_file(self, path):
-            pass
+            captured["cuts"] = [c.to_dict() for c in self.cuts]
 
     def _load_s(path):
         with gzip.open(path, "rt") as f:
@@ -504,7 +526,8 @@ def main():
             for k, v in sorig.items():
                 setattr(PS, k, v)
             meta["get_new_cuts_sincnet"][tag] = {"buffer": buffer, "split": split, "fa": log["fa"], "md": log["md"],
-                                                 "intervals": log["split"] if split else log["merged"], "report": buf.getvalue()}
+                                                 "intervals": log["split"] if split else log["merged"], "report": buf.getvalue(),
+                                                 "cuts": captured.pop("cuts")}
 
     # ---- a6 glue: binary_cross_entropy / interpolate (src/utils/loss.py:29-89), evaluated (and discarded) by _common_step
     from src.utils.loss import binary_cross_entropy

@@ -158,6 +158,7 @@ def test_get_new_cuts_matches_reference(dev, ref, golden_dir, tmp_path):
 def test_get_new_cuts_sincnet_matches_reference(dev, ref, golden_dir, tmp_path):
     """The drop-in predict_sincnet.get_new_cuts against the reference's own run (predict_sincnet.py:294-489)."""
     from src.scripts.predict_sincnet import get_new_cuts, get_timestamp_from_sample_boundary
+    from b200vad import manifests
     z, meta = ref
     g = meta["get_new_cuts_sincnet"]
     torch.save(torch.from_numpy(z["gnc_sincnet_preds"].astype(np.int64)), str(tmp_path / "preds.pt"))
@@ -178,6 +179,15 @@ def test_get_new_cuts_sincnet_matches_reference(dev, ref, golden_dir, tmp_path):
         assert fa == want["fa"] and md == want["md"], tag
         for key, name in (("detection_error", "Detection Error Rate"), ("false_alarm", "False Alarm Rate"), ("missed_detection", "Missed Detection Rate")):
             assert float(out[key]) == report_value(want["report"], name), (tag, key)
+        # the CutSet output (:391-467): the reference's own loop produced want["cuts"] and the counters of its report
+        assert [json.loads(json.dumps(c)) for c in out["cuts"]] == want["cuts"], tag
+        written = [json.loads(json.dumps(c)) for c in manifests.load_manifest(out["output_path"])]
+        assert written == want["cuts"], tag
+        for key, name in (("total_sup", "Total Supervisions"), ("in_sup", "Supervisions in new cuts"),
+                          ("unique_sup", "Unique Supervisions in new cuts"), ("not_in_sup", "Supervisions not in new cuts"),
+                          ("exceed_sup", "Supervisions exceeding new cuts"), ("in_multiple_sup", "Supervisions in multiple new cuts"),
+                          ("empty_cut", "Empty cuts")):
+            assert out["stats"][key] == int(report_value(want["report"], name + ":")), (tag, key)
     for (a, b, d), w in zip(z["sinc_ts_in"].tolist(), z["sinc_ts_out"].tolist()):
         assert list(get_timestamp_from_sample_boundary(a, b, d)) == w
 

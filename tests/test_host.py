@@ -160,8 +160,16 @@ def _gatherer_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import b200vad
-    g = b200vad.SegmentGatherer(device="cpu")
-    outs = []
+    res = []
+    for every in (1, 0, 2):                                    # per push / one exchange at the drain / every 2 pushes
+        res.append(_gatherer_run(b200vad, rank, world, every))
+    assert res[0] == res[1] == res[2]
+    q.put((rank, res[0]))
+    dist.destroy_process_group()
+
+
+def _gatherer_run(b200vad, rank, world, every):
+    g = b200vad.SegmentGatherer(device="cpu", every=every)
     for step in range(3):
         lo, hi = b200vad.shard_range(10, rank, world)
         n = (hi - lo) * (rank + 1) if step != 1 else 0       # an empty batch on every rank in the middle
@@ -170,9 +178,7 @@ def _gatherer_worker(rank, world, port, q):
             seg[i] = torch.tensor([i % (hi - lo), 100 * step + i, 100 * step + i + 5], dtype=torch.int32)
         seg_off = torch.tensor([0, n], dtype=torch.int64)
         g.push(seg, seg_off, row_base=lo)
-    outs = [o.tolist() for o in g.drain()]
-    q.put((rank, outs))
-    dist.destroy_process_group()
+    return [o.tolist() for o in g.drain()]
 
 
 def test_segment_gatherer_world2_gloo():
@@ -213,3 +219,45 @@ def test_gather_segments_world2_gloo():
         assert p.exitcode == 0
     want = [[i, 10 * i, 10 * i + 5] for i in range(5)] + [[i, 10 * i, 10 * i + 5] for i in range(5, 10)] * 2
     assert res[0] == res[1] == want
+
+
+def test_new_cuts_from_windows_match_reference_loop():
+    """The CutSet output of predict_sincnet.py:391-467 (host code): given the intervals the reference's own run produced, the
+    truncated cuts, their folded supervisions and the report counters equal what the reference's loop produced
+    (tests/golden/make_reference_golden.py; lhotse's MonoCut.truncate itself is restated, see b200vad/manifests.py)."""
+    import json
+    from b200vad import manifests
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    meta = json.load(open(os.path.join(gdir, "reference_golden.json")))["get_new_cuts_sincnet"]
+    cuts = manifests.load_manifest(os.path.join(gdir, "manifests", "cuts_sincnet.jsonl.gz"))
+    for tag in ("b0", "b1_split"):
+        want = meta[tag]
+        sup_dict = {s["id"]: [s["start"], s["duration"], s.get("text"), 0] for c in cuts for s in c["supervisions"]}
+        stats = {"empty_cut": 0, "in_sup": 0, "exceed_sup": 0, "in_multiple_sup": 0, "sup_set": set()}
+        got = []
+        for cut, windows in zip(cuts, want["intervals"]):
+            got += manifests.new_cuts_from_windows(cut, [tuple(w) for w in windows], sup_dict, stats)
+        assert [json.loads(json.dumps(c)) for c in got] == want["cuts"], tag
+        rep = {l.split(":")[0]: l.split(":")[1].strip() for l in want["report"].splitlines() if ":" in l}
+        assert stats["in_sup"] == int(rep["Supervisions in new cuts"]) and stats["empty_cut"] == int(rep["Empty cuts"])
+        assert stats["exceed_sup"] == int(rep["Supervisions exceeding new cuts"])
+        assert stats["in_multiple_sup"] == int(rep["Supervisions in multiple new cuts"])
+        assert len(stats["sup_set"]) == int(rep["Unique Supervisions in new cuts"])
+
+
+def test_truncate_cut_semantics():
+    """MonoCut.truncate as lhotse documents it: overlapping supervisions kept untrimmed and shifted, touching ones dropped,
+    the span clipped to the cut, boundaries on the sample grid."""
+    from b200vad import manifests
+    rec = manifests.recording("r", 160000)
+    sups = [manifests.supervision("a", "r", 0.5, 1.0, "A"), manifests.supervision("b", "r", 2.0, 1.0, "B"),
+            manifests.supervision("c", "r", 4.0, 3.0, "C")]
+    cut = manifests.mono_cut("r-0", rec, sups)
+    t = manifests.truncate_cut(cut, offset=1.0, duration=3.0, new_id="x")
+    assert (t["id"], t["start"], t["duration"]) == ("x", 1.0, 3.0)
+    assert [(s["id"], s["start"], s["duration"]) for s in t["supervisions"]] == [("a", -0.5, 1.0), ("b", 1.0, 1.0)]   # c only touches
+    t = manifests.truncate_cut(cut, offset=1.0, duration=3.0, keep_excessive_supervisions=False, new_id="x")
+    assert [s["id"] for s in t["supervisions"]] == ["b"]
+    t = manifests.truncate_cut(cut, offset=9.0, duration=5.0, new_id="y")
+    assert t["start"] == 9.0 and t["duration"] == 1.0 and t["supervisions"] == []
+    assert manifests.add_durations(0.1, 0.2, sampling_rate=16000) == 0.3

@@ -94,6 +94,109 @@ def mono_cut(cut_id: str, rec: Dict[str, Any], supervisions: Sequence[Dict[str, 
                      "supervisions": [dict(s) for s in supervisions], "recording": dict(rec), "type": "MonoCut"})
 
 
+# ---------------------------------------------------------------- cut truncation (the CutSet output of predict_sincnet.py)
+# lhotse is the reference's dependency for this (requirements.txt:13, an editable checkout, no version pinned) and is absent
+# here, so ``MonoCut.truncate`` is restated from its published behaviour (lhotse/cut/mono.py ``MonoCut.truncate``,
+# lhotse/utils.py ``add_durations`` / ``compute_num_samples`` / ``overlaps``, lhotse/supervision.py ``with_offset``):
+# parity with lhotse itself is UNPINNED; the reference's own loop around it (predict_sincnet.py:391-467) is pinned by
+# tests/golden/make_reference_golden.py, which runs that loop with this function standing in for lhotse's.
+def _num_samples(duration: float, sampling_rate: int) -> int:
+    """lhotse ``compute_num_samples``: round(duration * sr, 8 digits) to the nearest sample, halves up."""
+    from decimal import ROUND_HALF_UP, Decimal
+    return int(Decimal(round(duration * sampling_rate, ndigits=8)).quantize(0, rounding=ROUND_HALF_UP))
+
+
+def add_durations(*durations: float, sampling_rate: int) -> float:
+    """lhotse ``add_durations``: the sum taken on the sample grid (no floating-point drift in cut boundaries)."""
+    return sum(_num_samples(d, sampling_rate) for d in durations) / sampling_rate
+
+
+def _overlaps(a_start: float, a_end: float, b_start: float, b_end: float) -> bool:
+    """lhotse ``overlaps``: open-interval overlap; touching ends do not count."""
+    from math import isclose
+    return a_start < b_end and b_start < a_end and not isclose(a_start, b_end) and not isclose(b_start, a_end)
+
+
+def truncate_cut(cut: Dict[str, Any], offset: float = 0.0, duration: Optional[float] = None,
+                 keep_excessive_supervisions: bool = True, new_id: Optional[str] = None) -> Manifest:
+    """``MonoCut.truncate(offset=, duration=, keep_excessive_supervisions=)``: a cut over [offset, offset + duration) of
+    ``cut`` (clipped to its end), with the supervisions that overlap the new span (``keep_excessive_supervisions=True``) or lie
+    inside it (False), shifted by -offset and NOT trimmed, sorted by start.  lhotse assigns a random uuid unless the caller
+    renames the cut (the reference always does, ``.with_id``): pass ``new_id``."""
+    assert offset >= 0, f"offset must be non-negative (got {offset})"
+    sr = int(cut.get("recording", {}).get("sampling_rate", 16000)) if isinstance(cut.get("recording"), dict) else 16000
+    new_start = max(add_durations(cut["start"], offset, sampling_rate=sr), 0)
+    until = offset + (duration if duration is not None else cut["duration"])
+    new_duration = add_durations(until, -offset, sampling_rate=sr)
+    assert new_duration > 0.0, f"truncated cut would have non-positive duration {new_duration}"
+    past_end = (new_start + new_duration) - (cut["start"] + cut["duration"])
+    if past_end > 0:
+        new_duration -= past_end
+    sups = []
+    for sup in cut.get("supervisions", []):
+        sh = dict(sup)
+        sh["start"] = add_durations(sup["start"], -offset, sampling_rate=sr)
+        s_end = sh["start"] + sh["duration"]
+        if keep_excessive_supervisions:
+            keep = _overlaps(0.0, new_duration, sh["start"], s_end)
+        else:   # lhotse ``overspans``: the new span covers the supervision entirely
+            keep = 0.0 <= sh["start"] and s_end <= new_duration
+        if keep:
+            sups.append(sh)
+    sups.sort(key=lambda x: x["start"])
+    out = Manifest({k: v for k, v in cut.items()})
+    out["id"] = new_id if new_id is not None else f"{cut['id']}-truncated"
+    out["start"], out["duration"], out["supervisions"] = new_start, new_duration, sups
+    return out
+
+
+def new_cuts_from_windows(cut: Dict[str, Any], windows: Sequence[Tuple[float, float]], sup_dict: Dict[str, list],
+                          stats: Dict[str, Any], alignment: Optional[Dict[str, Any]] = None,
+                          recording_id: Optional[str] = None) -> List[Manifest]:
+    """predict_sincnet.py:391-462 for one recording: one new cut per predicted window (id ``<cut id>-<j>``) carrying ONE
+    supervision -- the earliest overlapping one, re-based to start 0 and stretched to the cut's duration, its text the
+    space-joined texts of every overlapping supervision (or, with a word-alignment file, the words that lie inside the
+    window).  Windows without supervisions are counted in ``stats['empty_cut']`` and dropped.  ``sup_dict`` maps supervision
+    id -> [start, duration, text, times_seen] over the whole manifest and ``stats`` accumulates the reference's counters
+    (``in_sup``, ``exceed_sup``, ``in_multiple_sup``, ``empty_cut``, ``sup_set``)."""
+    out = []
+    for j, (abs_start, abs_end) in enumerate(windows):
+        nc = truncate_cut(cut, offset=abs_start, duration=abs_end - abs_start, keep_excessive_supervisions=True,
+                          new_id=f"{cut['id']}-{j}")
+        sups = nc["supervisions"]
+        if len(sups) == 0:
+            stats["empty_cut"] += 1
+            continue
+        for sup in sups:
+            if sup["id"] in sup_dict:
+                ent = sup_dict[sup["id"]]
+                stats["in_sup"] += 1
+                stats["sup_set"].add(sup["id"])
+                ent[3] += 1
+                cut_start, sup_start = round(nc["start"], 2), round(ent[0], 2)
+                cut_end, sup_end = round(nc["start"] + nc["duration"], 2), round(ent[0] + ent[1], 2)
+                if cut_start > sup_start or cut_end < sup_end:
+                    stats["exceed_sup"] += 1
+                if ent[3] > 1:
+                    stats["in_multiple_sup"] += 1
+        text = "".join(s["text"] + " " for s in sups if s.get("text") is not None).strip()
+        if alignment is not None:
+            words = ""
+            for sup in alignment[recording_id]["supervisions"]:
+                if sup["start"] + sup["duration"] >= abs_start and abs_end >= sup["start"]:       # is_overlap (:543-544)
+                    for al in sup["alignment"]:
+                        if sup["start"] + al["start"] >= abs_start and sup["start"] + al["end"] <= abs_end:
+                            words += al["word"] + " "
+                elif sup["start"] > abs_end:
+                    break
+            text = words.strip()
+        first = dict(sups[0])
+        first["start"], first["duration"], first["text"] = 0, nc["duration"], text
+        nc["supervisions"] = [first]
+        out.append(nc)
+    return out
+
+
 def intervals_to_supervisions(recording_ids: Sequence[str], intervals_per_rec: Sequence[Sequence[Tuple[float, float]]],
                               tag: str = "vad") -> List[Manifest]:
     """Predicted speech intervals -> SupervisionSegment lines (what a downstream lhotse pipeline consumes)."""

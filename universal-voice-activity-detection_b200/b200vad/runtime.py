@@ -203,9 +203,15 @@ class SegmentGatherer:
     count.  The only host reads are the 8-byte total of a batch that has already finished and the world-size counts, both on
     the side stream.  ``drain()`` completes what is pending and returns the list of gathered (S, 3) int32 tensors (global
     utterance ids in column 0), one per push, identical on every rank.  Single-process use (no process group) skips the
-    collectives.  NCCL on CUDA tensors; the CPU test runs the same code over gloo with ``device="cpu"``."""
+    collectives.  NCCL on CUDA tensors; the CPU test runs the same code over gloo with ``device="cpu"``.
 
-    def __init__(self, device=None, group=None):
+    ``every=k`` batches k pushes into one exchange (SURVEY 8e's "every k batches"); ``every=0`` defers everything to
+    ``drain()`` -- one exchange per corpus shard, which is what a host-driven loop wants: completing a push reads the counts
+    on the host, so with one exchange per step every rank waits for the slowest rank once per step and the host cannot
+    submit the next copy meanwhile (measured at 2 GPUs through the host session: 49.6 ms per step, against 39.1 ms
+    without the per-step rendezvous)."""
+
+    def __init__(self, device=None, group=None, every: int = 1):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = group
@@ -215,15 +221,62 @@ class SegmentGatherer:
         self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.pending = None
         self.results = []
+        self.every = int(every)
+        self.batch = []
 
     def push(self, seg: torch.Tensor, seg_off: torch.Tensor, row_base: int = 0):
         ev = None
         if self.cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
+        if self.every != 1:
+            self.batch.append((seg, seg_off, int(row_base), ev))
+            if self.every > 1 and len(self.batch) >= self.every:
+                self._flush_batch()
+            return
         prev, self.pending = self.pending, (seg, seg_off, int(row_base), ev)
         if prev is not None:
             self._complete(prev)
+
+    def _flush_batch(self):
+        """One exchange for all batched pushes: compact each, concatenate, gather once, split back per push and rank."""
+        items, self.batch = self.batch, []
+        if not items:
+            return
+        ctx = torch.cuda.stream(self.side) if self.cuda else _NullCtx()
+        with ctx:
+            locs = []
+            for seg, seg_off, row_base, ev in items:
+                if self.cuda:
+                    self.side.wait_event(ev)
+                n = int(seg_off[-1].item())
+                loc = seg[:n].clone()
+                loc[:, 0] += row_base
+                locs.append(loc)
+                if self.cuda:
+                    seg.record_stream(self.side)
+                    seg_off.record_stream(self.side)
+            if self.world == 1:
+                self.results.extend(locs)
+                return
+            dev = items[0][0].device
+            k = len(locs)
+            cnt = torch.tensor([l.shape[0] for l in locs], dtype=torch.int64, device=dev)
+            counts = torch.empty(self.world * k, dtype=torch.int64, device=dev)
+            self.dist.all_gather_into_tensor(counts, cnt, group=self.group)
+            counts = counts.reshape(self.world, k).tolist()
+            m = max(max(sum(c) for c in counts), 1)
+            padded = torch.zeros((m, 3), dtype=torch.int32, device=dev)
+            mine = torch.cat(locs, dim=0)
+            padded[: mine.shape[0]] = mine
+            out = torch.empty((self.world * m, 3), dtype=torch.int32, device=dev)
+            self.dist.all_gather_into_tensor(out, padded, group=self.group)
+            for j in range(k):
+                parts = []
+                for r in range(self.world):
+                    o = r * m + sum(counts[r][:j])
+                    parts.append(out[o: o + counts[r][j]])
+                self.results.append(torch.cat(parts, dim=0))
 
     def _complete(self, item):
         seg, seg_off, row_base, ev = item
@@ -252,6 +305,7 @@ class SegmentGatherer:
                 seg_off.record_stream(self.side)
 
     def drain(self):
+        self._flush_batch()
         if self.pending is not None:
             prev, self.pending = self.pending, None
             self._complete(prev)
