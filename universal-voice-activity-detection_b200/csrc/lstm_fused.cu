@@ -111,15 +111,27 @@ __device__ long long g_fused_trace[F_TRACE_STEPS * 16 + 128];   // + per-part st
 // last words of a wait that timed out: written to page-locked HOST memory (readable after the context died), see lstm_fused_last_timeout
 __device__ volatile int* g_fused_err_host = nullptr;
 
+// h exchange variant: 0 = st.async (every 16-byte store credits the destination's h_ready barrier), 1 = plain remote
+// shared-memory stores + ONE release arrive per destination CTA
+#ifndef FUSED_EXCH_PLAIN
+#define FUSED_EXCH_PLAIN 0
+#endif
 #define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc)
 #define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc)
 template <bool CLUSTER_ACQUIRE>
 __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc) {
     if (!wacc && (CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) return;
     if (wacc && !CLUSTER_ACQUIRE && mbar_test_wait(bar, parity)) return;   // probe mode: count every wait that is not already satisfied
-    const long long t0 = clock64();
-    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s
+    const long long t0 = wacc ? clock64() : 0;
+    // suspended in hardware for up to 20 us per try (the default limit is ~80 cycles: see mbar_try_wait_hint); the time
+    // bound (~2 s) is checked once per 64 tries
+    unsigned tries = 0;
+    long long tb = 0;
+    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait_hint(bar, parity, 20000u))) {
+        if ((++tries & 63u) != 0) continue;
+        const long long now = clock64();
+        if (tb == 0) tb = now;
+        if (now - tb > 4000000000LL) {   // ~2 s
             volatile int* e = g_fused_err_host;
             if (e && e[0] == 0) {                              // (racy on purpose: any one record is enough)
                 e[0] = 1; e[1] = (int)blockIdx.x; e[2] = (int)threadIdx.x; e[3] = tag; e[4] = (int)bar; e[5] = (int)parity; e[6] = (int)gridDim.x;
@@ -184,7 +196,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         for (int q = 0; q < FMAXP; ++q) {
             mbar_init(bar_acc_ready(q), 1);
             mbar_init(bar_acc_free(q), 4);
-            mbar_init(bar_h_ready(q), 1);
+            mbar_init(bar_h_ready(q), FUSED_EXCH_PLAIN ? FC : 1);
             mbar_init(bar_h_free(q), FC);
             mbar_init(bar_slice(q), 4);
             mbar_init(bar_x_done(q), 1);
@@ -408,7 +420,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 // ph_a: h_ready phase bits, ph_b: x_done phase bits
                 // h_ready(q) = this thread's arming arrival + the 8 KB of h_s that the four CTAs' senders store into this CTA's
                 // tile (st.async credits the bytes); armed before the step whose pointwise pass produces them
-                if (T > 1)
+                if (T > 1 && !FUSED_EXCH_PLAIN)
                     for (int q = me; q < nparts; q += 2) mbar_expect_tx(bar_h_ready(q), (PROBE && (p.flags & 1)) ? F_HTILE / 2 : F_HTILE);
                 for (int s = 0; s < T; ++s) {
                     for (int q = me; q < nparts; q += 2) {
@@ -420,9 +432,13 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         ph_b ^= 1u << (q >> 1);
                         if (t2) t2[1] = clock64();
                         if (s > 0) {
+#if FUSED_EXCH_PLAIN
+                            FUSED_WAIT_CLUSTER(bar_h_ready(q), (ph_a >> q) & 1u, 4);   // four senders' release arrives (cluster scope)
+#else
                             FUSED_WAIT(bar_h_ready(q), (ph_a >> q) & 1u, 4);       // h_{s-1} of this part: all four slices landed
+#endif
                             ph_a ^= 1u << q;
-                            if (s < T - 1) mbar_expect_tx(bar_h_ready(q), (PROBE && (p.flags & 1)) ? F_HTILE / 2 : F_HTILE);   // arm for h_s
+                            if (!FUSED_EXCH_PLAIN && s < T - 1) mbar_expect_tx(bar_h_ready(q), (PROBE && (p.flags & 1)) ? F_HTILE / 2 : F_HTILE);   // arm for h_s
                             fence_proxy_async();                                   // st.async data -> tensor-core (async proxy) reads
                             tc_fence_after();
                             if (t2) t2[2] = clock64();
@@ -447,9 +463,9 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             // A whole warp per sender: the slice is copied with 16-byte st.async stores (SM-to-SM, a few hundred cycles; the
             // bytes are credited to the destination's h_ready barrier).  cp.async.bulk took ~3000 cycles per copy through the TMA
             // unit, and the same stores issued by the pointwise warps stalled them on the ~20 B/clk DSMEM port.
-            uint32_t cta_delta[FC];
+            uint32_t cta_delta[FC];                                            // [d]: address offset of CTA (rank + d) & 3 (static indices only)
 #pragma unroll
-            for (uint32_t d = 0; d < FC; ++d) cta_delta[d] = mapa_shared(smem_base, d) - smem_base;
+            for (uint32_t d = 0; d < FC; ++d) cta_delta[d] = mapa_shared(smem_base, (rank + d) & (FC - 1)) - smem_base;
             // ph_a: slice phase bits, ph_b: h_free phase bits
             for (int s = 0; s + 1 < T; ++s) {
                 for (int q = warp - F_W_SEND; q < nparts; q += 4) {
@@ -474,14 +490,27 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         // the three peers over DSMEM; the own copy is a plain shared-memory store (it does not take the SM-to-SM port)
 #pragma unroll
                         for (uint32_t d = 1; d < FC; ++d) {
-                            const uint32_t peer = (rank + d) & (FC - 1);
-                            st_async_v4(dst + c * 512 + cta_delta[peer], v, bar + cta_delta[peer]);
+#if FUSED_EXCH_PLAIN
+                            asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * 512 + cta_delta[d]),
+                                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+                            st_async_v4(dst + c * 512 + cta_delta[d], v, bar + cta_delta[d]);
+#endif
                         }
                         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * 512), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                     }
+#if FUSED_EXCH_PLAIN
+                    // every lane: its generic stores (local and remote) before the tensor cores' async-proxy reads, and before
+                    // lane 0's release arrives at cluster scope
+                    fence_proxy_async_all();
+                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    __syncwarp();
+                    if (lane < FC) mbar_arrive_cluster(mapa_shared(bar, (uint32_t)lane));   // one arrive per destination CTA (own included)
+#else
                     fence_proxy_async();                                           // own copy: generic stores before the tensor core's reads
                     __syncwarp();
                     if (lane == 0) mbar_complete_tx(bar, (PROBE && (p.flags & 1)) ? F_BOX / 2 : F_BOX);
+#endif
                     if (trl) trace[(s - F_TRACE_S0) * 16 + 8] = clock64();
                 }
             }
