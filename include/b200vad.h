@@ -65,11 +65,16 @@ B200VAD_API int b200vad_set_head_fused(int on);
 /* Sequences per CTA of the tcgen05 recurrence: 0 = automatic (16 while the batch fits one wave of CTAs -- low latency
  * for small batches / streaming --, else 64), or 16 / 64 to force one (validation, tuning). */
 B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);
-/* LSTM layers with input width <= 256 (PyanNet2.py:95,170): 1 (default) = one fused kernel per layer on 4-CTA clusters
+/* LSTM layers with input width <= 256 (PyanNet2.py:95,170): 1 = one fused kernel per layer on 4-CTA clusters
  * (input projection + recurrence, W_ih and W_hh as two fp16 planes each in tensor memory, no intermediate in HBM);
+ * 2 = the same layer with every product issued as tcgen05.mma.cta_group::2 by CTA pairs (each CTA holds half of every
+ * operand tile: half the x and h traffic per SM; bit-identical to 1);
  * 0 = the round-1 path (projection GEMM -> xg in HBM -> recurrence with a single-plane W_hh), kept for cross-validation
- * and for wider inputs (768-dim SSL features on layer 0). */
+ * and for wider inputs (768-dim SSL features on layer 0).  The environment variable B200VAD_LSTM_MODE sets the initial mode. */
 B200VAD_API int b200vad_set_lstm_fused(int on);
+/* tuning bits of mode 2 (default 3): 1 = the input-product issuers yield to a recurrent product that is ready to issue,
+ * 2 = two sets of h operand tiles (no "tile free" hand-shake on the per-step chain).  Results do not depend on them. */
+B200VAD_API int b200vad_set_lstm_pair_opt(int opt);
 /* clusters of 4 CTAs of the fused LSTM kernel that are co-resident on the current device (cudaOccupancyMaxActiveClusters) */
 B200VAD_API int b200vad_lstm_fused_clusters(void);
 /* timing probes of the fused kernel for tools/fused_ablate.py (RESULTS ARE WRONG while flags != 0): 1 no h exchange, 2 no

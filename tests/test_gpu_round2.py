@@ -212,3 +212,35 @@ def test_reference_golden_trained_spreads(dev, golden_dir):
     near = np.abs(ref_p - 0.5) <= util.NEAR_THR
     for b, t in zip(*np.nonzero(d.numpy()[..., 0] != ref_d)):
         assert near[b, max(0, t - 24): t + 25].any(), (b, t)
+
+
+@pytest.mark.parametrize("shape", [(16, 8, 80, 1), (3, 100, 80, 2), (130, 40, 60, 4), (300, 30, 256, 2), (1000, 64, 80, 4)])
+def test_lstm_layer_modes_agree(dev, shape):
+    """The three LSTM layer paths (b200vad_set_lstm_fused): 2 = fused layer on CTA pairs (cta_group::2 MMAs, csrc/lstm_pair.cu) must be
+    BIT-identical to 1 = fused layer (csrc/lstm_fused.cu) -- same products in the same order, only the operand tiles are split
+    over two CTAs --, with both tuning variants of the pair kernel; and both stay within the tolerance of the oracle."""
+    import b200vad
+    B, T, D, L = shape
+    lib = b200vad.lib()
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    x = (torch.randn(B, T, D, generator=g) * 3 - 5) if D == 80 else torch.randn(B, T, D, generator=g)
+    o = util.make_oracle("PyanNet2", {"encoding_dim": D, "lstm": {"hidden_size": 128, "num_layers": L, "bidirectional": True,
+                                                                  "monolithic": True, "dropout": 0.0}}, spread=True, feats=x, sigma=2.0)
+    with torch.no_grad():
+        ref = o(x).squeeze(-1)
+    blob = b200vad.pack_model(o.model.state_dict(), dev, D, L)
+    xd = x.to(dev)
+    out = {}
+    try:
+        for mode, opt in ((1, 3), (2, 0), (2, 3)):
+            lib.b200vad_set_lstm_fused(mode)
+            lib.b200vad_set_lstm_pair_opt(opt)
+            out[(mode, opt)] = torch.ops.b200vad.lstm_head(xd, blob, L).cpu()
+    finally:
+        lib.b200vad_set_lstm_fused(1)
+        lib.b200vad_set_lstm_pair_opt(3)
+    assert torch.equal(out[(2, 0)], out[(1, 3)])
+    assert torch.equal(out[(2, 3)], out[(1, 3)])
+    err = util.prob_err(out[(2, 3)].reshape(ref.shape), ref)
+    print(f"B={B} T={T} D={D} L={L}: pair == fused bit for bit; rel err of p vs oracle {err:.2e}")
+    assert err <= util.PROB_RTOL, err

@@ -1,5 +1,5 @@
 """GPU check of the fused LSTM layer kernel (csrc/lstm_fused.cu): PyanNet2 probabilities through torch.ops.b200vad.lstm_head
-with the fused kernel on / off against a float64 torch reference on the same device, for several (B, T, D, layers, logit spread).
+with the layer kernels (2 = CTA-pair fused, 1 = fused, 0 = projection + recurrence) against a float64 torch reference on the same device, for several (B, T, D, layers, logit spread).
 
     python tools/fused_check.py [quick]
 
@@ -52,7 +52,7 @@ def main():
         blob = b200vad.pack_model({k: v.float() for k, v in m.model.state_dict().items()}, dev, D, L)
         xd = x.to(dev)
         out = {}
-        for fused in (1, 0):
+        for fused in (2, 1, 0):
             lib.b200vad_set_lstm_fused(fused)
             torch.cuda.synchronize()
             t0 = time.time()
@@ -63,9 +63,12 @@ def main():
         r = ref.squeeze(-1)
         e1 = ((out[1][0].reshape(r.shape) - r).abs() / r.abs()).max().item()
         e0 = ((out[0][0].reshape(r.shape) - r).abs() / r.abs()).max().item()
+        e2 = ((out[2][0].reshape(r.shape) - r).abs() / r.abs()).max().item()
         d = (out[1][0] - out[0][0]).abs().max().item()
-        print(f"B={B} T={T} D={D} L={L} sigma={sigma}: fused err {e1:.3e} ({out[1][1]*1e3:.1f} ms)  legacy err {e0:.3e} ({out[0][1]*1e3:.1f} ms)  "
-              f"|fused-legacy| {d:.3e}  p in [{r.min().item():.4f}, {r.max().item():.4f}]", flush=True)
+        d2 = (out[2][0] - out[1][0]).abs().max().item()
+        print(f"B={B} T={T} D={D} L={L} sigma={sigma}: pair err {e2:.3e} ({out[2][1]*1e3:.1f} ms)  fused err {e1:.3e} ({out[1][1]*1e3:.1f} ms)  "
+              f"legacy err {e0:.3e} ({out[0][1]*1e3:.1f} ms)  |fused-legacy| {d:.3e}  |pair-fused| {d2:.3e}  "
+              f"p in [{r.min().item():.4f}, {r.max().item():.4f}]", flush=True)
 
 
 if __name__ == "__main__":

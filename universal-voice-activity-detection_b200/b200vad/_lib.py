@@ -28,6 +28,7 @@ PROTOTYPES = {
     "b200vad_set_impl": (c_int, [c_int]),
     "b200vad_set_lstm_tile": (c_int, [c_int]),
     "b200vad_set_lstm_fused": (c_int, [c_int]),
+    "b200vad_set_lstm_pair_opt": (c_int, [c_int]),
     "b200vad_lstm_fused_clusters": (c_int, []),
     "b200vad_set_lstm_fused_debug": (c_int, [c_int, c_int]),
     "b200vad_lstm_fused_read_debug": (c_int, [c_void_p, c_int]),

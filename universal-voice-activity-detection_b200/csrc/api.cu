@@ -66,7 +66,16 @@ int set_max_dynamic_smem(const void* func, int bytes) {
 static int g_impl = 2;        // 2 = tcgen05 kernels (default), 1 = warp-MMA kernels (validation only)
 static int g_proj_terms = 2;  // fp16 products per k-step of the layer >= 1 input projections: 2 (default) or 3 (validation)
 static int g_head_fused = 1;   // head as one kernel (z1 planes stay on chip, default) or as two launches (validation)
-static int g_lstm_fused = 1;   // layers with D <= 256: 1 = fused projection + recurrence on 4-CTA clusters (default), 0 = projection GEMM -> xg -> recurrence
+// layers with D <= 256: 2 = fused projection + recurrence with cta_group::2 MMAs on CTA pairs (lstm_pair.cu), 1 = the same on
+// single-CTA MMAs (lstm_fused.cu), 0 = projection GEMM -> xg -> recurrence; -1 = not chosen yet (B200VAD_LSTM_MODE, else the default)
+static int g_lstm_fused = -1;
+static int lstm_mode() {
+    if (g_lstm_fused < 0) {
+        const char* e = getenv("B200VAD_LSTM_MODE");
+        g_lstm_fused = (e && atoi(e) >= 0 && atoi(e) <= 2) ? atoi(e) : 1;
+    }
+    return g_lstm_fused;
+}
 static int g_proj_kernel = 2;  // input projections with K <= 256: 0 = gemm_ts_kernel<3>, 1 = gemm_xg2_kernel, 2 = gemm_xg_pair_kernel (default)
 static int num_sms_cached() {
     static int n = 0;
@@ -221,13 +230,18 @@ static int model_forward(const void* packed, int D, int L, const float* x, const
             int* const sync = reinterpret_cast<int*>(x_hi);
             const size_t sync_bytes = 2 * align_up(sizeof(__half) * D8 * rows);
             const int terms = (l > 0 && g_proj_terms == 2) ? 2 : 3;
-            if (g_lstm_fused && lstm_fused_supported(lo.D)) {
+            if (lstm_mode() && lstm_fused_supported(lo.D)) {
                 // one kernel per layer: W_ih and W_hh (two planes each) resident in tensor memory, no xg round trip
                 __half* fyh = reinterpret_cast<__half*>(outbuf);
                 __half* fyl = fyh + rows * 2 * kHidden;
                 const int fscaled = (g_proj_terms == 2 && l + 1 < L) ? 1 : 0;
-                if ((rc = lstm_fused_launch(a_hi, a_lo, lda, bc, (int)T, lo.D, w_hi, w_lo, lo.Kp, reinterpret_cast<const __half*>(pk + lo.whh),
-                                            reinterpret_cast<const __half*>(pk + lo.whh_lo), bias, terms, fyh, fyl, fscaled, st))) return rc;
+                if (lstm_mode() == 2)
+                    rc = lstm_pair_launch(a_hi, a_lo, lda, bc, (int)T, lo.D, w_hi, w_lo, lo.Kp, reinterpret_cast<const __half*>(pk + lo.whh),
+                                          reinterpret_cast<const __half*>(pk + lo.whh_lo), bias, terms, fyh, fyl, st);
+                else
+                    rc = lstm_fused_launch(a_hi, a_lo, lda, bc, (int)T, lo.D, w_hi, w_lo, lo.Kp, reinterpret_cast<const __half*>(pk + lo.whh),
+                                           reinterpret_cast<const __half*>(pk + lo.whh_lo), bias, terms, fyh, fyl, fscaled, st);
+                if (rc) return rc;
                 a_hi = fyh; a_lo = fyl; lda = 2 * kHidden;
                 outbuf = (outbuf == buf0) ? buf1 : buf0;
                 continue;
@@ -423,7 +437,13 @@ int b200vad_set_projection_kernel(int which) {
 }
 
 int b200vad_set_lstm_fused(int on) {
-    g_lstm_fused = on ? 1 : 0;
+    B200VAD_CHECK_ARG(on >= 0 && on <= 2, "mode must be 0 (projection + recurrence kernels), 1 (fused layer kernel) or 2 (fused, CTA-pair MMAs)");
+    g_lstm_fused = on;
+    return B200VAD_OK;
+}
+int b200vad_set_lstm_pair_opt(int opt) {
+    B200VAD_CHECK_ARG(opt >= 0 && opt <= 127, "opt is a bit mask: 1 input products yield to recurrent ones, 2 double-buffered h tiles; 4, 8, 32 are timing probes (wrong results)");
+    lstm_pair_set_opt(opt);
     return B200VAD_OK;
 }
 int b200vad_lstm_fused_clusters(void) { return lstm_fused_clusters(); }
@@ -433,10 +453,13 @@ int b200vad_set_lstm_fused_debug(int flags, int lag) {
 }
 int b200vad_lstm_fused_last_timeout(int* out7) {
     B200VAD_CHECK_ARG(out7, "null buffer");
-    return lstm_fused_last_timeout(out7);
+    int rc = lstm_fused_last_timeout(out7);
+    if (rc == B200VAD_OK && out7[0] == 0) rc = lstm_pair_last_timeout(out7);
+    return rc;
 }
 int b200vad_lstm_fused_read_debug(long long* host, int n) {
     B200VAD_CHECK_ARG(host && n != 0, "null buffer");
+    if (n > 0 && lstm_mode() == 2) return lstm_pair_read_debug(host, n);
     return lstm_fused_read_debug(host, n);
 }
 int b200vad_set_lstm_tile(int sequences_per_cta) {

@@ -68,6 +68,13 @@ int lstm_fused_last_timeout(int* out7);
 int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int D, const __half* wih_hi,
                       const __half* wih_lo, int ldw, const __half* whh_hi, const __half* whh_lo, const float* bias, int terms,
                       __half* y_a, __half* y_b, int y_scaled, cudaStream_t st);
+// the same layer with every product issued as cta_group::2 MMAs by CTA pairs (lstm_pair.cu): half the operand traffic per CTA
+int lstm_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, int T, int D, const __half* wih_hi,
+                     const __half* wih_lo, int ldw, const __half* whh_hi, const __half* whh_lo, const float* bias, int terms,
+                     __half* y_a, __half* y_b, cudaStream_t st);
+int lstm_pair_last_timeout(int* out7);
+void lstm_pair_set_opt(int opt);
+int lstm_pair_read_debug(long long* host, int n);
 int add_bias(const float* a, const float* b, float* out, int n, cudaStream_t stream);
 int threshold_median_launch(const float* prob, int B, int64_t T, float thr, int kernel, void* out, int elem,
                             int32_t* near_count, float near_tol, cudaStream_t stream);

@@ -242,6 +242,12 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// same with an explicit cluster mask (clusters of two pairs: either the issuing pair's two CTAs or all four)
+__device__ __forceinline__ void mma_commit_pair_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
