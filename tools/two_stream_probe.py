@@ -26,7 +26,10 @@ def main():
     blob = b200vad.pack_model(model.model.state_dict(), dev, 80, 4)
     wav = synth.noise_batch(rows, 128000, seed=1234, pin=True).to(dev)
     ref = None
-    for nstreams, prio in ((1, None), (2, None), (2, (-1, 0)), (3, None)):
+    configs = ((1, None), (2, None), (2, (-1, 0)), (3, None))
+    if len(sys.argv) > 3:                                   # e.g. "2": only the two-stream configuration (stress runs)
+        configs = tuple((int(c), None) for c in sys.argv[3].split(","))
+    for nstreams, prio in configs:
         if prio:
             streams = [torch.cuda.Stream(priority=p) for p in prio]
         else:

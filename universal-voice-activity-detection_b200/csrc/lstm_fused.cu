@@ -97,6 +97,7 @@ struct FusedParams {
     int items_per_dir;       // work items per direction; parts are spread evenly over them
     int stages;              // x ring depth
     int prefetch_steps;      // L2 prefetch distance of the x tiles, in time steps (0 = off)
+    int variant;             // B200VAD_FUSED_VARIANT (robustness experiments): 1 cluster-wide sync after the weight load, 2 local commits in multicast form
     int flags;               // timing probes (wrong results): 2 no y store, 4 no cell math, 8 no recurrent MMAs, 16 no input MMAs, 32 wait-time table, 64 timeline
 };
 
@@ -292,7 +293,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
         loaded_dir = dir;
         tc_fence_before();
-        __syncthreads();
+        if (p.variant & 1) cluster_sync_all(); else __syncthreads();
         tc_fence_after();
 
         if (warp == F_W_PROD) {
@@ -399,7 +400,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                             }
                         }
                         mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
-                        mma_commit(bar_x_done(pp));
+                        if (p.variant & 2) mma_commit_mc(bar_x_done(pp), (uint16_t)(1u << rank)); else mma_commit(bar_x_done(pp));
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                         if (t3) t3[3] = clock64();
                         if (trx) trace[(s - F_TRACE_S0) * 16 + 15] = clock64();
@@ -451,7 +452,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                     mma_f16_ts(d, tmem_base + F_WHH_COL + 8 * jj, fdesc(hb + (uint32_t)((jj >> 2) * (F_BOX >> 4) + (jj & 3) * 2)), idesc, 1);
                             }
                         }
-                        mma_commit(bar_acc_ready(q));                              // (s = 0: h_{-1} = 0, the input product alone)
+                        if (p.variant & 2) mma_commit_mc(bar_acc_ready(q), (uint16_t)(1u << rank)); else mma_commit(bar_acc_ready(q));   // (s = 0: h_{-1} = 0, the input product alone)
                         if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA's copy of this part's h tile may be overwritten
                         if (t2) t2[3] = clock64();
                         if (trh) trace[(s - F_TRACE_S0) * 16 + 1] = clock64();
@@ -620,6 +621,15 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         cluster_sync_all();
         tc_fence_after();
     }
+    // The last `stages` multicast commits onto x_empty are not consumed by any load: they must have LANDED in this CTA before it
+    // exits (an arrive that finds its target CTA gone is a fault, and after the exit the shared memory may belong to another
+    // kernel's CTA when a second stream keeps the SM busy).  The producer waits for them exactly as if it were to refill the ring.
+    if (warp == F_W_PROD && elect_one()) {
+        for (int k = 0; k < p.stages; ++k) {
+            FUSED_WAIT(bar_x_empty(xst), xph ^ 1u, 1);
+            if (++xst == p.stages) { xst = 0; xph ^= 1u; }
+        }
+    }
     if (wacc) wacc[0] += clock64();
     tc_fence_before();
     cluster_sync_all();                                       // no CTA exits while a peer may still signal or multicast into it
@@ -725,6 +735,9 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     static int pf_env = -1;
     if (pf_env < 0) { const char* e = getenv("B200VAD_FUSED_PREFETCH"); pf_env = e ? atoi(e) : 0; }
     p.prefetch_steps = pf_env;
+    static int variant_env = -1;
+    if (variant_env < 0) { const char* e = getenv("B200VAD_FUSED_VARIANT"); variant_env = e ? atoi(e) : 0; }
+    p.variant = variant_env;
     const int nc = fused_max_clusters();
     // work items: parts of 16 sequences, spread evenly over items_per_dir items per direction (<= 8 parts each); choose the
     // count that minimises waves x step cost (a step costs ~ max(parts, 4) part slots: with fewer parts in flight the
@@ -732,10 +745,12 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     const int P = (B + FPN - 1) / FPN;
     int best_ipd = (P + FMAXP - 1) / FMAXP;
     double best_cost = 1e30;
+    static double part_floor = -1.0;
+    if (part_floor < 0) { const char* e = getenv("B200VAD_FUSED_PART_FLOOR"); part_floor = e ? atof(e) : 4.0; }
     for (int ipd = (P + FMAXP - 1) / FMAXP; ipd <= P; ++ipd) {
         const int maxp = (P + ipd - 1) / ipd;
         const int waves = (2 * ipd + nc - 1) / nc;
-        const double cost = waves * std::max<double>(maxp, 4.0);
+        const double cost = waves * std::max<double>(maxp, part_floor);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_ipd = ipd; }
         if (maxp == 1) break;
     }

@@ -545,6 +545,13 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         cluster_sync_all();
         tc_fence_after();
     }
+    // drain: the last `stages` multicast commits onto this CTA's x_empty barriers must have landed before it exits (lstm_fused.cu)
+    if (warp == P_W_PROD && elect_one()) {
+        for (int k = 0; k < p.stages; ++k) {
+            PWAIT(bar_x_empty(xst), xph ^ 1u, 1);
+            if (++xst == p.stages) { xst = 0; xph ^= 1u; }
+        }
+    }
     if (wacc) wacc[0] += clock64();
     tc_fence_before();
     cluster_sync_all();
