@@ -740,17 +740,18 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     p.variant = variant_env;
     const int nc = fused_max_clusters();
     // work items: parts of 16 sequences, spread evenly over items_per_dir items per direction (<= 8 parts each); choose the
-    // count that minimises waves x step cost (a step costs ~ max(parts, 4) part slots: with fewer parts in flight the
-    // per-part MMA -> pointwise -> exchange chain is the critical path)
+    // count that minimises waves x step time.  Measured step time (us) of a cluster with n parts in flight (256 x 500: n = 1,
+    // 2, 4; 4096 x 800: n = 8; in between interpolated): one part runs at the unloaded latency of the chain MMA -> pointwise ->
+    // exchange, eight parts overlap 3.3 chains' worth.  Small batches (streaming: 256 sequences) therefore spread over all 33
+    // clusters with one part each (0.80 instead of 1.21 ms per layer), large ones keep eight parts per cluster.
+    static const double kStepUs[FMAXP + 1] = {0.0, 1.60, 1.93, 2.17, 2.41, 2.78, 3.16, 3.53, 3.90};
     const int P = (B + FPN - 1) / FPN;
     int best_ipd = (P + FMAXP - 1) / FMAXP;
     double best_cost = 1e30;
-    static double part_floor = -1.0;
-    if (part_floor < 0) { const char* e = getenv("B200VAD_FUSED_PART_FLOOR"); part_floor = e ? atof(e) : 4.0; }
     for (int ipd = (P + FMAXP - 1) / FMAXP; ipd <= P; ++ipd) {
         const int maxp = (P + ipd - 1) / ipd;
         const int waves = (2 * ipd + nc - 1) / nc;
-        const double cost = waves * std::max<double>(maxp, part_floor);
+        const double cost = waves * kStepUs[maxp];
         if (cost < best_cost - 1e-9) { best_cost = cost; best_ipd = ipd; }
         if (maxp == 1) break;
     }

@@ -642,10 +642,11 @@ int lstm_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, i
     const int P = (B + PPN - 1) / PPN;
     int best_ipd = (P + PMAXP - 1) / PMAXP;
     double best_cost = 1e30;
+    static const double kStepUs[PMAXP + 1] = {0.0, 1.60, 1.93, 2.17, 2.41, 2.78, 3.16, 3.53, 3.90};   // step time by parts in flight (lstm_fused.cu)
     for (int ipd = (P + PMAXP - 1) / PMAXP; ipd <= P; ++ipd) {
         const int maxp = (P + ipd - 1) / ipd;
         const int waves = (2 * ipd + nc - 1) / nc;
-        const double cost = waves * std::max<double>(maxp, 4.0);
+        const double cost = waves * kStepUs[maxp];
         if (cost < best_cost - 1e-9) { best_cost = cost; best_ipd = ipd; }
         if (maxp == 1) break;
     }
