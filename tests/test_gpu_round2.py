@@ -244,3 +244,23 @@ def test_lstm_layer_modes_agree(dev, shape):
     err = util.prob_err(out[(2, 3)].reshape(ref.shape), ref)
     print(f"B={B} T={T} D={D} L={L}: pair == fused bit for bit; rel err of p vs oracle {err:.2e}")
     assert err <= util.PROB_RTOL, err
+
+
+def test_forward_is_bit_reproducible(dev):
+    """the InstanceNorm statistics of the SincNet front-end (and the fbank row means) are accumulated with
+    atomicAdd(double) across CTAs; the partial sums are rounded to a fixed quantum so that the additions are exact and the
+    result does not depend on the order in which CTAs arrive: repeated forwards must be bit-identical."""
+    import b200vad
+    from src.engines import VadModel
+    torch.manual_seed(5)
+    wav = b200vad.synth.meeting_batch(64, 80000, seed=9).to(dev)
+    m = VadModel("PyanNet", {}).eval().to(dev)
+    with torch.no_grad():
+        outs = [m(wav.unsqueeze(1)).clone() for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    m2 = VadModel("PyanNet2", {"encoding_dim": 80}).eval()
+    blob = b200vad.pack_model(m2.model.state_dict(), dev, 80, 4)
+    runs = [torch.ops.b200vad.vad_pipeline_padded(wav, None, blob, 4, 0.5, 49) for _ in range(3)]
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1])

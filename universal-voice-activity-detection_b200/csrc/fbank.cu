@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) row_sum_kernel(const WT* __restrict__ wav
         double tot = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) tot += part[i];
-        atomicAdd(sums + b, tot);
+        atomicAdd(sums + b, exact_partial<32>(tot));      // exact additions: the row mean does not depend on the CTA order (common.cuh)
     }
 }
 

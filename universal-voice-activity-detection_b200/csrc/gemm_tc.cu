@@ -932,8 +932,8 @@ sinc_pool_gemm_kernel(const __grid_constant__ SincMaps maps, SincPoolParams p) {
                     sq = fmaf(m, m, sq);
                 }
             }
-            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2, (double)sum);
-            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2 + 1, (double)sq);
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2, exact_partial<32>((double)sum));   // exact -> order-independent (common.cuh)
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2 + 1, exact_partial<32>((double)sq));
         }
     }
     tc_fence_before();
@@ -1086,8 +1086,8 @@ conv_pool_gemm_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
                     sq = fmaf(m, m, sq);
                 }
             }
-            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2, (double)sum);
-            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2 + 1, (double)sq);
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2, exact_partial<32>((double)sum));   // exact -> order-independent (common.cuh)
+            atomicAdd(p.stats + ((int64_t)bi * p.n_valid + out) * 2 + 1, exact_partial<32>((double)sq));
         }
     }
     tc_fence_before();

@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
     if (threadIdx.x == 0) {
         double a = 0, c = 0;
         for (int i = 0; i < 8; ++i) { a += ps[i]; c += pq[i]; }
-        atomicAdd(stats + 2 * b, a);
-        atomicAdd(stats + 2 * b + 1, c);
+        atomicAdd(stats + 2 * b, exact_partial<32>(a));        // exact additions -> independent of the CTA order (common.cuh)
+        atomicAdd(stats + 2 * b + 1, exact_partial<32>(c));
     }
 }
 __global__ void __launch_bounds__(256) wave_norm_kernel(const float* __restrict__ wav, int64_t N, int64_t stride,
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256) pool_stats_kernel(const float* __restrict
     if (threadIdx.x < C) {
         double a = 0, d = 0;
         for (int r = 0; r < lanes; ++r) { a += ss[r * C + threadIdx.x]; d += sq[r * C + threadIdx.x]; }
-        atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2, a);
-        atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2 + 1, d);
+        atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2, exact_partial<32>(a));
+        atomicAdd(stats + ((int64_t)b * C + threadIdx.x) * 2 + 1, exact_partial<32>(d));
     }
 }
 // x = leaky_relu((x - mean) * rstd * gamma + beta): written in place as fp32, or -- when planes are given -- only as fp16
