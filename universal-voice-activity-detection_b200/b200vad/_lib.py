@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200vad.so")
+# B200VAD_LIB: another build of the same library (A/B runs of compile-time kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("B200VAD_LIB") or os.path.join(_HERE, "lib", "libb200vad.so")
 CSRC_DIR = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
 
 _lib = None

@@ -201,12 +201,12 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int base_parts = P / ipd, rem_parts = P % ipd;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(s), 1); mbar_init(bar_x_empty(s), FC); }
+        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(s), 1); mbar_init(bar_x_empty(s), (p.variant & 4) ? 1 : FC); }
         for (int q = 0; q < FMAXP; ++q) {
             mbar_init(bar_acc_ready(q), 1);
             mbar_init(bar_acc_free(q), FUSED_PW_SPLIT ? 8 : 4);
             mbar_init(bar_h_ready(q), FUSED_EXCH_PLAIN ? FC : 1);
-            mbar_init(bar_h_free(q), FC);
+            mbar_init(bar_h_free(q), (p.variant & 32) ? 1 : FC);
             mbar_init(bar_slice(q), FUSED_PW_SPLIT ? 8 : 4);
             mbar_init(bar_x_done(q), 1);
         }
@@ -335,6 +335,12 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         }
                         mbar_expect_tx(bar_x_full(xst), stage_bytes);
                         const uint32_t dst = smem_base + x_off + xst * stage_bytes;
+                        if (p.variant & 4) {                                       // experiment: every CTA fetches its whole tile itself (no multicast)
+                            for (int bi = 0; bi < nboxes; ++bi) {
+                                const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
+                                tma_load_3d(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst));
+                            }
+                        } else
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
                             tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst), (uint16_t)0xF);
@@ -407,7 +413,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 mma_f16_ts(d, wa0 + 8 * j, fdesc(xa + off), idesc, 1);
                             }
                         }
-                        mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
+                        if (p.variant & 4) mma_commit(bar_x_empty(xst)); else mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
                         if (p.variant & 2) mma_commit_mc(bar_x_done(pp), (uint16_t)(1u << rank)); else mma_commit(bar_x_done(pp));
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                         if (t3) t3[3] = clock64();
@@ -461,7 +467,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                             }
                         }
                         if (p.variant & 2) mma_commit_mc(bar_acc_ready(q), (uint16_t)(1u << rank)); else mma_commit(bar_acc_ready(q));   // (s = 0: h_{-1} = 0, the input product alone)
-                        if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA's copy of this part's h tile may be overwritten
+                        if (s < T - 1) { if (p.variant & 32) mma_commit(bar_h_free(q)); else mma_commit_mc(bar_h_free(q), (uint16_t)0xF); }   // every CTA's copy of this part's h tile may be overwritten
                         if (t2) t2[3] = clock64();
                         if (trh) trace[(s - F_TRACE_S0) * 16 + 1] = clock64();
                     }
@@ -499,6 +505,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         // the three peers over DSMEM; the own copy is a plain shared-memory store (it does not take the SM-to-SM port)
 #pragma unroll
                         for (uint32_t d = 1; d < FC; ++d) {
+                            if (p.variant & 16) continue;                          // experiment: no remote stores at all
 #if FUSED_EXCH_PLAIN
                             asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * 512 + cta_delta[d]),
                                          "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -518,7 +525,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #else
                     fence_proxy_async();                                           // own copy: generic stores before the tensor core's reads
                     __syncwarp();
-                    if (lane == 0) mbar_complete_tx(bar, (PROBE && (p.flags & 1)) ? F_BOX / 2 : F_BOX);
+                    if (lane == 0) mbar_complete_tx(bar, (p.variant & 16) ? F_HTILE : ((PROBE && (p.flags & 1)) ? F_BOX / 2 : F_BOX));
 #endif
                     if (trl) trace[(s - F_TRACE_S0) * 16 + 8] = clock64();
                 }

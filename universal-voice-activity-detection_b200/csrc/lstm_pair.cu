@@ -637,7 +637,9 @@ int lstm_pair_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, i
     int stages = 0;
     const int smem = pair_smem_bytes(p.kblocks, &stages);
     p.stages = stages;
-    p.opt = g_pair_opt;
+    static int opt_env = -2;
+    if (opt_env == -2) { const char* e = getenv("B200VAD_PAIR_OPT"); opt_env = e ? atoi(e) : -1; }
+    p.opt = opt_env >= 0 ? opt_env : g_pair_opt;
     const int nc = pair_max_clusters();
     const int P = (B + PPN - 1) / PPN;
     int best_ipd = (P + PMAXP - 1) / PMAXP;
