@@ -73,7 +73,9 @@ B200VAD_API int b200vad_set_lstm_tile(int sequences_per_cta);
  * and for wider inputs (768-dim SSL features on layer 0).  The environment variable B200VAD_LSTM_MODE sets the initial mode. */
 B200VAD_API int b200vad_set_lstm_fused(int on);
 /* tuning bits of mode 2 (default 3): 1 = the input-product issuers yield to a recurrent product that is ready to issue,
- * 2 = two sets of h operand tiles (no "tile free" hand-shake on the per-step chain).  Results do not depend on them. */
+ * 2 = two sets of h operand tiles (no "tile free" hand-shake on the per-step chain).  Results do not depend on bits 1 and 2.
+ * Bits 4, 8, 32 are timing probes of tools/lstm_modes_timing.py (one k-step of the input product, no recurrent MMAs, no x
+ * loads: RESULTS ARE WRONG while set); 64 fills the wait-site table read by b200vad_lstm_fused_read_debug (tools/pair_waits.py). */
 B200VAD_API int b200vad_set_lstm_pair_opt(int opt);
 /* clusters of 4 CTAs of the fused LSTM kernel that are co-resident on the current device (cudaOccupancyMaxActiveClusters) */
 B200VAD_API int b200vad_lstm_fused_clusters(void);
