@@ -125,10 +125,10 @@ __device__ volatile int* g_fused_err_host = nullptr;
 #ifndef FUSED_PW_SPLIT
 #define FUSED_PW_SPLIT 0
 #endif
-#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc)
-#define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc)
+#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc, (p.variant & 128) != 0)
+#define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc, false)
 template <bool CLUSTER_ACQUIRE>
-__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc) {
+__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc, bool no_hint) {
     if (!wacc && (CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) return;
     if (wacc && !CLUSTER_ACQUIRE && mbar_test_wait(bar, parity)) return;   // probe mode: count every wait that is not already satisfied
     const long long t0 = wacc ? clock64() : 0;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int
     // bound (~2 s) is checked once per 64 tries
     unsigned tries = 0;
     long long tb = 0;
-    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait_hint(bar, parity, 20000u))) {
+    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : (no_hint ? mbar_try_wait(bar, parity) : mbar_try_wait_hint(bar, parity, 20000u)))) {
         if ((++tries & 63u) != 0) continue;
         const long long now = clock64();
         if (tb == 0) tb = now;
@@ -343,6 +343,10 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         } else
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
+                            if (p.variant & 64) {                                  // experiment: 16-row boxes (tensor maps encoded with 16 rows)
+                                tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst), (uint16_t)0xF);
+                                tma_load_3d_mc(dst + bi * F_XBOX + F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN + FPN, bar_x_full(xst), (uint16_t)0xF);
+                            } else
                             tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst), (uint16_t)0xF);
                         }
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
@@ -843,6 +847,9 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     p.wih_hi = wih_hi; p.wih_lo = wih_lo; p.whh_hi = whh_hi; p.whh_lo = whh_lo; p.bias = bias; p.y_a = y_a; p.y_b = y_b;
     p.B = B; p.T = T; p.nk = (D + 15) / 16; p.kblocks = (D + 63) / 64; p.ldw = ldw; p.terms = terms;
     (void)y_scaled;                                          // the output planes are always the scaled split (see the header)
+    static int variant_env = -1;
+    if (variant_env < 0) { const char* e = getenv("B200VAD_FUSED_VARIANT"); variant_env = e ? atoi(e) : 0; }
+    p.variant = variant_env;
     int stages = 0;
     const int smem = fused_smem_bytes(p.kblocks, &stages);
     p.stages = stages;
@@ -852,9 +859,7 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     static int pf_env = -1;
     if (pf_env < 0) { const char* e = getenv("B200VAD_FUSED_PREFETCH"); pf_env = e ? atoi(e) : 0; }
     p.prefetch_steps = pf_env;
-    static int variant_env = -1;
-    if (variant_env < 0) { const char* e = getenv("B200VAD_FUSED_VARIANT"); variant_env = e ? atoi(e) : 0; }
-    p.variant = variant_env;
+
     const int nc = fused_max_clusters();
     // work items: parts of 16 sequences, spread evenly over items_per_dir items per direction (<= 8 parts each); choose the
     // count that minimises waves x step time.  Measured step time (us) of a cluster with n parts in flight (256 x 500: n = 1,
@@ -876,9 +881,10 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     const int grid = FC * std::min(nc, 2 * best_ipd);
     CUtensorMap tm_a, tm_b;
     int rc;
-    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, 2 * FPN,
+    const int box_rows = (p.variant & 64) ? FPN : 2 * FPN;
+    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, box_rows,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, 2 * FPN,
+    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, box_rows,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     const FusedKern kern = fused_pick(p.nk, terms, p.flags != 0);
     if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem))) return rc;
