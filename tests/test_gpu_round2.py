@@ -264,3 +264,36 @@ def test_forward_is_bit_reproducible(dev):
     runs = [torch.ops.b200vad.vad_pipeline_padded(wav, None, blob, 4, 0.5, 49) for _ in range(3)]
     for r in runs[1:]:
         assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1])
+
+
+def test_lstm_layers_next_to_a_busy_second_stream(dev):
+    """Regression test of the x_full phase-aliasing race of the fused layer kernels (csrc/lstm_fused.cu, header of bar_x_full): with
+    a 3-stage x ring (D = 256 layers) the two input-product issuers used to wait on successive phases of the SAME mbarrier; when the
+    x tiles were late -- a second stream saturating HBM -- the second issuer's parity wait aliased an older phase, consumed a
+    stale tile and corrupted the ring (`unspecified launch failure`, or silently different probabilities).  Each issuer now has
+    its own barrier set.  The LSTM stack runs at the bench shape next to a stream of elementwise kernels and must reproduce the
+    single-stream result bit for bit, in every layer mode."""
+    import b200vad
+    lib = b200vad.lib()
+    B, T, D, L = 4096, 800, 80, 4
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(B, T, D, generator=g) * 3 - 5).to(dev)
+    o = util.make_oracle("PyanNet2", {"encoding_dim": D})
+    blob = b200vad.pack_model(o.model.state_dict(), dev, D, L)
+    hog = torch.ones(256 << 20, device=dev)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    try:
+        for mode in (1, 2):
+            lib.b200vad_set_lstm_fused(mode)
+            ref = torch.ops.b200vad.lstm_head(x, blob, L).clone()
+            torch.cuda.synchronize()
+            for r in range(6):
+                with torch.cuda.stream(sb):
+                    for _ in range(150):
+                        hog.mul_(1.0001)
+                with torch.cuda.stream(sa):
+                    p = torch.ops.b200vad.lstm_head(x, blob, L)
+                torch.cuda.synchronize()
+                assert torch.equal(p, ref), (mode, r, (p - ref).abs().max().item())
+    finally:
+        lib.b200vad_set_lstm_fused(1)

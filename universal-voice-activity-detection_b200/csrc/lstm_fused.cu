@@ -181,7 +181,13 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int terms = NK > 0 ? TERMS : p.terms;
     const uint32_t stage_bytes = 2u * p.kblocks * F_XBOX;     // one stage = the x tile of a pair of parts
     const uint32_t bar_base = smem_base + x_off + p.stages * stage_bytes;
-    auto bar_x_full = [&](int s) { return bar_base + 8 * s; };
+    // x_full: ONE SET PER INPUT ISSUER (a slot of pair pp is consumed by issuer pp & 1).  With a single set and an odd ring depth
+    // (3 stages at D = 256) successive phases of a stage's barrier are waited on by DIFFERENT threads; a thread that reaches its
+    // slot before the other thread's (earlier) slot of the same stage has even landed then waits on a parity that aliases the
+    // phase before last and passes at once -- stale tile, an extra commit on x_empty, and with it a corrupted ring (seen as an
+    // `unspecified launch failure` whenever the x loads were slow: a second stream saturating HBM).  With its own set every
+    // barrier is waited on by one thread, phase after phase.
+    auto bar_x_full = [&](int me, int s) { return bar_base + (me ? 832 : 0) + 8 * s; };
     auto bar_x_empty = [&](int s) { return bar_base + 128 + 8 * s; };
     auto bar_acc_ready = [&](int q) { return bar_base + 256 + 8 * q; };
     auto bar_acc_free = [&](int q) { return bar_base + 320 + 8 * q; };
@@ -201,7 +207,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int base_parts = P / ipd, rem_parts = P % ipd;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(s), 1); mbar_init(bar_x_empty(s), (p.variant & 4) ? 1 : FC); }
+        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(0, s), 1); mbar_init(bar_x_full(1, s), 1); mbar_init(bar_x_empty(s), (p.variant & 4) ? 1 : FC); }
         for (int q = 0; q < FMAXP; ++q) {
             mbar_init(bar_acc_ready(q), 1);
             mbar_init(bar_acc_free(q), FUSED_PW_SPLIT ? 8 : 4);
@@ -231,6 +237,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     int xst = 0;                                              // producer / input-product issuer: next x ring stage ...
     uint32_t xph = 0;                                         // ... and its phase
     uint32_t ph_a = 0, ph_b = 0;                              // per-part phase bits (meaning depends on the role)
+    uint32_t xfph = 0;                                        // input-product issuer: phase bits of its own x_full set, per stage
     int loaded_dir = -1;
 
     for (int item = cluster_id; item < num_items; item += num_clusters) {
@@ -329,25 +336,25 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                             }
                         FUSED_WAIT(bar_x_empty(xst), xph ^ 1u, 1);                // all 4 CTAs' MMAs are done with this stage
                         if (PROBE && (p.flags & 256)) {                           // timing probe: no x loads (stale tiles)
-                            mbar_arrive(bar_x_full(xst));
+                            mbar_arrive(bar_x_full(pp & 1, xst));
                             if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                             continue;
                         }
-                        mbar_expect_tx(bar_x_full(xst), stage_bytes);
+                        mbar_expect_tx(bar_x_full(pp & 1, xst), stage_bytes);
                         const uint32_t dst = smem_base + x_off + xst * stage_bytes;
                         if (p.variant & 4) {                                       // experiment: every CTA fetches its whole tile itself (no multicast)
                             for (int bi = 0; bi < nboxes; ++bi) {
                                 const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                                tma_load_3d(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst));
+                                tma_load_3d(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(pp & 1, xst));
                             }
                         } else
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
                             if (p.variant & 64) {                                  // experiment: 16-row boxes (tensor maps encoded with 16 rows)
-                                tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst), (uint16_t)0xF);
-                                tma_load_3d_mc(dst + bi * F_XBOX + F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN + FPN, bar_x_full(xst), (uint16_t)0xF);
+                                tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(pp & 1, xst), (uint16_t)0xF);
+                                tma_load_3d_mc(dst + bi * F_XBOX + F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN + FPN, bar_x_full(pp & 1, xst), (uint16_t)0xF);
                             } else
-                            tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(xst), (uint16_t)0xF);
+                            tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(pp & 1, xst), (uint16_t)0xF);
                         }
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                     }
@@ -386,7 +393,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                             }
                         }
                         if (t3) t3[1] = clock64();
-                        FUSED_WAIT(bar_x_full(xst), xph, 3);
+                        FUSED_WAIT(bar_x_full(me, xst), (xfph >> xst) & 1u, 3);   // own barrier set: its phases are this thread's own uses of the stage
+                        xfph ^= 1u << xst;
                         tc_fence_after();
                         if (t3) t3[2] = clock64();
                         if (trx) trace[(s - F_TRACE_S0) * 16 + 13] = clock64();
@@ -795,6 +803,9 @@ static int fused_smem_bytes(int kblocks, int* stages_out) {
     const int stage = 2 * kblocks * F_XBOX;
     int stages = (F_SMEM_MAX - 1024 - F_SMEM_FIXED - 1024) / stage;
     if (stages > F_MAX_STAGES) stages = F_MAX_STAGES;
+    static int cap = -1;                                     // B200VAD_FUSED_STAGES: cap of the x ring depth (experiments)
+    if (cap < 0) { const char* e = getenv("B200VAD_FUSED_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && stages > cap) stages = cap;
     *stages_out = stages;
     return 1024 + F_SMEM_FIXED + stages * stage + 1024;
 }

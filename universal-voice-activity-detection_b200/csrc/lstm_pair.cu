@@ -128,7 +128,9 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int terms = NK > 0 ? TERMS : p.terms;
     const uint32_t stage_bytes = 2u * p.kblocks * P_XBOX;
     const uint32_t bar_base = smem_base + x_off + p.stages * stage_bytes;
-    auto bar_x_full = [&](int s) { return bar_base + 8 * s; };          // leader: own tile (tx) + the odd CTA's forward; odd: own tile
+    // leader: own tile (tx) + the odd CTA's forward; odd: own tile.  One set per input issuer / forwarder (slots of pair pp belong to
+    // issuer pp & 1), so that every barrier is waited on by ONE thread, phase after phase (lstm_fused.cu has the reason)
+    auto bar_x_full = [&](int me, int s) { return bar_base + (me ? 896 : 0) + 8 * s; };
     auto bar_x_empty = [&](int s) { return bar_base + 128 + 8 * s; };   // both pairs' MMAs are done with the stage (multicast commits)
     auto bar_acc_ready = [&](int q) { return bar_base + 256 + 8 * q; }; // the pair's commit
     auto bar_acc_free = [&](int q) { return bar_base + 320 + 8 * q; };  // leader's: 4 + 4 pointwise warps of the pair
@@ -155,7 +157,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int base_parts = P / ipd, rem_parts = P % ipd;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P_MAX_STAGES; ++s) { mbar_init(bar_x_full(s), is_leader ? 2 : 1); mbar_init(bar_x_empty(s), 2); }
+        for (int s = 0; s < P_MAX_STAGES; ++s) { mbar_init(bar_x_full(0, s), is_leader ? 2 : 1); mbar_init(bar_x_full(1, s), is_leader ? 2 : 1); mbar_init(bar_x_empty(s), 2); }
         for (int q = 0; q < PMAXP; ++q) {
             mbar_init(bar_acc_ready(q), 1);
             mbar_init(bar_acc_free(q), 8);
@@ -184,6 +186,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int xst = 0;
     uint32_t xph = 0;
     uint32_t ph_a = 0, ph_b = 0;
+    uint32_t xfph = 0;                                        // input issuer / x forwarder: phase bits of its own x_full set, per stage
     int loaded_dir = -1;
 
     for (int item = cluster_id; item < num_items; item += num_clusters) {
@@ -268,15 +271,15 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     for (int pp = 0; pp < npairs; ++pp) {
                         PWAIT(bar_x_empty(xst), xph ^ 1u, 1);
                         if (PROBE && (p.opt & 32)) {                                          // timing probe: no x loads (stale tiles)
-                            mbar_arrive(bar_x_full(xst));
+                            mbar_arrive(bar_x_full(pp & 1, xst));
                             if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                             continue;
                         }
-                        mbar_expect_tx(bar_x_full(xst), stage_bytes);
+                        mbar_expect_tx(bar_x_full(pp & 1, xst), stage_bytes);
                         const uint32_t dst = smem_base + x_off + xst * stage_bytes;
                         for (int bi = sub; bi < nboxes; bi += 2) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                            tma_load_3d_mc(dst + bi * P_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * PPN + (int)hf * PPN, bar_x_full(xst), mc);
+                            tma_load_3d_mc(dst + bi * P_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * PPN + (int)hf * PPN, bar_x_full(pp & 1, xst), mc);
                         }
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                     }
@@ -307,7 +310,8 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                     }
                                 }
                             }
-                            PWAIT_CL(bar_x_full(xst), xph, 3);
+                            PWAIT_CL(bar_x_full(me, xst), (xfph >> xst) & 1u, 3);
+                            xfph ^= 1u << xst;
                             tc_fence_after();
                             const uint32_t xa = pdesc_lo(smem_base + x_off + xst * stage_bytes), xb = xa + plane_lo;
                             const uint32_t d = tmem_base + P_ACC_COL + pp * 2 * PPN;
@@ -354,11 +358,12 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                 } else {
                     // ===================== x forwarder (odd CTA): own half tile landed -> one arrive on the leader's x_full =====================
-                    const uint32_t remote0 = mapa_shared(bar_x_full(0), leader);
+                    const uint32_t remote0 = mapa_shared(bar_x_full(me, 0), leader);
                     for (int s = 0; s < T; ++s) {
                         for (int pp = 0; pp < npairs; ++pp) {
                             if ((pp & 1) == me) {
-                                PWAIT(bar_x_full(xst), xph, 3);
+                                PWAIT(bar_x_full(me, xst), (xfph >> xst) & 1u, 3);
+                                xfph ^= 1u << xst;
                                 mbar_arrive_cluster(remote0 + 8 * xst);
                             }
                             if (++xst == p.stages) { xst = 0; xph ^= 1u; }
