@@ -31,12 +31,15 @@
 //     index is free as long as A and B agree: K block r (64 slots = one 128-byte swizzled row) is [h1 of units 32r..32r+31 |
 //     h2 of the same units], exactly what CTA r produces, so a CTA's contribution is ONE contiguous box.
 //
-// What bounds it (profiles/r02_lstm_fused.md): every CTA sends 48 KB and receives 48 KB of h per step, and the DSMEM port of an
-// SM moves ~17 B/clk: ~6000 cycles per step for 128 sequences, twice the 3072 cycles the tensor pipe needs.  All exchange
-// mechanisms tried hit the same wall or a latency one: cp.async.bulk by a sender thread (~3000 cycles per copy through the TMA
-// unit), st.async from the pointwise warps (they stall on the port), and an exchange through the output planes in L2 (TMA
-// store + multicast TMA load: no DSMEM traffic but two ~1-2 us TMA round trips on the per-step chain; that variant also
-// showed an intermittent launch failure on B200 and is kept only as tools/experiments/lstm_fused_l2_exchange.cu.txt).
+// What bounds it (profiles/r02_lstm_fused.md): a step of a cluster with n parts in flight takes ~1.6 us + 0.26 us (n - 1): a fixed
+// chain latency (recurrent MMAs -> accumulator read -> cell arithmetic -> h exchange -> next MMAs, ~2 900 cycles) plus a per-part
+// cost close to the part's tensor-pipe time (384 cycles: 16 recurrent MMAs x 8 + 16 input MMAs x 16).  n = 8 is all the
+// accumulator columns TMEM has left, so half of the step is unhidden latency.  Every CTA also sends 48 KB and receives 48 KB of h
+// per step over the SM-to-SM port (~17 B/clk).  Exchange mechanisms tried: cp.async.bulk by a sender thread (~3000 cycles per
+// copy through the TMA unit), st.async from the pointwise warps (they stall on the port), and an exchange through the output
+// planes in L2 (TMA store + multicast TMA load: two ~1-2 us TMA round trips on the per-step chain; that variant showed
+// intermittent launch failures -- in hindsight probably the x_full race described at bar_x_full, which any delay of the x tiles
+// exposes -- and is kept only as tools/experiments/lstm_fused_l2_exchange.cu.txt).
 //
 // Precision (DESIGN.md "Precision"): every product is split-precision with fp32 accumulation.  Activations travel as the
 // scaled split x1 = fp16((1 - s) x), x2 = fp16(x - x1), s = 2^-6, weights as W_hi = fp16(W), W' = fp16(W_hi + W_lo / s):
@@ -97,7 +100,6 @@ struct FusedParams {
     int items_per_dir;       // work items per direction; parts are spread evenly over them
     int stages;              // x ring depth
     int prefetch_steps;      // L2 prefetch distance of the x tiles, in time steps (0 = off)
-    int variant;             // B200VAD_FUSED_VARIANT (robustness experiments): 1 cluster-wide sync after the weight load, 2 local commits in multicast form
     int flags;               // timing probes (wrong results): 2 no y store, 4 no cell math, 8 no recurrent MMAs, 16 no input MMAs, 32 wait-time table, 64 timeline
 };
 
@@ -125,10 +127,10 @@ __device__ volatile int* g_fused_err_host = nullptr;
 #ifndef FUSED_PW_SPLIT
 #define FUSED_PW_SPLIT 0
 #endif
-#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc, (p.variant & 128) != 0)
-#define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc, false)
+#define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc)
+#define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc)
 template <bool CLUSTER_ACQUIRE>
-__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc, bool no_hint) {
+__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag, long long* wacc) {
     if (!wacc && (CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) return;
     if (wacc && !CLUSTER_ACQUIRE && mbar_test_wait(bar, parity)) return;   // probe mode: count every wait that is not already satisfied
     const long long t0 = wacc ? clock64() : 0;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int
     // bound (~2 s) is checked once per 64 tries
     unsigned tries = 0;
     long long tb = 0;
-    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : (no_hint ? mbar_try_wait(bar, parity) : mbar_try_wait_hint(bar, parity, 20000u)))) {
+    while (!(CLUSTER_ACQUIRE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait_hint(bar, parity, 20000u))) {
         if ((++tries & 63u) != 0) continue;
         const long long now = clock64();
         if (tb == 0) tb = now;
@@ -207,12 +209,12 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int base_parts = P / ipd, rem_parts = P % ipd;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(0, s), 1); mbar_init(bar_x_full(1, s), 1); mbar_init(bar_x_empty(s), (p.variant & 4) ? 1 : FC); }
+        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(0, s), 1); mbar_init(bar_x_full(1, s), 1); mbar_init(bar_x_empty(s), FC); }
         for (int q = 0; q < FMAXP; ++q) {
             mbar_init(bar_acc_ready(q), 1);
             mbar_init(bar_acc_free(q), FUSED_PW_SPLIT ? 8 : 4);
             mbar_init(bar_h_ready(q), FUSED_EXCH_PLAIN ? FC : 1);
-            mbar_init(bar_h_free(q), (p.variant & 32) ? 1 : FC);
+            mbar_init(bar_h_free(q), FC);
             mbar_init(bar_slice(q), FUSED_PW_SPLIT ? 8 : 4);
             mbar_init(bar_x_done(q), 1);
         }
@@ -308,7 +310,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
         loaded_dir = dir;
         tc_fence_before();
-        if (p.variant & 1) cluster_sync_all(); else __syncthreads();
+        __syncthreads();
         tc_fence_after();
 
         if (warp == F_W_PROD) {
@@ -342,18 +344,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         }
                         mbar_expect_tx(bar_x_full(pp & 1, xst), stage_bytes);
                         const uint32_t dst = smem_base + x_off + xst * stage_bytes;
-                        if (p.variant & 4) {                                       // experiment: every CTA fetches its whole tile itself (no multicast)
-                            for (int bi = 0; bi < nboxes; ++bi) {
-                                const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                                tma_load_3d(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(pp & 1, xst));
-                            }
-                        } else
                         for (int bi = (int)rank; bi < nboxes; bi += FC) {
                             const int pl = bi >= p.kblocks, kb = pl ? bi - p.kblocks : bi;
-                            if (p.variant & 64) {                                  // experiment: 16-row boxes (tensor maps encoded with 16 rows)
-                                tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(pp & 1, xst), (uint16_t)0xF);
-                                tma_load_3d_mc(dst + bi * F_XBOX + F_BOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN + FPN, bar_x_full(pp & 1, xst), (uint16_t)0xF);
-                            } else
                             tma_load_3d_mc(dst + bi * F_XBOX, pl ? &tm_b : &tm_a, kb * 64, t, seq0 + pp * 2 * FPN, bar_x_full(pp & 1, xst), (uint16_t)0xF);
                         }
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
@@ -425,8 +417,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                 mma_f16_ts(d, wa0 + 8 * j, fdesc(xa + off), idesc, 1);
                             }
                         }
-                        if (p.variant & 4) mma_commit(bar_x_empty(xst)); else mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
-                        if (p.variant & 2) mma_commit_mc(bar_x_done(pp), (uint16_t)(1u << rank)); else mma_commit(bar_x_done(pp));
+                        mma_commit_mc(bar_x_empty(xst), (uint16_t)0xF);
+                        mma_commit(bar_x_done(pp));
                         if (++xst == p.stages) { xst = 0; xph ^= 1u; }
                         if (t3) t3[3] = clock64();
                         if (trx) trace[(s - F_TRACE_S0) * 16 + 15] = clock64();
@@ -478,8 +470,8 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                                     mma_f16_ts(d, tmem_base + F_WHH_COL + 8 * jj, fdesc(hb + (uint32_t)((jj >> 2) * (F_BOX >> 4) + (jj & 3) * 2)), idesc, 1);
                             }
                         }
-                        if (p.variant & 2) mma_commit_mc(bar_acc_ready(q), (uint16_t)(1u << rank)); else mma_commit(bar_acc_ready(q));   // (s = 0: h_{-1} = 0, the input product alone)
-                        if (s < T - 1) { if (p.variant & 32) mma_commit(bar_h_free(q)); else mma_commit_mc(bar_h_free(q), (uint16_t)0xF); }   // every CTA's copy of this part's h tile may be overwritten
+                        mma_commit(bar_acc_ready(q));                              // (s = 0: h_{-1} = 0, the input product alone)
+                        if (s < T - 1) mma_commit_mc(bar_h_free(q), (uint16_t)0xF);   // every CTA's copy of this part's h tile may be overwritten
                         if (t2) t2[3] = clock64();
                         if (trh) trace[(s - F_TRACE_S0) * 16 + 1] = clock64();
                     }
@@ -517,7 +509,6 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         // the three peers over DSMEM; the own copy is a plain shared-memory store (it does not take the SM-to-SM port)
 #pragma unroll
                         for (uint32_t d = 1; d < FC; ++d) {
-                            if (p.variant & 16) continue;                          // experiment: no remote stores at all
 #if FUSED_EXCH_PLAIN
                             asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * 512 + cta_delta[d]),
                                          "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -537,7 +528,7 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #else
                     fence_proxy_async();                                           // own copy: generic stores before the tensor core's reads
                     __syncwarp();
-                    if (lane == 0) mbar_complete_tx(bar, (p.variant & 16) ? F_HTILE : ((PROBE && (p.flags & 1)) ? F_BOX / 2 : F_BOX));
+                    if (lane == 0) mbar_complete_tx(bar, (PROBE && (p.flags & 1)) ? F_BOX / 2 : F_BOX);
 #endif
                     if (trl) trace[(s - F_TRACE_S0) * 16 + 8] = clock64();
                 }
@@ -858,9 +849,6 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     p.wih_hi = wih_hi; p.wih_lo = wih_lo; p.whh_hi = whh_hi; p.whh_lo = whh_lo; p.bias = bias; p.y_a = y_a; p.y_b = y_b;
     p.B = B; p.T = T; p.nk = (D + 15) / 16; p.kblocks = (D + 63) / 64; p.ldw = ldw; p.terms = terms;
     (void)y_scaled;                                          // the output planes are always the scaled split (see the header)
-    static int variant_env = -1;
-    if (variant_env < 0) { const char* e = getenv("B200VAD_FUSED_VARIANT"); variant_env = e ? atoi(e) : 0; }
-    p.variant = variant_env;
     int stages = 0;
     const int smem = fused_smem_bytes(p.kblocks, &stages);
     p.stages = stages;
@@ -892,10 +880,9 @@ int lstm_fused_launch(const __half* x_a, const __half* x_b, int64_t lda, int B, 
     const int grid = FC * std::min(nc, 2 * best_ipd);
     CUtensorMap tm_a, tm_b;
     int rc;
-    const int box_rows = (p.variant & 64) ? FPN : 2 * FPN;
-    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, box_rows,
+    if ((rc = make_tmap_3d(&tm_a, x_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, 2 * FPN,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, box_rows,
+    if ((rc = make_tmap_3d(&tm_b, x_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, T, B, lda * 2, (uint64_t)T * lda * 2, 64, 1, 2 * FPN,
                            CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     const FusedKern kern = fused_pick(p.nk, terms, p.flags != 0);
     if ((rc = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem))) return rc;
