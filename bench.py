@@ -481,6 +481,7 @@ def main():
     # its per-kernel CUDA-event timings (roofline) need kernels that do not wait for another stream's work.
     two_streams = None
     if world == 1 and not args.skip_modes:
+      try:
         ss = [torch.cuda.Stream(device=dev) for _ in range(2)]
         keep = [None, None]
 
@@ -505,11 +506,18 @@ def main():
                        "note": "same device-resident step, batches alternating over two CUDA streams (informational)"}
         del keep, ss
         torch.cuda.empty_cache()          # two more 21 GB workspaces sit in the allocator's per-stream pools; the C-side sessions below use cudaMalloc
+      except Exception as exc:  # noqa: BLE001 -- informational
+        two_streams = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        print(f"bench.py: the two-stream arm failed: {exc}", file=sys.stderr)
 
     # ---------------- the SincNet path (PyanNet) and the other BASELINE configs at this build (single GPU only)
     extra = {}
     if world == 1 and not args.skip_modes:
-        extra = other_paths(torch, b200vad, VadModel, dev, blob, wav_dev, rows)
+        try:
+            extra = other_paths(torch, b200vad, VadModel, dev, blob, wav_dev, rows)
+        except Exception as exc:  # noqa: BLE001 -- informational arms must not cost the headline line
+            extra = {"modes_error": f"{type(exc).__name__}: {exc}"[:300]}
+            print(f"bench.py: the informational arms failed: {exc}", file=sys.stderr)
 
     if rank == 0:
         peaks = load_peaks()
@@ -584,9 +592,12 @@ def main():
             line["two_streams"] = two_streams
         if world == 1 and not args.skip_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt = cpu_reference(512, 1, 1, threads)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"512 x {SECONDS:.0f} s utterances (oracle: torch CPU fbank + nn.LSTM + scipy medfilt + Python RLE), {dt:.1f} s/step"}
+            try:
+                v, dt = cpu_reference(512, 1, 1, threads)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                        "sample": f"512 x {SECONDS:.0f} s utterances (oracle: torch CPU fbank + nn.LSTM + scipy medfilt + Python RLE), {dt:.1f} s/step"}
+            except Exception as exc:  # noqa: BLE001 -- the GPU line is still worth printing
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {type(exc).__name__}: {exc}"[:300]}
         jout.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
