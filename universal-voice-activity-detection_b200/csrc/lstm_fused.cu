@@ -119,14 +119,6 @@ __device__ volatile int* g_fused_err_host = nullptr;
 #ifndef FUSED_EXCH_PLAIN
 #define FUSED_EXCH_PLAIN 0
 #endif
-// pointwise work split: 1 = a warp pass covers 8 of a part's 16 sequences (two warps per (part, lane quarter), each warp serves
-// four parts): half the serial instruction count of a pass; 0 (default) = one warp per (part, lane quarter), two parts per warp.
-// Measured: bit-identical, 7.84 instead of 6.3 ms per layer at 8 parts per cluster and no change at 1 part (0.80 ms at 256 x 500):
-// the pass is bound by its fixed latencies (TMEM load, MUFU chain, shared-memory round trips, barrier hand-offs), not by its
-// instruction count, and twice as many passes only add issue pressure.
-#ifndef FUSED_PW_SPLIT
-#define FUSED_PW_SPLIT 0
-#endif
 #define FUSED_WAIT(bar, parity, tag) mbar_wait_tag<false>(bar, parity, tag, wacc)
 #define FUSED_WAIT_CLUSTER(bar, parity, tag) mbar_wait_tag<true>(bar, parity, tag, wacc)
 template <bool CLUSTER_ACQUIRE>
@@ -212,10 +204,10 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_x_full(0, s), 1); mbar_init(bar_x_full(1, s), 1); mbar_init(bar_x_empty(s), FC); }
         for (int q = 0; q < FMAXP; ++q) {
             mbar_init(bar_acc_ready(q), 1);
-            mbar_init(bar_acc_free(q), FUSED_PW_SPLIT ? 8 : 4);
+            mbar_init(bar_acc_free(q), 4);
             mbar_init(bar_h_ready(q), FUSED_EXCH_PLAIN ? FC : 1);
             mbar_init(bar_h_free(q), FC);
-            mbar_init(bar_slice(q), FUSED_PW_SPLIT ? 8 : 4);
+            mbar_init(bar_slice(q), 4);
             mbar_init(bar_x_done(q), 1);
         }
         mbar_fence_init();
@@ -533,107 +525,6 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     if (trl) trace[(s - F_TRACE_S0) * 16 + 8] = clock64();
                 }
             }
-#if FUSED_PW_SPLIT
-        } else if ((warp >> 3) < nparts) {
-            // ===================== pointwise warps: warp (ps, hh, g) = parts ps, ps + 2, ps + 4, ps + 6 (the parts of recurrent issuer ps,
-            // in its order), sequences 8 hh .. 8 hh + 7 of each, units 8 g .. 8 g + 7 of this CTA =====================
-            // lane l reads the accumulator row of gate l & 3 of unit 8 g + (l >> 2) for its 8 sequences, turns it into exponentials,
-            // and the four lanes of a unit transpose (gate x sequence) through the warp-private scratch, after which lane l owns all
-            // four gates of 2 cells: unit 8 g + (l >> 2), sequences 8 hh + 2 (l & 3) + {0, 1} -- one packed-fp32 pair.
-            const int ps = warp >> 3, hh = (warp >> 2) & 1, g = warp & 3;
-            const int uu = lane >> 2, jj = lane & 3;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16) + F_ACC_COL + 8 * hh;
-            const float bias = __ldg(p.bias + dir * kGates + jj * kHidden + (int)rank * FU + 8 * g + uu);
-            unsigned char* const scr = smem_gen + c_off + warp * F_SCRATCH;
-            auto scr_at = [&](int row, int c) -> unsigned char* {
-                return scr + (((row * 64) + ((c ^ ((row >> 1) & 3)) << 4)) ^ (((row >> 2) & 1) << 6));
-            };
-            const float s1 = 1.f - kPlaneScale;
-            const float L2E2 = 2.f * kLog2e;
-            float cst[4][2];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) { cst[a][0] = 0.f; cst[a][1] = 0.f; }
-            // layer output: lanes 0 .. 15 = (row 8 hh + (lane & 7), plane lane >> 3), the 16-byte chunk of this warp's 8 units
-            const int yrow = 8 * hh + (lane & 7);
-            __half* const yplane = ((lane >> 3) & 1) ? p.y_b : p.y_a;
-            // ph_a: acc_ready phase bits (bit k)
-            for (int s = 0; s < T; ++s) {
-                const int t = dir == 0 ? s : T - 1 - s;
-                const bool exchange = s + 1 < T;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int q = ps + 2 * k;
-                    if (q >= nparts) break;
-                    FUSED_WAIT(bar_acc_ready(q), (ph_a >> k) & 1u, 6);
-                    ph_a ^= 1u << k;
-                    tc_fence_after();
-                    const bool tr_on = tr_item && warp == 0 && k == 0 && s >= F_TRACE_S0 && s < F_TRACE_S0 + F_TRACE_STEPS;
-                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 2] = clock64();
-                    float z[8];
-                    tmem_ld8(lane_addr + q * FPN, z);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acc_free(q));                   // the next step's input product may overwrite the accumulator
-                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 3] = clock64();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] = fast_ex2(fminf(z[j] + bias, 29.f));
-                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 4] = clock64();
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        *reinterpret_cast<float4*>(scr_at(lane, c)) = make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]);
-                    __syncwarp();
-                    float ev[4][2];                                                // [gate][cell]: sequence 8 hh + 2 jj + cell
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float2 v = *reinterpret_cast<const float2*>(scr_at((lane & ~3) + b, jj >> 1) + (jj & 1) * 8);
-                        ev[b][0] = v.x; ev[b][1] = v.y;
-                    }
-                    __syncwarp();
-                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 5] = clock64();
-                    float hv[2];
-                    {
-                        const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), k2 = pack2(L2E2, L2E2);
-                        if (PROBE && (p.flags & 4)) { hv[0] = ev[0][0] * 1e-3f; hv[1] = ev[3][1] * 1e-3f; }
-                        else {
-                            const f32x2 pei = pack2(ev[0][0], ev[0][1]), pef = pack2(ev[1][0], ev[1][1]);
-                            const f32x2 peg = pack2(ev[2][0], ev[2][1]), peo = pack2(ev[3][0], ev[3][1]);
-                            // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(eg + 1)) with one reciprocal (lstm_tc.cu)
-                            const f32x2 di = add2(pei, one), df = add2(pef, one), dg = add2(peg, one);
-                            const f32x2 dig = mul2(di, dg);
-                            const f32x2 den = mul2(df, dig);
-                            const f32x2 cn = mul2(fma2(pack2(cst[k][0], cst[k][1]), dig, mul2(add2(peg, mone), df)), rcp2(den));
-                            unpack2(cn, cst[k][0], cst[k][1]);
-                            const f32x2 ec = ex2_clamped2(mul2(cn, k2));
-                            const f32x2 h2v = mul2(add2(ec, mone), rcp2(mul2(add2(peo, one), add2(ec, one))));
-                            unpack2(h2v, hv[0], hv[1]);
-                        }
-                    }
-                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 10] = clock64();
-                    // h_s planes -> the CTA's staging slice of (step parity, part), operand layout (see the unsplit variant below)
-                    unsigned char* const stg = smem_gen + g_off + ((s & 1) * FMAXP + q) * F_BOX;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int row = 8 * hh + 2 * jj + c;
-                        __half a1, a2;
-                        split_scaled_f16(hv[c], s1, a1, a2);
-                        unsigned char* const rp = stg + row * 128 + uu * 2;
-                        *reinterpret_cast<__half*>(rp + ((g ^ (row & 7)) << 4)) = a1;
-                        *reinterpret_cast<__half*>(rp + (((4 + g) ^ (row & 7)) << 4)) = a2;
-                    }
-                    __syncwarp();
-                    if (exchange && lane == 0) mbar_arrive(bar_slice(q));          // (release: the sender warp reads the slice with plain loads)
-                    if (lane < 16) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(stg + yrow * 128 + (((((lane >> 3) & 1) * 4 + g) ^ (yrow & 7)) << 4));
-                        const int b = seq0 + q * FPN + yrow;
-                        if (b < p.B && !(PROBE && (p.flags & 2)))
-                            *reinterpret_cast<uint4*>(yplane + ((size_t)b * T + t) * (2 * kHidden) + dir * kHidden + (int)rank * FU + 8 * g) = v;
-                    }
-                    if (tr_on) trace[(s - F_TRACE_S0) * 16 + 12] = clock64();
-                }
-            }
-        }
-#else
         } else if ((warp >> 2) < nparts) {
             // ===================== pointwise warps: warp (pg, g) = parts pg and pg + 4, units 8 g .. 8 g + 7 of this CTA =====================
             // lane l reads the accumulator row of gate l & 3 of unit 8 g + (l >> 2) for the part's 16 sequences, turns it into
@@ -735,7 +626,6 @@ lstm_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
             }
         }
-#endif
         // item boundary: every role of every CTA is done with this item's tiles and barriers
         tc_fence_before();
         cluster_sync_all();
