@@ -33,9 +33,9 @@
 //
 // What bounds it (profiles/r02_lstm_fused.md): a step of a cluster with n parts in flight takes ~1.6 us + 0.26 us (n - 1): a fixed
 // chain latency (recurrent MMAs -> accumulator read -> cell arithmetic -> h exchange -> next MMAs, ~2 900 cycles) plus a per-part
-// cost close to the part's tensor-pipe time (384 cycles: 16 recurrent MMAs x 8 + 16 input MMAs x 16).  n = 8 is all the
-// accumulator columns TMEM has left, so half of the step is unhidden latency.  Every CTA also sends 48 KB and receives 48 KB of h
-// per step over the SM-to-SM port (~17 B/clk).  Exchange mechanisms tried: cp.async.bulk by a sender thread (~3000 cycles per
+// cost of ~475 cycles: a part needs 384 tensor-pipe cycles (16 recurrent MMAs x 8 + 16 input MMAs x 16), 6 KB out + 6 KB in over
+// the SM-to-SM port (~17 B/clk: 360-720 cycles) and ~320 issue slots per SM sub-partition.  n = 8 is all the accumulator columns
+// TMEM has left, so half of the step is unhidden latency.  Exchange mechanisms tried: cp.async.bulk by a sender thread (~3000 cycles per
 // copy through the TMA unit), st.async from the pointwise warps (they stall on the port), and an exchange through the output
 // planes in L2 (TMA store + multicast TMA load: two ~1-2 us TMA round trips on the per-step chain; that variant showed
 // intermittent launch failures -- in hindsight probably the x_full race described at bar_x_full, which any delay of the x tiles
